@@ -1,0 +1,133 @@
+"""Deterministic synthetic inputs for tests and bench.
+
+There is no dataset or checkpoint on the GPU box, so the workload is: smooth
+(band-limited) random 32-channel stereo features at the KITTI shape, the real
+KITTI demo-sample geometry (numbers below were read once from the reference's
+``demo/data/kitti/kitti_000008_infos.pkl``: ``P2`` and
+``inv(prev_cam2global) @ cur_cam2global`` as ``VideoPipeline`` derives it,
+mmdet3d/datasets/pipelines/loading.py:530-537), and random weights keyed by the
+reference ``state_dict`` names.  Everything is generated from NumPy's legacy
+MT19937 ``RandomState`` so every process regenerates identical tensors.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# KITTI sample 000008, camera 2 projection padded to 4x4 (calib['P2'])
+KITTI_P2 = np.array(
+    [[721.5377, 0.0, 609.5593, 44.85728],
+     [0.0, 721.5377, 172.854, 0.2163791],
+     [0.0, 0.0, 1.0, 0.002745884],
+     [0.0, 0.0, 0.0, 1.0]], dtype=np.float64)
+
+# cur -> prev camera transforms for the three previous sweeps of the demo sample
+KITTI_CUR2PREV = np.array([
+    [[0.999302046, -0.001022011, 0.037342192, 0.048377033],
+     [0.000957212, 0.99999813, 0.00173758, 0.015017807],
+     [-0.037344459, -0.001701675, 0.999300674, 0.321288688],
+     [0.0, 0.0, 0.0, 1.0]],
+    [[0.99658589, -0.004466793, 0.082434821, 0.122045509],
+     [0.004160789, 0.999984333, 0.003887874, 0.034121847],
+     [-0.082450365, -0.003532619, 0.996588961, 0.662983686],
+     [0.0, 0.0, 0.0, 1.0]],
+    [[0.991866141, -0.009969419, 0.126890392, 0.213423159],
+     [0.009329447, 0.999941439, 0.005634116, 0.059576494],
+     [-0.126938255, -0.004405767, 0.991900695, 0.958234025],
+     [0.0, 0.0, 0.0, 1.0]]], dtype=np.float64)
+
+
+def depth_cfg_for(num_planes, downsample_factor=4):
+    """Model-level depth_cfg (configs/dfm/dfm_r34_1x8_kitti-3d-3class.py:4-9)
+    with num_bins chosen so that D = num_bins / downsample_factor planes."""
+    return dict(mode='UD', num_bins=num_planes * downsample_factor,
+                depth_min=2, depth_max=59.6,
+                downsample_factor=downsample_factor)
+
+
+def smooth_field(rng, c, h, w, cell=8):
+    """Band-limited random feature map [1, c, h, w] fp32 (N(0,1) on a 1/cell
+    lattice, bicubic-upsampled) -- bilinear taps of it are not noise-amplifying
+    ('sampling-coordinate reproducibility')."""
+    lh, lw = math.ceil(h / cell) + 3, math.ceil(w / cell) + 3
+    low = torch.from_numpy(
+        rng.standard_normal((1, c, lh, lw)).astype(np.float32))
+    up = F.interpolate(low, size=(lh * cell, lw * cell), mode='bicubic',
+                       align_corners=False)
+    return up[:, :, cell:cell + h, cell:cell + w].contiguous()
+
+
+def make_img_meta(h, w, sweep=2, flip=False, crop_offset=(0, 0), scale=1.0,
+                  ori_shape=None):
+    """The img_meta keys DfMBackbone.forward reads (dfm_backbone.py:150-172)."""
+    if ori_shape is None:
+        ori_shape = (h, w, 3)
+    return dict(
+        ori_cam2img=KITTI_P2.astype(np.float32).tolist(),
+        cur2prevs=torch.from_numpy(
+            KITTI_CUR2PREV[sweep:sweep + 1].astype(np.float32)),
+        ori_shape=tuple(ori_shape),
+        pad_shape=(h, w, 3),
+        img_shape=(h, w, 3),
+        flip=flip,
+        crop_offset=list(crop_offset),
+        scale_factor=[scale, scale, scale, scale])
+
+
+def _kaiming(rng, shape, fan_in, gain=1.0):
+    std = gain * math.sqrt(2.0 / fan_in)
+    return (rng.standard_normal(shape) * std).astype(np.float32)
+
+
+def make_backbone_params(rng, num_planes, in_channels=32, cv=32):
+    """Random DfMBackbone parameters keyed by the reference state_dict names
+    (SURVEY.md section 8a 'State').  GroupNorm affine is randomised so gamma/beta
+    are exercised."""
+    p = {}
+
+    def gn(name, c):
+        p[name + '.weight'] = (0.5 + rng.random_sample(c)).astype(np.float32)
+        p[name + '.bias'] = (0.2 * rng.standard_normal(c)).astype(np.float32)
+
+    def convmod(name, cin, cout):
+        p[name + '.conv.weight'] = _kaiming(rng, (cout, cin, 3, 3, 3), cin * 27)
+        gn(name + '.gn', cout)
+
+    def hg(name, c):
+        for sub, ci, co, seq in (('conv1', c, 2 * c, True),
+                                 ('conv2', 2 * c, 2 * c, False),
+                                 ('conv3', 2 * c, 2 * c, True),
+                                 ('conv4', 2 * c, 2 * c, True)):
+            pre = f'{name}.{sub}.0' if seq else f'{name}.{sub}'
+            p[pre + '.0.weight'] = _kaiming(rng, (co, ci, 3, 3, 3), ci * 27)
+            gn(pre + '.1', co)
+        # ConvTranspose3d weight layout is (in, out, kd, kh, kw)
+        p[f'{name}.conv5.0.weight'] = _kaiming(
+            rng, (2 * c, 2 * c, 3, 3, 3), 2 * c * 27 / 8)
+        gn(f'{name}.conv5.1', 2 * c)
+        p[f'{name}.conv6.0.weight'] = _kaiming(
+            rng, (2 * c, c, 3, 3, 3), 2 * c * 27 / 8)
+        gn(f'{name}.conv6.1', c)
+
+    for sfx, cin in (('', 2 * in_channels), ('_mono', in_channels)):
+        convmod('dres0' + sfx, cin, cv)
+        convmod('dres1' + sfx, cv, cv)
+        tower = 'mono' if sfx else 'stereo'
+        hg(f'hg_{tower}.0', cv)
+        convmod(f'pred_{tower}.0.0', cv, cv)
+        p[f'pred_{tower}.0.1.weight'] = _kaiming(rng, (1, cv, 3, 3, 3), cv * 27)
+    p['aggregate_cost.weight'] = _kaiming(
+        rng, (num_planes, 2 * num_planes, 1, 1), 2 * num_planes, gain=0.7)
+    return {k: torch.from_numpy(v) for k, v in p.items()}
+
+
+def make_kitti_pair(seed, h, w, num_planes, c=32, sweep=2, flip=False,
+                    crop_offset=(0, 0), scale=1.0, ori_shape=None):
+    """One synthetic (cur, prev) stereo-feature pair + img_metas + weights."""
+    rng = np.random.RandomState(seed)
+    cur = smooth_field(rng, c, h, w)
+    prev = smooth_field(rng, c, h, w)
+    params = make_backbone_params(rng, num_planes, c, 32)
+    metas = [make_img_meta(h, w, sweep, flip, crop_offset, scale, ori_shape)]
+    return cur, prev, metas, params

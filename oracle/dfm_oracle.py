@@ -1,0 +1,419 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference DfM hot path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
+/ ``--impl reference`` legs may import this module, and only as the checker or
+as the timed CPU baseline.  The product (``depth_from_motion_b200``) never
+imports it and has no CPU fallback.
+
+What this is
+------------
+A function-by-function restatement, in plain fp32 PyTorch-CPU calls, of the path
+SURVEY.md section 8(a) lists, each function citing the reference file:line it
+follows (paths relative to the reference checkout, commit e2321189):
+
+    a1  build_dfm_cost      mmdet3d/models/backbones/dfm_backbone.py:217-314
+    a2  DfMBackbone.forward mmdet3d/models/backbones/dfm_backbone.py:143-214
+    a3  hourglass           mmdet3d/models/utils/conv_modules.py:73-149
+    a4  pred + gate         mmdet3d/models/backbones/dfm_backbone.py:118-141
+    a5  DepthHead.forward   mmdet3d/models/dense_heads/depth_head.py:190-212
+    a6  point_sample + MultiViewDfM.feature_transformation
+                            mmdet3d/models/fusion_layers/point_fusion.py:14-106
+                            mmdet3d/models/detectors/multiview_dfm.py:119-209
+    a7  DfMNeck / OutdoorImVoxelNeck / ResModule
+                            mmdet3d/models/necks/dfm_neck.py:10-122
+                            mmdet3d/models/necks/imvoxel_neck.py:8-117
+    a9  points_cam2img / points_img2cam
+                            mmdet3d/core/bbox/structures/utils.py:176-248
+
+Third-party arithmetic: every number on this path is produced by PyTorch ATen
+ops in the reference (README pins torch 1.9 + mmcv-full 1.6.0, the latter used
+for ConvModule *wiring* only).  The restatement therefore calls the same ATen
+ops on CPU (conv3d, conv_transpose3d, group_norm(eps=1e-5), batch_norm,
+grid_sample, interpolate(trilinear), softmax, inverse) in the same order with
+the same argument values; parameters are passed as a flat dict keyed by the
+reference ``state_dict`` names.
+
+Pinning
+------------------------------
+The reference's own tests hold golden vectors only for the geometry helpers
+(tests/test_utils/test_utils.py:186-193, tests/test_utils/test_box3d.py:1653-1680)
+and ``point_sample`` (tests/test_models/test_fusion/test_point_fusion.py:13-58);
+those are reproduced in tests/test_oracle_golden.py.  For build_dfm_cost /
+DfMBackbone / DepthHead / DfMNeck the reference has NO tests, so this
+restatement is pinned against outputs of the reference's own source files
+executed verbatim in the build container (oracle/ref_loader.py), committed as
+fixtures under tests/golden/ by tests/golden/make_golden.py.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+GN_EPS = 1e-5  # nn.GroupNorm default, conv_modules.py:42-43
+
+
+# ----------------------------------------------------------------------------
+# a9  geometry helpers
+# ----------------------------------------------------------------------------
+def points_cam2img(points_3d, proj_mat, with_depth=False):
+    """core/bbox/structures/utils.py:176-214."""
+    d1, d2 = proj_mat.shape[:2]
+    assert (d1, d2) in ((3, 3), (3, 4), (4, 4))
+    if d1 == 3:
+        expanded = torch.eye(4, dtype=proj_mat.dtype)
+        expanded[:d1, :d2] = proj_mat
+        proj_mat = expanded
+    ones = points_3d.new_ones(list(points_3d.shape[:-1]) + [1])
+    points_4 = torch.cat([points_3d, ones], dim=-1)
+    point_2d = points_4 @ proj_mat.T
+    res = point_2d[..., :2] / point_2d[..., 2:3]
+    if with_depth:
+        res = torch.cat([res, point_2d[..., 2:3]], dim=-1)
+    return res
+
+
+def points_img2cam(points, cam2img):
+    """core/bbox/structures/utils.py:217-248."""
+    assert cam2img.shape[0] <= 4 and cam2img.shape[1] <= 4
+    assert points.shape[1] == 3
+    xys = points[:, :2]
+    depths = points[:, 2].view(-1, 1)
+    unnormed_xys = torch.cat([xys * depths, depths], dim=1)
+    pad = torch.eye(4, dtype=xys.dtype)
+    pad[:cam2img.shape[0], :cam2img.shape[1]] = cam2img
+    inv_pad = torch.inverse(pad).transpose(0, 1)
+    n = unnormed_xys.shape[0]
+    homo = torch.cat([unnormed_xys, xys.new_ones((n, 1))], dim=1)
+    return torch.mm(homo, inv_pad)[:, :3]
+
+
+# ----------------------------------------------------------------------------
+# a1  plane-sweep volume
+# ----------------------------------------------------------------------------
+def build_dfm_cost(cur_feats, prev_feats, depths, feat_sample_factor,
+                   cost_sample_factor, cam2imgs, cur2prevs, img_shape,
+                   flip=False, img_crop_offset=(0, 0), img_scale_factor=1.0):
+    """dfm_backbone.py:217-314.  Returns [B, 2C, D, Ho, Wo]."""
+    crop = torch.tensor(img_crop_offset)
+    batch_size = cur_feats.shape[0]
+    h_in, w_in = cur_feats.shape[-2:]
+    num_depths = depths.shape[-1]
+    h_out = round(h_in / cost_sample_factor)
+    w_out = round(w_in / cost_sample_factor)
+    ws = torch.linspace(0, w_out - 1, w_out) * feat_sample_factor * \
+        cost_sample_factor                                        # :247-248
+    hs = torch.linspace(0, h_out - 1, h_out) * feat_sample_factor * \
+        cost_sample_factor                                        # :249-250
+    ds_3d, ys_3d, xs_3d = torch.meshgrid(depths, hs, ws, indexing='ij')
+    grid = torch.stack([xs_3d, ys_3d, ds_3d], dim=-1)            # :253
+    grid = grid[None].repeat(batch_size, 1, 1, 1, 1)
+    for idx in range(batch_size):                                 # :257-271
+        grid[..., :2] += crop
+        grid[..., :2] /= img_scale_factor
+        if flip:
+            org_h, org_w = img_shape
+            grid[..., 0] = org_w - grid[..., 0]
+        grid3d = points_img2cam(grid[idx].view(-1, 3), cam2imgs[idx][:3])
+        pad_ones = grid3d.new_ones(grid3d.shape[0], 1)
+        homo_grid3d = torch.cat([grid3d, pad_ones], dim=1)
+        cur_grid = points_cam2img(grid3d, cam2imgs[idx])[:, :2]
+        prev_grid3d = (homo_grid3d @ cur2prevs[idx].transpose(0, 1))[:, :3]
+        prev_grid = points_cam2img(prev_grid3d, cam2imgs[idx])[:, :2]
+    cur_grid = cur_grid.view(batch_size, 1, -1, 2)
+    prev_grid = prev_grid.view(batch_size, 1, -1, 2)
+    if flip:                                                      # :278-281
+        org_h, org_w = img_shape
+        cur_grid[..., 0] = org_w - cur_grid[..., 0]
+        prev_grid[..., 0] = org_w - prev_grid[..., 0]
+    cur_grid *= img_scale_factor
+    prev_grid *= img_scale_factor
+    cur_grid -= crop
+    prev_grid -= crop
+    cur_grid /= feat_sample_factor
+    prev_grid /= feat_sample_factor
+    cur_grid[..., 0] = cur_grid[..., 0] / (w_in - 1) * 2 - 1     # :291-294
+    cur_grid[..., 1] = cur_grid[..., 1] / (h_in - 1) * 2 - 1
+    prev_grid[..., 0] = prev_grid[..., 0] / (w_in - 1) * 2 - 1
+    prev_grid[..., 1] = prev_grid[..., 1] / (h_in - 1) * 2 - 1
+    cur_cost = F.grid_sample(cur_feats, cur_grid, mode='bilinear',
+                             padding_mode='zeros', align_corners=True)
+    cur_cost = cur_cost.view(batch_size, -1, num_depths, h_out, w_out)
+    prev_cost = F.grid_sample(prev_feats, prev_grid, mode='bilinear',
+                              padding_mode='zeros', align_corners=True)
+    prev_cost = prev_cost.view(batch_size, -1, num_depths, h_out, w_out)
+    return torch.cat([cur_cost, prev_cost], dim=1)                # :313
+
+
+# ----------------------------------------------------------------------------
+# a2-a4  3-D aggregation.  `q` is an optional operand-rounding hook used only by
+# the precision study in DESIGN.md (identity by default => exact restatement).
+# ----------------------------------------------------------------------------
+def _ident(x):
+    return x
+
+
+def _gn(x, p, prefix, groups=32):
+    return F.group_norm(x, groups, p[prefix + '.weight'], p[prefix + '.bias'],
+                        GN_EPS)
+
+
+def _conv_module(x, p, name, act=True, q=_ident):
+    """mmcv ConvModule(conv3d k3 s1 p1, bias=False) -> GN(32) -> [ReLU];
+    dfm_backbone.py:50-66, 118-127."""
+    y = F.conv3d(q(x), q(p[name + '.conv.weight']), None, 1, 1)
+    y = _gn(y, p, name + '.gn')
+    return F.relu(y) if act else y
+
+
+def hourglass(x, p, name, q=_ident):
+    """conv_modules.py:129-149 with presqu = postsqu = None (dfm_backbone.py:181)."""
+    def cb(t, sub, stride):  # convbn_3d, conv_modules.py:27-43
+        y = F.conv3d(q(t), q(p[f'{name}.{sub}.0.weight']), None, stride, 1)
+        return _gn(y, p, f'{name}.{sub}.1')
+
+    def cb_seq(t, sub, stride):  # nn.Sequential(convbn_3d, ReLU)
+        y = F.conv3d(q(t), q(p[f'{name}.{sub}.0.0.weight']), None, stride, 1)
+        return F.relu(_gn(y, p, f'{name}.{sub}.0.1'))
+
+    def deconv(t, sub):  # ConvTranspose3d k3 p1 op1 s2 + GN, conv_modules.py:104-127
+        y = F.conv_transpose3d(q(t), q(p[f'{name}.{sub}.0.weight']), None, 2,
+                               1, 1)
+        return _gn(y, p, f'{name}.{sub}.1')
+
+    out = cb_seq(x, 'conv1', 2)              # :131
+    pre = F.relu(cb(out, 'conv2', 1))        # :132-136
+    out = cb_seq(pre, 'conv3', 2)            # :138
+    out = cb_seq(out, 'conv4', 1)            # :139
+    post = F.relu(deconv(out, 'conv5') + pre)  # :145
+    out = deconv(post, 'conv6')              # :147
+    return out, pre, post
+
+
+def _tower(x, p, sfx, q=_ident):
+    """dfm_backbone.py:175-183 (stereo) / :189-197 (mono) with num_hg == 1."""
+    cost0 = _conv_module(x, p, 'dres0' + sfx, True, q)
+    cost0 = _conv_module(cost0, p, 'dres1' + sfx, False, q) + cost0
+    hg_name = ('hg_mono' if sfx else 'hg_stereo') + '.0'
+    res, _, _ = hourglass(cost0, p, hg_name, q)
+    return cost0 + res
+
+
+def _pred(x, p, name, q=_ident):
+    """build_depth_pred_module, dfm_backbone.py:118-128."""
+    y = _conv_module(x, p, name + '.0', True, q)
+    return F.conv3d(q(y), q(p[name + '.1.weight']), None, 1, 1)
+
+
+def mono_stereo_aggregate(stereo_cost, mono_cost, p, q=_ident):
+    """dfm_backbone.py:130-141."""
+    cost1 = _pred(stereo_cost, p, 'pred_stereo.0', q)
+    mono_cost1 = _pred(mono_cost, p, 'pred_mono.0', q)
+    cost = torch.cat((cost1, mono_cost1), dim=1).flatten(1, 2)
+    weight = F.conv2d(cost, p['aggregate_cost.weight']).unsqueeze(1).sigmoid()
+    return weight * cost1 + (1 - weight) * mono_cost1
+
+
+def aggregate_volume(cost_raw, p, in_channels=32, q=_ident):
+    """DfMBackbone.forward after build_dfm_cost, dfm_backbone.py:174-214."""
+    cur_cost = _tower(cost_raw, p, '', q)
+    cur_cost_mono = _tower(cost_raw[:, :in_channels], p, '_mono', q)
+    cost = mono_stereo_aggregate(cur_cost, cur_cost_mono, p, q)
+    return cost, cur_cost, cur_cost_mono
+
+
+def downsampled_depth(depth_cfg):
+    """DfM.prepare_depth, detectors/dfm.py:147-168 (plane centres, offset 0.5)."""
+    nb, ds = depth_cfg['num_bins'], depth_cfg['downsample_factor']
+    interval = (depth_cfg['depth_max'] - depth_cfg['depth_min']) / nb
+    d = torch.zeros(nb // ds, dtype=torch.float32)
+    for i in range(nb // ds):
+        d[i] = (i + 0.5) * ds * interval + depth_cfg['depth_min']
+    return d
+
+
+def depth_samples(depth_cfg):
+    """DfM.prepare_depth, detectors/dfm.py:169-172 (full-resolution bin centres)."""
+    nb = depth_cfg['num_bins']
+    interval = (depth_cfg['depth_max'] - depth_cfg['depth_min']) / nb
+    d = torch.zeros(nb, dtype=torch.float32)
+    for i in range(nb):
+        d[i] = (i + 0.5) * interval + depth_cfg['depth_min']
+    return d
+
+
+def dfm_backbone_forward(p, cur_feats, prev_feats, img_metas, depth_cfg,
+                         in_channels=32, cost_sample_factor=4,
+                         feat_sample_factor=1, q=_ident):
+    """DfMBackbone.forward, dfm_backbone.py:143-214."""
+    ori_cam2imgs = torch.as_tensor(
+        np.array([m['ori_cam2img'] for m in img_metas]), dtype=torch.float32)
+    cur2prevs = torch.stack([torch.as_tensor(np.asarray(m['cur2prevs']),
+                                             dtype=torch.float32)
+                             for m in img_metas])
+    cost_raw = build_dfm_cost(
+        cur_feats, prev_feats, downsampled_depth(depth_cfg),
+        feat_sample_factor, cost_sample_factor, ori_cam2imgs, cur2prevs[0],
+        img_metas[0]['ori_shape'][:2], img_metas[0].get('flip', False),
+        img_metas[0]['crop_offset'],
+        img_scale_factor=img_metas[0].get('scale_factor', [1.0])[0])
+    return aggregate_volume(cost_raw, p, in_channels, q)
+
+
+# ----------------------------------------------------------------------------
+# a5  DepthHead.forward (with_convs=False, the KITTI config)
+# ----------------------------------------------------------------------------
+def depth_head_forward(cost, samples, downsample_factor=4):
+    """depth_head.py:190-212: x4 trilinear (align_corners) -> softmax(D) ->
+    expectation over the full-resolution bin centres."""
+    vol = F.interpolate(cost, scale_factor=downsample_factor, mode='trilinear',
+                        align_corners=True)
+    sm = F.softmax(vol, dim=2)
+    preds = torch.sum(sm * samples[None, None, :, None, None], 2)
+    return vol, sm, preds
+
+
+# ----------------------------------------------------------------------------
+# a6  multi-view voxel lifting
+# ----------------------------------------------------------------------------
+def point_sample(img_features, points, proj_mat, img_scale_factor,
+                 img_crop_offset, img_flip, img_pad_shape, img_shape,
+                 aligned=True, valid_flag=False):
+    """point_fusion.py:14-106 with apply_3d_transformation == identity (no 3-D
+    augmentation keys in img_meta at test time, coord_transform.py:9-92)."""
+    if valid_flag:
+        proj = points_cam2img(points, proj_mat, with_depth=True)
+        pts_2d, depths = proj[..., :2], proj[..., 2]
+    else:
+        pts_2d = points_cam2img(points, proj_mat)
+    img_coors = pts_2d[:, 0:2] * img_scale_factor
+    img_coors = img_coors - img_crop_offset
+    coor_x, coor_y = torch.split(img_coors, 1, dim=1)
+    if img_flip:
+        ori_h, ori_w = img_shape
+        coor_x = ori_w - coor_x
+    h, w = img_pad_shape
+    norm_y = coor_y / h * 2 - 1
+    norm_x = coor_x / w * 2 - 1
+    grid = torch.cat([norm_x, norm_y], dim=1).unsqueeze(0).unsqueeze(0)
+    mode = 'bilinear' if aligned else 'nearest'
+    feats = F.grid_sample(img_features, grid, mode=mode, padding_mode='zeros',
+                          align_corners=True)
+    if valid_flag:
+        valid = (coor_x.squeeze() < w) & (coor_x.squeeze() > 0) & \
+            (coor_y.squeeze() < h) & (coor_y.squeeze() > 0) & (depths > 0)
+        vf = feats.squeeze().t().clone()
+        vf[~valid] = 0
+        return vf, valid
+    return feats.squeeze().t()
+
+
+def voxel_centers(n_voxels, point_cloud_range):
+    """AlignedAnchor3DRangeGenerator.grid_anchors -> [:, :3]
+    (core/anchor/anchor_3d_generator.py:225-341 as configured at
+    detectors/multiview_dfm.py:54-61,122-123): centres ordered z-major,
+    then y, then x fastest ... reshaped by the caller as [Nz, Ny, Nx]."""
+    nx, ny, nz = n_voxels
+    x0, y0, z0, x1, y1, z1 = point_cloud_range
+    vx, vy, vz = (x1 - x0) / nx, (y1 - y0) / ny, (z1 - z0) / nz
+    xs = torch.arange(nx, dtype=torch.float32) * vx + (x0 + vx / 2)
+    ys = torch.arange(ny, dtype=torch.float32) * vy + (y0 + vy / 2)
+    zs = torch.arange(nz, dtype=torch.float32) * vz + (z0 + vz / 2)
+    zz, yy, xx = torch.meshgrid(zs, ys, xs, indexing='ij')
+    return torch.stack([xx, yy, zz], dim=-1).reshape(-1, 3)
+
+
+def multiview_lift(feats, points, n_voxels, lidar2imgs, num_views, num_frames,
+                   img_scale_factor, img_crop_offset, img_flip, input_shape,
+                   img_shapes, temporal_aggregate='mean'):
+    """MultiViewDfM.feature_transformation, multiview_dfm.py:139-209, one sample,
+    valid_sample=True.  feats [T*Nv, C, H, W] -> [C(*T), Nx, Ny, Nz]."""
+    frame_volume, frame_valid = [], []
+    for f in range(num_frames):
+        vol, flags = [], []
+        for v in range(num_views):
+            s = f * num_views + v
+            vf, valid = point_sample(
+                feats[s][None], points, lidar2imgs[s], img_scale_factor,
+                img_crop_offset, img_flip, input_shape, img_shapes[s][:2],
+                aligned=False, valid_flag=True)
+            vol.append(vf)
+            flags.append(valid)
+        nums = torch.stack(flags, 0).sum(0)
+        volume = torch.stack(vol, 0).sum(0)
+        volume[~(nums > 0)] = 0
+        frame_volume.append(volume)
+        frame_valid.append(nums)
+    if temporal_aggregate == 'mean':
+        fv = torch.stack(frame_volume, 0).sum(0)
+        fn = torch.stack(frame_valid, 0).sum(0)
+        fv[~(fn > 0)] = 0
+        fv = fv / torch.clamp(fn[:, None], min=1)
+    else:  # 'concat'
+        fn = torch.stack(frame_valid, 1)
+        fv = torch.stack(frame_volume, 1)
+        fv[~(fn > 0)] = 0
+        fv = (fv / torch.clamp(fn[:, :, None], min=1)).flatten(1, 2)
+    return fv.reshape(list(n_voxels[::-1]) + [-1]).permute(3, 2, 1, 0)
+
+
+# ----------------------------------------------------------------------------
+# a7  BEV necks (eval mode: BatchNorm3d uses running statistics)
+# ----------------------------------------------------------------------------
+def _bn(x, p, prefix):
+    return F.batch_norm(x, p[prefix + '.running_mean'],
+                        p[prefix + '.running_var'], p[prefix + '.weight'],
+                        p[prefix + '.bias'], False, 0.0, 1e-5)
+
+
+def _res_module(x, p, name):
+    """imvoxel_neck.py:71-117: relu(x + BN(conv(relu(BN(conv x)))))."""
+    y = F.relu(_bn(F.conv3d(x, p[name + '.conv0.conv.weight'], None, 1, 1), p,
+                   name + '.conv0.bn'))
+    y = _bn(F.conv3d(y, p[name + '.conv1.conv.weight'], None, 1, 1), p,
+            name + '.conv1.bn')
+    return F.relu(x + y)
+
+
+def _neck_tower(x, p, name):
+    """imvoxel_neck.py:27-56 / dfm_neck.py:29-88 (one tower of six layers)."""
+    x = _res_module(x, p, f'{name}.0')
+    x = F.relu(_bn(F.conv3d(x, p[f'{name}.1.conv.weight'], None, (1, 1, 2), 1),
+                   p, f'{name}.1.bn'))
+    x = _res_module(x, p, f'{name}.2')
+    x = F.relu(_bn(F.conv3d(x, p[f'{name}.3.conv.weight'], None, (1, 1, 2), 1),
+                   p, f'{name}.3.bn'))
+    x = _res_module(x, p, f'{name}.4')
+    x = F.relu(_bn(F.conv3d(x, p[f'{name}.5.conv.weight'], None, 1, (1, 1, 0)),
+                   p, f'{name}.5.bn'))
+    return x
+
+
+def imvoxel_neck_forward(p, x):
+    """OutdoorImVoxelNeck.forward, imvoxel_neck.py:58-68."""
+    x = _neck_tower(x, p, 'model')
+    assert x.shape[-1] == 1
+    return [x[..., 0].transpose(-1, -2)]
+
+
+def dfm_neck_forward(p, x, mono_channels):
+    """DfMNeck.forward, dfm_neck.py:97-118."""
+    mono = _neck_tower(x[:, :mono_channels], p, 'mono_layers')
+    stereo = _neck_tower(x, p, 'stereo_layers')
+    assert mono.shape[-1] == 1 and stereo.shape[-1] == 1
+    mono = mono[..., 0].transpose(-1, -2)
+    stereo = stereo[..., 0].transpose(-1, -2)
+    w = F.conv2d(torch.cat([mono, stereo], 1),
+                 p['aggregate_layer.weight']).sigmoid()      # :114-116
+    return [w * mono + (1 - w) * stereo]                    # :117
+
+
+# ----------------------------------------------------------------------------
+# helpers shared by tests / bench (deterministic synthetic inputs, NumPy legacy
+# MT19937 so both sides of a fixture regenerate identical tensors)
+# ----------------------------------------------------------------------------
+def tf32_round(x):
+    """Round-to-nearest-even to 10 mantissa bits (precision study only)."""
+    xi = x.contiguous().view(torch.int32)
+    r = ((xi >> 13) & 1) + 0x0FFF
+    return ((xi + r) & ~0x1FFF).view(torch.float32)

@@ -1,0 +1,234 @@
+"""TEST INFRASTRUCTURE ONLY -- executes the reference's own hot-path sources verbatim.
+
+This loader exists so the restatement in ``oracle/dfm_oracle.py`` can be pinned
+against the *unmodified* reference and so golden vectors
+under ``tests/golden/`` can be generated from it (``tests/golden/make_golden.py``).
+It only works in the build container, where ``/root/reference`` is mounted; the
+GPU box has no ``/root/reference`` and nothing shipped there imports this file.
+
+``import mmdet3d`` is impossible here (mmcv / mmdet / mmseg are not installed;
+``mmdet3d/__init__.py:2-5`` version-asserts them).  The hot-path files need mmcv
+only for ``ConvModule`` / ``BaseModule`` / ``Registry`` wiring, so we install
+minimal stand-ins for those names in ``sys.modules`` and then exec these files
+straight from the read-only reference tree:
+
+    mmdet3d/core/utils/array_converter.py
+    mmdet3d/core/bbox/structures/utils.py      (points_cam2img / points_img2cam)
+    mmdet3d/models/utils/conv_modules.py       (convbn_3d, hourglass)
+    mmdet3d/models/backbones/dfm_backbone.py   (DfMBackbone, build_dfm_cost)
+    mmdet3d/models/dense_heads/depth_head.py   (DepthHead)
+    mmdet3d/models/necks/imvoxel_neck.py       (OutdoorImVoxelNeck, ResModule)
+    mmdet3d/models/necks/dfm_neck.py           (DfMNeck)
+
+No reference source is copied into this repository.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+REFERENCE_ROOT = os.environ.get('DFM_REFERENCE_ROOT', '/root/reference')
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'mmdet3d'))
+
+
+class _Registry:
+    """Stand-in for mmcv.utils.Registry: decorator + name->class table."""
+
+    def __init__(self, name):
+        self.name = name
+        self.module_dict = {}
+
+    def register_module(self, name=None, force=False, module=None):
+        def _reg(cls):
+            self.module_dict[name or cls.__name__] = cls
+            return cls
+
+        if module is not None:
+            return _reg(module)
+        return _reg
+
+    def get(self, key):
+        return self.module_dict.get(key)
+
+    def build(self, cfg):
+        cfg = dict(cfg)
+        return self.module_dict[cfg.pop('type')](**cfg)
+
+
+class _BaseModule(nn.Module):
+    """Stand-in for mmcv.runner.BaseModule (init_cfg plumbing only)."""
+
+    def __init__(self, init_cfg=None):
+        super().__init__()
+        self.init_cfg = init_cfg
+
+    def init_weights(self):
+        pass
+
+
+_NORMS = {
+    'GN': ('gn', lambda c, cfg: nn.GroupNorm(cfg['num_groups'], c)),
+    'BN3d': ('bn', lambda c, cfg: nn.BatchNorm3d(c)),
+    'BN': ('bn', lambda c, cfg: nn.BatchNorm2d(c)),
+}
+_CONVS = {'Conv3d': nn.Conv3d, 'Conv2d': nn.Conv2d, None: nn.Conv2d}
+
+
+class _ConvModule(nn.Module):
+    """Stand-in for mmcv.cnn.ConvModule with the wiring the hot path relies on:
+    conv(bias = no norm) -> norm (child named 'gn'/'bn') -> ReLU, order fixed."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1,
+                 padding=0, dilation=1, groups=1, bias='auto', conv_cfg=None,
+                 norm_cfg=None, act_cfg=dict(type='ReLU'), inplace=True,
+                 **kwargs):
+        super().__init__()
+        conv_type = None if conv_cfg is None else conv_cfg['type']
+        self.with_norm = norm_cfg is not None
+        self.with_activation = act_cfg is not None
+        if bias == 'auto':
+            bias = not self.with_norm
+        self.conv = _CONVS[conv_type](in_channels, out_channels, kernel_size,
+                                      stride=stride, padding=padding,
+                                      dilation=dilation, groups=groups,
+                                      bias=bias)
+        if self.with_norm:
+            self.norm_name, make = _NORMS[norm_cfg['type']]
+            self.add_module(self.norm_name, make(out_channels, norm_cfg))
+        if self.with_activation:
+            assert act_cfg['type'] == 'ReLU'
+            self.activate = nn.ReLU(inplace=inplace)
+
+    @property
+    def norm(self):
+        return getattr(self, self.norm_name) if self.with_norm else None
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.with_norm:
+            x = self.norm(x)
+        if self.with_activation:
+            x = self.activate(x)
+        return x
+
+    def init_weights(self):
+        pass
+
+
+def _pkg(name):
+    m = types.ModuleType(name)
+    m.__path__ = []
+    sys.modules[name] = m
+    return m
+
+
+def _exec(modname, relpath):
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    spec = importlib.util.spec_from_file_location(modname, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_LOADED = None
+
+
+def load_reference():
+    """Returns a namespace with the reference's own classes/functions."""
+    global _LOADED
+    if _LOADED is not None:
+        return _LOADED
+    if not reference_available():
+        raise RuntimeError(f'reference tree not found at {REFERENCE_ROOT}')
+    saved = {k: v for k, v in sys.modules.items()
+             if k.split('.')[0] in ('mmcv', 'mmdet', 'mmdet3d')}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        mmcv = _pkg('mmcv')
+        cnn = _pkg('mmcv.cnn')
+        cnn.ConvModule = _ConvModule
+        runner = _pkg('mmcv.runner')
+        runner.BaseModule = _BaseModule
+        runner.force_fp32 = lambda *a, **k: (lambda f: f)
+        runner.auto_fp16 = lambda *a, **k: (lambda f: f)
+        utils = _pkg('mmcv.utils')
+        utils.Registry = _Registry
+        mmcv.cnn, mmcv.runner, mmcv.utils = cnn, runner, utils
+
+        _pkg('mmdet')
+        mm = _pkg('mmdet.models')
+        mb = _pkg('mmdet.models.builder')
+        for n in ('BACKBONES', 'NECKS', 'HEADS', 'DETECTORS', 'LOSSES'):
+            setattr(mb, n, _Registry(n))
+        mm.builder = mb
+        mm.BACKBONES, mm.NECKS, mm.HEADS = mb.BACKBONES, mb.NECKS, mb.HEADS
+
+        _pkg('mmdet3d')
+        _pkg('mmdet3d.core')
+        _pkg('mmdet3d.core.utils')
+        _pkg('mmdet3d.core.bbox')
+        _pkg('mmdet3d.core.bbox.structures')
+        _pkg('mmdet3d.models')
+        _pkg('mmdet3d.models.utils')
+        _pkg('mmdet3d.models.backbones')
+        _pkg('mmdet3d.models.necks')
+        _pkg('mmdet3d.models.dense_heads')
+        b3 = _pkg('mmdet3d.models.builder')
+        b3.NECKS = _Registry('NECKS3D')
+        sys.modules['mmdet3d.models'].builder = b3
+
+        ac = _exec('mmdet3d.core.utils.array_converter',
+                   'mmdet3d/core/utils/array_converter.py')
+        sys.modules['mmdet3d.core.utils'].array_converter = ac.array_converter
+        sys.modules['mmdet3d.core.utils'].ArrayConverter = ac.ArrayConverter
+
+        # structures/utils.py imports `from mmdet3d.core.utils import array_converter`
+        su = _exec('mmdet3d.core.bbox.structures.utils',
+                   'mmdet3d/core/bbox/structures/utils.py')
+        for pkgname in ('mmdet3d.core.bbox', 'mmdet3d.core.bbox.structures'):
+            sys.modules[pkgname].points_cam2img = su.points_cam2img
+            sys.modules[pkgname].points_img2cam = su.points_img2cam
+
+        cm = _exec('mmdet3d.models.utils.conv_modules',
+                   'mmdet3d/models/utils/conv_modules.py')
+        sys.modules['mmdet3d.models.utils'].hourglass = cm.hourglass
+        sys.modules['mmdet3d.models.utils'].convbn_3d = cm.convbn_3d
+
+        bb = _exec('mmdet3d.models.backbones.dfm_backbone',
+                   'mmdet3d/models/backbones/dfm_backbone.py')
+        dh = _exec('mmdet3d.models.dense_heads.depth_head',
+                   'mmdet3d/models/dense_heads/depth_head.py')
+        iv = _exec('mmdet3d.models.necks.imvoxel_neck',
+                   'mmdet3d/models/necks/imvoxel_neck.py')
+        sys.modules['mmdet3d.models.necks'].imvoxel_neck = iv
+        dn = _exec('mmdet3d.models.necks.dfm_neck',
+                   'mmdet3d/models/necks/dfm_neck.py')
+
+        ns = types.SimpleNamespace(
+            points_cam2img=su.points_cam2img,
+            points_img2cam=su.points_img2cam,
+            hourglass=cm.hourglass,
+            convbn_3d=cm.convbn_3d,
+            DfMBackbone=bb.DfMBackbone,
+            build_dfm_cost=bb.build_dfm_cost,
+            DepthHead=dh.DepthHead,
+            OutdoorImVoxelNeck=iv.OutdoorImVoxelNeck,
+            ResModule=iv.ResModule,
+            DfMNeck=dn.DfMNeck,
+            ConvModule=_ConvModule,
+        )
+        _LOADED = ns
+        return ns
+    finally:
+        for k in [k for k in sys.modules
+                  if k.split('.')[0] in ('mmcv', 'mmdet', 'mmdet3d')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
