@@ -1,0 +1,133 @@
+"""ctypes binding of ``include/dfm_b200.h`` (the C-ABI shared library).
+
+The library is built in-tree by ``__graft_entry__.build()`` /
+``depth_from_motion_b200/build.py`` as ``depth_from_motion_b200/libdfm_b200.so``.
+There is no fallback: if the library is missing, or no sm_100 GPU is visible
+when a compute entry point is called, the caller gets a ``RuntimeError``.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_longlong,
+                    c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdfm_b200.so')
+
+DFM_OK = 0
+DFM_CONV_AUTO, DFM_CONV_SIMT, DFM_CONV_TC = 0, 1, 2
+DFM_OUT_COST, DFM_OUT_STEREO, DFM_OUT_MONO = 1, 2, 4
+
+# every symbol include/dfm_b200.h declares (tests/test_capi_symbols.py checks the
+# header against this list and against the built library)
+SYMBOLS = (
+    'dfm_last_error', 'dfm_version', 'dfm_device_info', 'dfm_launch_counters',
+    'dfm_backbone_create', 'dfm_backbone_destroy', 'dfm_backbone_set_param',
+    'dfm_backbone_set_depths', 'dfm_backbone_missing_params',
+    'dfm_backbone_workspace_bytes', 'dfm_backbone_forward',
+    'dfm_backbone_forward_host', 'dfm_backbone_cost_device',
+    'dfm_backbone_debug_tensor', 'dfm_op_build_cost_volume', 'dfm_op_conv3d',
+    'dfm_depth_head_forward', 'dfm_multiview_lift', 'dfm_neck_create',
+    'dfm_neck_destroy', 'dfm_neck_set_param', 'dfm_neck_missing_params',
+    'dfm_neck_forward',
+)
+
+
+class Geometry(ctypes.Structure):
+    """``dfm_geometry_t``."""
+    _fields_ = [('cam2img', c_double * 16), ('cur2prev', c_double * 16),
+                ('crop_x', c_double), ('crop_y', c_double),
+                ('scale', c_double), ('org_w', c_double), ('flip', c_int),
+                ('reserved', c_int)]
+
+
+class BackboneDesc(ctypes.Structure):
+    """``dfm_backbone_desc_t``."""
+    _fields_ = [('in_channels', c_int), ('cv_channels', c_int),
+                ('feat_h', c_int), ('feat_w', c_int), ('num_planes', c_int),
+                ('cost_sample_factor', c_int), ('feat_sample_factor', c_int),
+                ('conv_impl', c_int)]
+
+
+class LiftDesc(ctypes.Structure):
+    """``dfm_lift_desc_t``."""
+    _fields_ = [('num_frames', c_int), ('num_views', c_int),
+                ('channels', c_int), ('feat_h', c_int), ('feat_w', c_int),
+                ('n_voxels', c_int * 3), ('scale_x', c_float),
+                ('scale_y', c_float), ('crop_x', c_float), ('crop_y', c_float),
+                ('flip', c_int), ('input_h', c_int), ('input_w', c_int),
+                ('concat', c_int)]
+
+
+class NeckDesc(ctypes.Structure):
+    """``dfm_neck_desc_t``."""
+    _fields_ = [('in_channels', c_int), ('out_channels', c_int),
+                ('num_frames', c_int), ('nx', c_int), ('ny', c_int),
+                ('nz', c_int), ('conv_impl', c_int)]
+
+
+_lib = None
+
+
+def library_built():
+    return os.path.isfile(LIB_PATH)
+
+
+def lib():
+    """Loads the shared library once; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not library_built():
+        raise RuntimeError(
+            f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; '
+            'g.build()"` (nvcc, sm_100a). There is no CPU/PyTorch fallback.')
+    L = ctypes.CDLL(LIB_PATH)
+    fp, vp, ip = POINTER(c_float), c_void_p, POINTER(c_int)
+    L.dfm_last_error.restype = c_char_p
+    L.dfm_version.restype = c_int
+    L.dfm_device_info.argtypes = [ip, ip, ip, POINTER(c_longlong)]
+    L.dfm_launch_counters.argtypes = [POINTER(c_longlong), POINTER(c_longlong)]
+    L.dfm_backbone_create.argtypes = [POINTER(BackboneDesc), POINTER(vp)]
+    L.dfm_backbone_destroy.argtypes = [vp]
+    L.dfm_backbone_set_param.argtypes = [vp, c_char_p, vp, c_longlong]
+    L.dfm_backbone_set_depths.argtypes = [vp, vp, c_int]
+    L.dfm_backbone_missing_params.argtypes = [vp]
+    L.dfm_backbone_workspace_bytes.argtypes = [vp]
+    L.dfm_backbone_workspace_bytes.restype = c_longlong
+    L.dfm_backbone_forward.argtypes = [vp, vp, vp, POINTER(Geometry), vp, vp,
+                                       vp, vp]
+    L.dfm_backbone_forward_host.argtypes = [vp, vp, vp, POINTER(Geometry),
+                                            c_int, vp, vp, vp, vp]
+    L.dfm_backbone_cost_device.argtypes = [vp]
+    L.dfm_backbone_cost_device.restype = vp
+    L.dfm_backbone_debug_tensor.argtypes = [vp, c_char_p, vp, c_longlong, vp]
+    L.dfm_op_build_cost_volume.argtypes = [vp, vp, c_int, c_int, c_int, vp,
+                                           c_int, c_int, c_int,
+                                           POINTER(Geometry), vp, vp]
+    L.dfm_op_conv3d.argtypes = [vp, c_int, c_int, c_int, c_int, vp, c_int,
+                                POINTER(c_int), POINTER(c_int), c_int, c_int,
+                                vp, vp]
+    L.dfm_depth_head_forward.argtypes = [vp, vp, c_int, c_int, c_int, c_int,
+                                         vp, vp, vp, vp]
+    L.dfm_multiview_lift.argtypes = [POINTER(LiftDesc), vp, vp, vp, vp, vp, vp,
+                                     vp, vp]
+    L.dfm_neck_create.argtypes = [POINTER(NeckDesc), POINTER(vp)]
+    L.dfm_neck_destroy.argtypes = [vp]
+    L.dfm_neck_set_param.argtypes = [vp, c_char_p, vp, c_longlong]
+    L.dfm_neck_missing_params.argtypes = [vp]
+    L.dfm_neck_forward.argtypes = [vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    """Turns a DFM_ERR_* return code into a RuntimeError with the C message."""
+    if rc != DFM_OK:
+        msg = lib().dfm_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'{what} failed (code {rc}): {msg}')
+
+
+def launch_counters():
+    a, b = c_longlong(0), c_longlong(0)
+    lib().dfm_launch_counters(ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value

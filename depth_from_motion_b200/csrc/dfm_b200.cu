@@ -1,0 +1,854 @@
+// C-ABI implementation of include/dfm_b200.h: handles, weight repacking, and the
+// per-frame launch sequence of the DfM plane-sweep cost-volume path on one B200.
+#include "../../include/dfm_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "simt_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0}, g_tc_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                    \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+      return fail(DFM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__) +   \
+                                    " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+#define DFM_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != DFM_OK) return rc__; \
+  } while (0)
+
+#define LAUNCH_CHECK()                       \
+  do {                                       \
+    g_launches.fetch_add(1);                 \
+    CU_TRY(cudaGetLastError());              \
+  } while (0)
+
+struct DevBuf {
+  float* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    if (p && n >= count) return DFM_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    CU_TRY(cudaMalloc(&p, count * sizeof(float)));
+    n = count;
+    return DFM_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+size_t g_dummy = 0;
+
+struct Norm {  // GroupNorm (statistics computed per frame) or folded BatchNorm (static)
+  int C = 0;
+  DevBuf gamma, beta, scale, shift;
+  double* sums = nullptr;
+  int init(int c) {
+    C = c;
+    DFM_TRY(gamma.alloc(c));
+    DFM_TRY(beta.alloc(c));
+    DFM_TRY(scale.alloc(c));
+    DFM_TRY(shift.alloc(c));
+    CU_TRY(cudaMalloc(&sums, 2 * c * sizeof(double)));
+    return DFM_OK;
+  }
+  void release() {
+    gamma.release();
+    beta.release();
+    scale.release();
+    shift.release();
+    if (sums) cudaFree(sums);
+    sums = nullptr;
+  }
+};
+
+struct ConvW {
+  int Cin = 0, Cout = 0, transposed = 0;
+  DevBuf simt;          // [27][Cin][Cout] fp32
+  dfm::TcWeights tc;    // bf16 hi/lo images for the tensor-core kernel
+};
+
+// (Cout,Cin,3,3,3) or transposed (Cin,Cout,3,3,3)  ->  [tap][ci][co]
+std::vector<float> repack_simt(const float* w, int Cin, int Cout, int transposed) {
+  std::vector<float> o((size_t)27 * Cin * Cout);
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int t = 0; t < 27; ++t) {
+        const size_t src = transposed ? ((size_t)ci * Cout + co) * 27 + t
+                                      : ((size_t)co * Cin + ci) * 27 + t;
+        o[((size_t)t * Cin + ci) * Cout + co] = w[src];
+      }
+  return o;
+}
+
+int upload(DevBuf& b, const float* h, size_t n) {
+  DFM_TRY(b.alloc(n));
+  CU_TRY(cudaMemcpy(b.p, h, n * sizeof(float), cudaMemcpyHostToDevice));
+  return DFM_OK;
+}
+
+int set_conv(ConvW& cw, const float* h, long long numel, int Cin, int Cout, int transposed) {
+  if (numel != (long long)27 * Cin * Cout)
+    return fail(DFM_ERR_INVALID, "conv weight has wrong element count");
+  cw.Cin = Cin;
+  cw.Cout = Cout;
+  cw.transposed = transposed;
+  const std::vector<float> p = repack_simt(h, Cin, Cout, transposed);
+  DFM_TRY(upload(cw.simt, p.data(), p.size()));
+  if (dfm::tc_supported(Cin, Cout, transposed)) {
+    std::string err;
+    if (!cw.tc.build(p.data(), Cin, Cout, &err)) return fail(DFM_ERR_CUDA, err);
+  }
+  return DFM_OK;
+}
+
+dfm::Term term(const DevBuf& x, const Norm* nrm, int relu) {
+  dfm::Term t;
+  t.x = x.p;
+  t.scale = nrm ? nrm->scale.p : nullptr;
+  t.shift = nrm ? nrm->shift.p : nullptr;
+  t.relu = relu;
+  return t;
+}
+
+dfm::Src src1(dfm::Term a, int outer_relu = 0) {
+  dfm::Src s{};
+  s.t[0] = a;
+  s.n = 1;
+  s.outer_relu = outer_relu;
+  return s;
+}
+dfm::Src src2(dfm::Term a, dfm::Term b, int outer_relu = 0) {
+  dfm::Src s{};
+  s.t[0] = a;
+  s.t[1] = b;
+  s.n = 2;
+  s.outer_relu = outer_relu;
+  return s;
+}
+dfm::Src src3(dfm::Term a, dfm::Term b, dfm::Term c) {
+  dfm::Src s{};
+  s.t[0] = a;
+  s.t[1] = b;
+  s.t[2] = c;
+  s.n = 3;
+  s.outer_relu = 0;
+  return s;
+}
+
+dfm::ConvGeom geom_s(int Di, int Hi, int Wi, int Cin, int Cout, int sd, int sh, int sw, int pd,
+                     int ph, int pw) {
+  dfm::ConvGeom g{};
+  g.Di = Di; g.Hi = Hi; g.Wi = Wi; g.Cin = Cin; g.Cout = Cout;
+  g.sd = sd; g.sh = sh; g.sw = sw; g.pd = pd; g.ph = ph; g.pw = pw;
+  g.transposed = 0;
+  g.Do = (Di + 2 * pd - 3) / sd + 1;
+  g.Ho = (Hi + 2 * ph - 3) / sh + 1;
+  g.Wo = (Wi + 2 * pw - 3) / sw + 1;
+  return g;
+}
+dfm::ConvGeom geom_t(int Di, int Hi, int Wi, int Cin, int Cout) {
+  dfm::ConvGeom g{};
+  g.Di = Di; g.Hi = Hi; g.Wi = Wi; g.Cin = Cin; g.Cout = Cout;
+  g.sd = g.sh = g.sw = 2; g.pd = g.ph = g.pw = 1;
+  g.transposed = 1;
+  g.Do = 2 * Di; g.Ho = 2 * Hi; g.Wo = 2 * Wi;
+  return g;
+}
+
+template <int CIN, int COUT, class L>
+int launch_simt(const L& ld, const ConvW& w, float* out, const dfm::ConvGeom& g,
+                cudaStream_t st) {
+  const long long nout = (long long)g.Do * g.Ho * g.Wo;
+  const long long warps = (nout + 7) / 8;
+  const long long blocks = (warps + 7) / 8;
+  dfm::conv3d_simt_kernel<CIN, COUT, L><<<(unsigned)blocks, 256, 0, st>>>(ld, w.simt.p, out, g);
+  LAUNCH_CHECK();
+  return DFM_OK;
+}
+
+template <class L>
+int conv_simt_dispatch(const L& ld, const ConvW& w, float* out, const dfm::ConvGeom& g,
+                       cudaStream_t st) {
+#define CASE(ci, co) \
+  if (g.Cin == ci && g.Cout == co) return launch_simt<ci, co, L>(ld, w, out, g, st)
+  CASE(32, 32);
+  CASE(64, 32);
+  CASE(32, 64);
+  CASE(64, 64);
+  CASE(64, 128);
+  CASE(128, 128);
+  CASE(128, 256);
+  CASE(256, 256);
+#undef CASE
+  return fail(DFM_ERR_INVALID, "conv3d: unsupported (Cin, Cout) = (" + std::to_string(g.Cin) +
+                                   ", " + std::to_string(g.Cout) + ")");
+}
+
+// conv with a Src-transform input; picks the tensor-core kernel when allowed/available
+int run_conv(const dfm::Src& s, const ConvW& w, float* out, const dfm::ConvGeom& g, int impl,
+             cudaStream_t st) {
+  const bool tc_ok = w.tc.ready() && dfm::tc_geom_supported(g);
+  if (impl == DFM_CONV_TC && !tc_ok)
+    return fail(DFM_ERR_INVALID, "conv3d: no tensor-core kernel for this layer");
+  if (impl != DFM_CONV_SIMT && tc_ok) {
+    std::string err;
+    if (!dfm::tc_conv_src(s, w.tc, out, g, st, &err)) return fail(DFM_ERR_CUDA, err);
+    g_launches.fetch_add(1);
+    g_tc_launches.fetch_add(1);
+    return DFM_OK;
+  }
+  dfm::SrcLoader ld{s, g.Cin, g.Hi, g.Wi};
+  return conv_simt_dispatch(ld, w, out, g, st);
+}
+
+int run_conv_warp(const dfm::WarpLoader& ld, const ConvW& w, float* out, const dfm::ConvGeom& g,
+                  int impl, cudaStream_t st) {
+  const bool tc_ok = w.tc.ready() && dfm::tc_geom_supported(g);
+  if (impl == DFM_CONV_TC && !tc_ok)
+    return fail(DFM_ERR_INVALID, "conv3d(warp): no tensor-core kernel for this layer");
+  if (impl != DFM_CONV_SIMT && tc_ok) {
+    std::string err;
+    if (!dfm::tc_conv_warp(ld, w.tc, out, g, st, &err)) return fail(DFM_ERR_CUDA, err);
+    g_launches.fetch_add(1);
+    g_tc_launches.fetch_add(1);
+    return DFM_OK;
+  }
+  return conv_simt_dispatch(ld, w, out, g, st);
+}
+
+int run_gn(const float* raw, long long V, Norm& n, int groups, cudaStream_t st) {
+  CU_TRY(cudaMemsetAsync(n.sums, 0, 2 * n.C * sizeof(double), st));
+  const int blocks = (int)std::min<long long>(148 * 8, (V * n.C + 255) / 256);
+  if (n.C == 32)
+    dfm::channel_stats_kernel<32><<<blocks, 256, 0, st>>>(raw, V, n.sums);
+  else if (n.C == 64)
+    dfm::channel_stats_kernel<64><<<blocks, 256, 0, st>>>(raw, V, n.sums);
+  else
+    return fail(DFM_ERR_INVALID, "GroupNorm: unsupported channel count");
+  LAUNCH_CHECK();
+  dfm::gn_finalize_kernel<<<1, 64, 0, st>>>(n.sums, n.gamma.p, n.beta.p, n.C, groups, (double)V,
+                                           1e-5f, n.scale.p, n.shift.p);
+  LAUNCH_CHECK();
+  return DFM_OK;
+}
+
+int to_nhwc(const float* in, float* out, int C, long long HW, cudaStream_t st) {
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32), block(32, 8);
+  dfm::nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(in, out, C, HW);
+  LAUNCH_CHECK();
+  return DFM_OK;
+}
+int to_ncdhw(const float* in, float* out, int C, long long V, cudaStream_t st) {
+  dim3 grid((unsigned)((V + 31) / 32), (C + 31) / 32), block(32, 8);
+  dfm::cl_to_ncdhw_kernel<<<grid, block, 0, st>>>(in, out, C, V);
+  LAUNCH_CHECK();
+  return DFM_OK;
+}
+
+void mat4_mul(const double* a, const double* b, double* o) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double s = 0;
+      for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+      o[i * 4 + j] = s;
+    }
+}
+bool mat4_inv(const double* m, double* inv) {
+  double a[4][8];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      a[i][j] = m[i * 4 + j];
+      a[i][4 + j] = i == j ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 4; ++r)
+      if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+    if (std::fabs(a[piv][c]) < 1e-300) return false;
+    if (piv != c)
+      for (int j = 0; j < 8; ++j) std::swap(a[piv][j], a[c][j]);
+    const double d = a[c][c];
+    for (int j = 0; j < 8; ++j) a[c][j] /= d;
+    for (int r = 0; r < 4; ++r)
+      if (r != c) {
+        const double f = a[r][c];
+        for (int j = 0; j < 8; ++j) a[r][j] -= f * a[c][j];
+      }
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) inv[i * 4 + j] = a[i][4 + j];
+  return true;
+}
+
+// M = P4 * T * P4^-1 in fp64; the reference pads cam2img[:3] into an identity 4x4
+// (structures/utils.py:239-241) and re-homogenises with ones (dfm_backbone.py:267-271).
+int make_warp_geom(const dfm_geometry_t* gm, int Hf, int Wf, int csf, int fsf, dfm::WarpGeom* out) {
+  // unproject uses cam2img[:3] padded into an identity 4x4 (structures/utils.py:239-241);
+  // the 3-D points are re-homogenised with ones before cur2prev and again before the
+  // projection (dfm_backbone.py:267-271, structures/utils.py:206), i.e. the 4th row of
+  // cur2prev never contributes.
+  double P[16], Pi[16], T[16], tmp[16], M[16];
+  for (int i = 0; i < 16; ++i) P[i] = gm->cam2img[i];
+  P[12] = P[13] = P[14] = 0.0;
+  P[15] = 1.0;
+  for (int i = 0; i < 16; ++i) T[i] = gm->cur2prev[i];
+  T[12] = T[13] = T[14] = 0.0;
+  T[15] = 1.0;
+  if (!mat4_inv(P, Pi)) return fail(DFM_ERR_INVALID, "ori_cam2img is singular");
+  mat4_mul(T, Pi, tmp);
+  mat4_mul(P, tmp, M);
+  dfm::WarpGeom g{};
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) g.A[i * 3 + j] = (float)M[i * 4 + j];
+    g.t[i] = (float)M[i * 4 + 3];
+  }
+  g.scale = (float)gm->scale;
+  g.inv_scale = (float)(1.0 / gm->scale);
+  g.crop_x = (float)gm->crop_x;
+  g.crop_y = (float)gm->crop_y;
+  g.org_w = (float)gm->org_w;
+  g.lattice = (float)(fsf * csf);
+  g.inv_fsf = 1.f / (float)fsf;
+  g.step = csf;
+  g.flip = gm->flip;
+  g.Hf = Hf;
+  g.Wf = Wf;
+  *out = g;
+  return DFM_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+// backbone handle
+// =====================================================================================
+struct Tower {
+  ConvW dres0, dres1, c1, c2, c3, c4, c5, c6, p0;
+  DevBuf p1w;  // [27][32]
+  Norm g0, g1, gc1, gc2, gc3, gc4, gc5, gc6, gp0;
+  DevBuf raw0, raw1, b1, b2, b3, b4, b5, b6, cur, p0b, logit;
+};
+
+struct dfm_backbone {
+  dfm_backbone_desc_t d;
+  int D, Ho, Wo;
+  Tower st, mo;
+  DevBuf cur_nhwc, prev_nhwc, depths, wagg, cost, volume_dbg;
+  bool depths_set = false;
+  std::set<std::string> missing;
+  std::map<std::string, std::pair<const DevBuf*, int>> dbg;  // name -> (buffer, channels)
+};
+
+namespace {
+
+int tower_alloc(Tower& t, int D, int Ho, int Wo, int cv) {
+  const size_t V = (size_t)D * Ho * Wo, V2 = V / 8, V4 = V / 64;
+  DFM_TRY(t.raw0.alloc(V * cv));
+  DFM_TRY(t.raw1.alloc(V * cv));
+  DFM_TRY(t.b1.alloc(V2 * 2 * cv));
+  DFM_TRY(t.b2.alloc(V2 * 2 * cv));
+  DFM_TRY(t.b3.alloc(V4 * 2 * cv));
+  DFM_TRY(t.b4.alloc(V4 * 2 * cv));
+  DFM_TRY(t.b5.alloc(V2 * 2 * cv));
+  DFM_TRY(t.b6.alloc(V * cv));
+  DFM_TRY(t.cur.alloc(V * cv));
+  DFM_TRY(t.p0b.alloc(V * cv));
+  DFM_TRY(t.logit.alloc(V));
+  DFM_TRY(t.g0.init(cv));
+  DFM_TRY(t.g1.init(cv));
+  DFM_TRY(t.gc1.init(2 * cv));
+  DFM_TRY(t.gc2.init(2 * cv));
+  DFM_TRY(t.gc3.init(2 * cv));
+  DFM_TRY(t.gc4.init(2 * cv));
+  DFM_TRY(t.gc5.init(2 * cv));
+  DFM_TRY(t.gc6.init(cv));
+  DFM_TRY(t.gp0.init(cv));
+  return DFM_OK;
+}
+
+void tower_release(Tower& t) {
+  for (DevBuf* b : {&t.raw0, &t.raw1, &t.b1, &t.b2, &t.b3, &t.b4, &t.b5, &t.b6, &t.cur, &t.p0b,
+                    &t.logit, &t.p1w})
+    b->release();
+  for (Norm* n : {&t.g0, &t.g1, &t.gc1, &t.gc2, &t.gc3, &t.gc4, &t.gc5, &t.gc6, &t.gp0})
+    n->release();
+  for (ConvW* c : {&t.dres0, &t.dres1, &t.c1, &t.c2, &t.c3, &t.c4, &t.c5, &t.c6, &t.p0}) {
+    c->simt.release();
+    c->tc.release();
+  }
+}
+
+std::vector<std::string> tower_param_names(bool mono) {
+  const std::string sfx = mono ? "_mono" : "";
+  const std::string hg = mono ? "hg_mono.0" : "hg_stereo.0";
+  const std::string pr = mono ? "pred_mono.0" : "pred_stereo.0";
+  std::vector<std::string> v;
+  for (const char* m : {"dres0", "dres1"}) {
+    v.push_back(std::string(m) + sfx + ".conv.weight");
+    v.push_back(std::string(m) + sfx + ".gn.weight");
+    v.push_back(std::string(m) + sfx + ".gn.bias");
+  }
+  for (const char* c : {"conv1.0", "conv2", "conv3.0", "conv4.0", "conv5", "conv6"}) {
+    v.push_back(hg + "." + c + ".0.weight");
+    v.push_back(hg + "." + c + ".1.weight");
+    v.push_back(hg + "." + c + ".1.bias");
+  }
+  v.push_back(pr + ".0.conv.weight");
+  v.push_back(pr + ".0.gn.weight");
+  v.push_back(pr + ".0.gn.bias");
+  v.push_back(pr + ".1.weight");
+  return v;
+}
+
+bool ends_with(const std::string& s, const std::string& e) {
+  return s.size() >= e.size() && s.compare(s.size() - e.size(), e.size(), e) == 0;
+}
+
+int set_norm_param(Norm& n, const std::string& name, const float* h, long long numel) {
+  if (numel != n.C) return fail(DFM_ERR_INVALID, name + ": wrong element count");
+  DevBuf& dst = ends_with(name, ".weight") ? n.gamma : n.beta;
+  CU_TRY(cudaMemcpy(dst.p, h, numel * sizeof(float), cudaMemcpyHostToDevice));
+  return DFM_OK;
+}
+
+int tower_set_param(Tower& t, bool mono, int cin0, int cv, const std::string& name,
+                    const float* h, long long numel, bool* handled) {
+  const std::string sfx = mono ? "_mono" : "";
+  const std::string hg = mono ? "hg_mono.0" : "hg_stereo.0";
+  const std::string pr = mono ? "pred_mono.0" : "pred_stereo.0";
+  *handled = true;
+  if (name == "dres0" + sfx + ".conv.weight") return set_conv(t.dres0, h, numel, cin0, cv, 0);
+  if (name == "dres1" + sfx + ".conv.weight") return set_conv(t.dres1, h, numel, cv, cv, 0);
+  if (name == "dres0" + sfx + ".gn.weight" || name == "dres0" + sfx + ".gn.bias")
+    return set_norm_param(t.g0, name, h, numel);
+  if (name == "dres1" + sfx + ".gn.weight" || name == "dres1" + sfx + ".gn.bias")
+    return set_norm_param(t.g1, name, h, numel);
+  struct HG { const char* key; ConvW* w; Norm* n; int ci, co, tr; };
+  const HG hgs[] = {{"conv1.0", &t.c1, &t.gc1, cv, 2 * cv, 0},    {"conv2", &t.c2, &t.gc2, 2 * cv, 2 * cv, 0},
+                    {"conv3.0", &t.c3, &t.gc3, 2 * cv, 2 * cv, 0}, {"conv4.0", &t.c4, &t.gc4, 2 * cv, 2 * cv, 0},
+                    {"conv5", &t.c5, &t.gc5, 2 * cv, 2 * cv, 1},   {"conv6", &t.c6, &t.gc6, 2 * cv, cv, 1}};
+  for (const HG& e : hgs) {
+    const std::string base = hg + "." + e.key;
+    if (name == base + ".0.weight") return set_conv(*e.w, h, numel, e.ci, e.co, e.tr);
+    if (name == base + ".1.weight" || name == base + ".1.bias")
+      return set_norm_param(*e.n, name, h, numel);
+  }
+  if (name == pr + ".0.conv.weight") return set_conv(t.p0, h, numel, cv, cv, 0);
+  if (name == pr + ".0.gn.weight" || name == pr + ".0.gn.bias")
+    return set_norm_param(t.gp0, name, h, numel);
+  if (name == pr + ".1.weight") {
+    if (numel != 27LL * cv) return fail(DFM_ERR_INVALID, name + ": wrong element count");
+    std::vector<float> p((size_t)27 * cv);  // (1,cv,3,3,3) -> [tap][c]
+    for (int c = 0; c < cv; ++c)
+      for (int k = 0; k < 27; ++k) p[(size_t)k * cv + c] = h[(size_t)c * 27 + k];
+    return upload(t.p1w, p.data(), p.size());
+  }
+  *handled = false;
+  return DFM_OK;
+}
+
+// one tower of DfMBackbone.forward: dfm_backbone.py:175-183 / 189-197 + pred convs
+int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& wl,
+                  float* d_feat_out, cudaStream_t st) {
+  const int D = bb->D, Ho = bb->Ho, Wo = bb->Wo, cv = bb->d.cv_channels;
+  const int impl = bb->d.conv_impl;
+  const long long V = (long long)D * Ho * Wo;
+  const int cin0 = mono ? bb->d.in_channels : 2 * bb->d.in_channels;
+
+  // dres0 on the on-the-fly volume
+  dfm::ConvGeom g = geom_s(D, Ho, Wo, cin0, cv, 1, 1, 1, 1, 1, 1);
+  DFM_TRY(run_conv_warp(wl, t.dres0, t.raw0.p, g, impl, st));
+  DFM_TRY(run_gn(t.raw0.p, V, t.g0, 32, st));
+  // dres1 (GN, no act) on relu(gn(raw0))
+  g = geom_s(D, Ho, Wo, cv, cv, 1, 1, 1, 1, 1, 1);
+  DFM_TRY(run_conv(src1(term(t.raw0, &t.g0, 1)), t.dres1, t.raw1.p, g, impl, st));
+  DFM_TRY(run_gn(t.raw1.p, V, t.g1, 32, st));
+  // cost0 = gn1(raw1) + relu(gn0(raw0)) is never stored: consumers re-evaluate it
+  const dfm::Term T1 = term(t.raw1, &t.g1, 0), T0 = term(t.raw0, &t.g0, 1);
+  // hourglass (conv_modules.py:129-149)
+  g = geom_s(D, Ho, Wo, cv, 2 * cv, 2, 2, 2, 1, 1, 1);
+  DFM_TRY(run_conv(src2(T1, T0), t.c1, t.b1.p, g, impl, st));
+  const int D2 = g.Do, H2 = g.Ho, W2 = g.Wo;
+  const long long V2 = (long long)D2 * H2 * W2;
+  DFM_TRY(run_gn(t.b1.p, V2, t.gc1, 32, st));
+  g = geom_s(D2, H2, W2, 2 * cv, 2 * cv, 1, 1, 1, 1, 1, 1);
+  DFM_TRY(run_conv(src1(term(t.b1, &t.gc1, 1)), t.c2, t.b2.p, g, impl, st));
+  DFM_TRY(run_gn(t.b2.p, V2, t.gc2, 32, st));
+  g = geom_s(D2, H2, W2, 2 * cv, 2 * cv, 2, 2, 2, 1, 1, 1);
+  DFM_TRY(run_conv(src1(term(t.b2, &t.gc2, 1)), t.c3, t.b3.p, g, impl, st));
+  const int D4 = g.Do, H4 = g.Ho, W4 = g.Wo;
+  const long long V4 = (long long)D4 * H4 * W4;
+  DFM_TRY(run_gn(t.b3.p, V4, t.gc3, 32, st));
+  g = geom_s(D4, H4, W4, 2 * cv, 2 * cv, 1, 1, 1, 1, 1, 1);
+  DFM_TRY(run_conv(src1(term(t.b3, &t.gc3, 1)), t.c4, t.b4.p, g, impl, st));
+  DFM_TRY(run_gn(t.b4.p, V4, t.gc4, 32, st));
+  g = geom_t(D4, H4, W4, 2 * cv, 2 * cv);
+  DFM_TRY(run_conv(src1(term(t.b4, &t.gc4, 1)), t.c5, t.b5.p, g, impl, st));
+  DFM_TRY(run_gn(t.b5.p, V2, t.gc5, 32, st));
+  // post = relu(gn5(conv5) + pre),  pre = relu(gn2(conv2))
+  g = geom_t(D2, H2, W2, 2 * cv, cv);
+  DFM_TRY(run_conv(src2(term(t.b5, &t.gc5, 0), term(t.b2, &t.gc2, 1), 1), t.c6, t.b6.p, g, impl,
+                   st));
+  DFM_TRY(run_gn(t.b6.p, V, t.gc6, 32, st));
+  // cur_cost = cost0 + gn6(conv6): channels-last copy for the pred conv + NCDHW output
+  {
+    dim3 grid((unsigned)((V + 31) / 32), (cv + 31) / 32), block(32, 8);
+    dfm::materialize_kernel<<<grid, block, 0, st>>>(src3(T1, T0, term(t.b6, &t.gc6, 0)), cv, V,
+                                                    t.cur.p, d_feat_out);
+    LAUNCH_CHECK();
+  }
+  // depth prediction module (dfm_backbone.py:118-128)
+  g = geom_s(D, Ho, Wo, cv, cv, 1, 1, 1, 1, 1, 1);
+  DFM_TRY(run_conv(src1(term(t.cur, nullptr, 0)), t.p0, t.p0b.p, g, impl, st));
+  DFM_TRY(run_gn(t.p0b.p, V, t.gp0, 32, st));
+  {
+    const long long threads = V * 8;
+    dfm::conv3d_c32_to_1_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+        src1(term(t.p0b, &t.gp0, 1)), t.p1w.p, t.logit.p, D, Ho, Wo);
+    LAUNCH_CHECK();
+  }
+  return DFM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dfm_last_error(void) { return g_err.c_str(); }
+int dfm_version(void) { return 100; }
+
+int dfm_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* l2_bytes) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(DFM_ERR_NOGPU, "no CUDA device visible");
+  }
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  CU_TRY(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (l2_bytes) *l2_bytes = p.l2CacheSize;
+  return DFM_OK;
+}
+
+int dfm_launch_counters(long long* launches, long long* tc_launches) {
+  if (launches) *launches = g_launches.load();
+  if (tc_launches) *tc_launches = g_tc_launches.load();
+  return DFM_OK;
+}
+
+int dfm_backbone_create(const dfm_backbone_desc_t* desc, dfm_backbone_t** out) {
+  if (!desc || !out) return fail(DFM_ERR_INVALID, "null argument");
+  if (desc->in_channels != 32 || desc->cv_channels != 32)
+    return fail(DFM_ERR_INVALID, "only in_channels == cv_channels == 32 is implemented");
+  const int csf = desc->cost_sample_factor, fsf = desc->feat_sample_factor;
+  if (csf < 1 || fsf < 1) return fail(DFM_ERR_INVALID, "sample factors must be >= 1");
+  const int Ho = (int)std::lround((double)desc->feat_h / csf);
+  const int Wo = (int)std::lround((double)desc->feat_w / csf);
+  const int D = desc->num_planes;
+  if (D % 4 || Ho % 4 || Wo % 4 || D < 4 || Ho < 4 || Wo < 4)
+    return fail(DFM_ERR_INVALID,
+                "D, H/4 and W/4 must be positive multiples of 4 (the reference hourglass "
+                "adds conv5 output to conv2 output, conv_modules.py:145)");
+  if ((Ho - 1) * csf > desc->feat_h - 1 || (Wo - 1) * csf > desc->feat_w - 1)
+    return fail(DFM_ERR_INVALID, "feature size not compatible with cost_sample_factor");
+  int sm = 0, maj = 0, mnr = 0;
+  DFM_TRY(dfm_device_info(&sm, &maj, &mnr, nullptr));
+  if (maj != 10) return fail(DFM_ERR_NOGPU, "this library is built for sm_100a only");
+  dfm_backbone* bb = new dfm_backbone();
+  bb->d = *desc;
+  bb->D = D;
+  bb->Ho = Ho;
+  bb->Wo = Wo;
+  const size_t HW = (size_t)desc->feat_h * desc->feat_w;
+  int rc = DFM_OK;
+  auto chk = [&](int r) { if (rc == DFM_OK) rc = r; };
+  chk(bb->cur_nhwc.alloc(HW * desc->in_channels));
+  chk(bb->prev_nhwc.alloc(HW * desc->in_channels));
+  chk(bb->depths.alloc(D));
+  chk(bb->wagg.alloc((size_t)D * 2 * D));
+  chk(bb->cost.alloc((size_t)D * Ho * Wo));
+  chk(tower_alloc(bb->st, D, Ho, Wo, desc->cv_channels));
+  chk(tower_alloc(bb->mo, D, Ho, Wo, desc->cv_channels));
+  if (rc != DFM_OK) {
+    dfm_backbone_destroy(bb);
+    return rc;
+  }
+  for (bool mono : {false, true})
+    for (const std::string& n : tower_param_names(mono)) bb->missing.insert(n);
+  bb->missing.insert("aggregate_cost.weight");
+  for (int m = 0; m < 2; ++m) {
+    Tower& t = m ? bb->mo : bb->st;
+    const std::string s = m ? "_mono" : "";
+    bb->dbg["raw0" + s] = {&t.raw0, 32};
+    bb->dbg["raw1" + s] = {&t.raw1, 32};
+    bb->dbg["c1" + s] = {&t.b1, 64};
+    bb->dbg["c2" + s] = {&t.b2, 64};
+    bb->dbg["c3" + s] = {&t.b3, 64};
+    bb->dbg["c4" + s] = {&t.b4, 64};
+    bb->dbg["c5" + s] = {&t.b5, 64};
+    bb->dbg["c6" + s] = {&t.b6, 32};
+    bb->dbg["cur" + s] = {&t.cur, 32};
+    bb->dbg["p0" + s] = {&t.p0b, 32};
+    bb->dbg["logit" + s] = {&t.logit, 1};
+  }
+  *out = bb;
+  return DFM_OK;
+}
+
+int dfm_backbone_destroy(dfm_backbone_t* bb) {
+  if (!bb) return DFM_OK;
+  tower_release(bb->st);
+  tower_release(bb->mo);
+  for (DevBuf* b : {&bb->cur_nhwc, &bb->prev_nhwc, &bb->depths, &bb->wagg, &bb->cost,
+                    &bb->volume_dbg})
+    b->release();
+  delete bb;
+  return DFM_OK;
+}
+
+int dfm_backbone_set_param(dfm_backbone_t* bb, const char* name, const float* h_data,
+                           long long numel) {
+  if (!bb || !name || !h_data) return fail(DFM_ERR_INVALID, "null argument");
+  const std::string n(name);
+  const int cv = bb->d.cv_channels, ci = bb->d.in_channels;
+  if (n == "aggregate_cost.weight") {
+    if (numel != (long long)bb->D * 2 * bb->D)
+      return fail(DFM_ERR_INVALID, "aggregate_cost.weight: expected (D, 2D, 1, 1)");
+    CU_TRY(cudaMemcpy(bb->wagg.p, h_data, numel * sizeof(float), cudaMemcpyHostToDevice));
+    bb->missing.erase(n);
+    return DFM_OK;
+  }
+  bool handled = false;
+  DFM_TRY(tower_set_param(bb->st, false, 2 * ci, cv, n, h_data, numel, &handled));
+  if (!handled) DFM_TRY(tower_set_param(bb->mo, true, ci, cv, n, h_data, numel, &handled));
+  if (!handled) return fail(DFM_ERR_INVALID, "unknown DfMBackbone parameter: " + n);
+  bb->missing.erase(n);
+  return DFM_OK;
+}
+
+int dfm_backbone_set_depths(dfm_backbone_t* bb, const float* h_depths, int n) {
+  if (!bb || !h_depths) return fail(DFM_ERR_INVALID, "null argument");
+  if (n != bb->D) return fail(DFM_ERR_INVALID, "downsampled_depth must have D entries");
+  CU_TRY(cudaMemcpy(bb->depths.p, h_depths, n * sizeof(float), cudaMemcpyHostToDevice));
+  bb->depths_set = true;
+  return DFM_OK;
+}
+
+int dfm_backbone_missing_params(const dfm_backbone_t* bb) {
+  return bb ? (int)bb->missing.size() : -1;
+}
+
+long long dfm_backbone_workspace_bytes(const dfm_backbone_t* bb) {
+  if (!bb) return 0;
+  long long n = 0;
+  for (const Tower* t : {&bb->st, &bb->mo})
+    for (const DevBuf* b : {&t->raw0, &t->raw1, &t->b1, &t->b2, &t->b3, &t->b4, &t->b5, &t->b6,
+                            &t->cur, &t->p0b, &t->logit})
+      n += (long long)b->n * 4;
+  n += (long long)(bb->cur_nhwc.n + bb->prev_nhwc.n + bb->cost.n) * 4;
+  return n;
+}
+
+int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_prev,
+                         const dfm_geometry_t* geom, float* d_cost, float* d_stereo,
+                         float* d_mono, void* stream) {
+  if (!bb || !d_cur || !d_prev || !geom) return fail(DFM_ERR_INVALID, "null argument");
+  if (!bb->missing.empty())
+    return fail(DFM_ERR_STATE, "missing parameter: " + *bb->missing.begin() + " (+" +
+                                   std::to_string(bb->missing.size() - 1) + " more)");
+  if (!bb->depths_set) return fail(DFM_ERR_STATE, "downsampled_depth not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = bb->d.in_channels;
+  const long long HW = (long long)bb->d.feat_h * bb->d.feat_w;
+  DFM_TRY(to_nhwc(d_cur, bb->cur_nhwc.p, C, HW, st));
+  DFM_TRY(to_nhwc(d_prev, bb->prev_nhwc.p, C, HW, st));
+  dfm::WarpLoader wl{};
+  wl.cur = bb->cur_nhwc.p;
+  wl.prev = bb->prev_nhwc.p;
+  wl.depths = bb->depths.p;
+  wl.C = C;
+  wl.first = 0;
+  DFM_TRY(make_warp_geom(geom, bb->d.feat_h, bb->d.feat_w, bb->d.cost_sample_factor,
+                         bb->d.feat_sample_factor, &wl.g));
+  DFM_TRY(tower_forward(bb, bb->st, false, wl, d_stereo, st));
+  DFM_TRY(tower_forward(bb, bb->mo, true, wl, d_mono, st));
+  // mono/stereo gate (dfm_backbone.py:130-141)
+  const int HWo = bb->Ho * bb->Wo;
+  const size_t smem = (size_t)2 * bb->D * 32 * sizeof(float);
+  if (smem > 48 * 1024)
+    CU_TRY(cudaFuncSetAttribute(dfm::gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  dfm::gate_kernel<<<(HWo + 31) / 32, 128, smem, st>>>(bb->st.logit.p, bb->mo.logit.p, bb->wagg.p,
+                                                       bb->cost.p, bb->D, HWo);
+  LAUNCH_CHECK();
+  if (d_cost)
+    CU_TRY(cudaMemcpyAsync(d_cost, bb->cost.p, (size_t)bb->D * HWo * sizeof(float),
+                           cudaMemcpyDeviceToDevice, st));
+  return DFM_OK;
+}
+
+const float* dfm_backbone_cost_device(const dfm_backbone_t* bb) { return bb ? bb->cost.p : nullptr; }
+
+int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const float* h_prev,
+                              const dfm_geometry_t* geom, int out_flags, float* h_cost,
+                              float* h_stereo, float* h_mono, void* stream) {
+  if (!bb || !h_cur || !h_prev) return fail(DFM_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nfeat = (size_t)bb->d.in_channels * bb->d.feat_h * bb->d.feat_w;
+  const size_t V = (size_t)bb->D * bb->Ho * bb->Wo;
+  // staging: NCHW inputs land in the (otherwise later-written) p0 buffers of the towers
+  float* d_cur = bb->st.p0b.p;
+  float* d_prev = bb->mo.p0b.p;
+  if (nfeat > bb->st.p0b.n) return fail(DFM_ERR_INVALID, "feature map larger than staging buffer");
+  CU_TRY(cudaMemcpyAsync(d_cur, h_cur, nfeat * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(d_prev, h_prev, nfeat * 4, cudaMemcpyHostToDevice, st));
+  float* d_st = nullptr;
+  float* d_mo = nullptr;
+  DevBuf tmp_s, tmp_m;
+  if ((out_flags & DFM_OUT_STEREO) && h_stereo) {
+    DFM_TRY(tmp_s.alloc(V * 32));
+    d_st = tmp_s.p;
+  }
+  if ((out_flags & DFM_OUT_MONO) && h_mono) {
+    DFM_TRY(tmp_m.alloc(V * 32));
+    d_mo = tmp_m.p;
+  }
+  int rc = dfm_backbone_forward(bb, d_cur, d_prev, geom, nullptr, d_st, d_mo, stream);
+  if (rc == DFM_OK && (out_flags & DFM_OUT_COST) && h_cost)
+    if (cudaMemcpyAsync(h_cost, bb->cost.p, V * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      rc = fail(DFM_ERR_CUDA, "D2H copy of cost failed");
+  if (rc == DFM_OK && d_st)
+    if (cudaMemcpyAsync(h_stereo, d_st, V * 32 * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      rc = fail(DFM_ERR_CUDA, "D2H copy of stereo feature failed");
+  if (rc == DFM_OK && d_mo)
+    if (cudaMemcpyAsync(h_mono, d_mo, V * 32 * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      rc = fail(DFM_ERR_CUDA, "D2H copy of mono feature failed");
+  cudaError_t e = cudaStreamSynchronize(st);
+  tmp_s.release();
+  tmp_m.release();
+  if (rc == DFM_OK && e != cudaSuccess) rc = fail(DFM_ERR_CUDA, cudaGetErrorString(e));
+  return rc;
+}
+
+int dfm_backbone_debug_tensor(dfm_backbone_t* bb, const char* name, float* d_out,
+                              long long numel, void* stream) {
+  if (!bb || !name || !d_out) return fail(DFM_ERR_INVALID, "null argument");
+  auto it = bb->dbg.find(name);
+  if (it == bb->dbg.end()) return fail(DFM_ERR_INVALID, std::string("unknown tensor ") + name);
+  const DevBuf* b = it->second.first;
+  if ((size_t)numel > b->n) return fail(DFM_ERR_INVALID, "numel larger than the tensor");
+  CU_TRY(cudaMemcpyAsync(d_out, b->p, numel * sizeof(float), cudaMemcpyDeviceToDevice,
+                         (cudaStream_t)stream));
+  return DFM_OK;
+}
+
+// -------------------------------------------------------------------------------------
+int dfm_op_build_cost_volume(const float* d_cur, const float* d_prev, int C, int H, int W,
+                             const float* h_depths, int D, int cost_sample_factor,
+                             int feat_sample_factor, const dfm_geometry_t* geom,
+                             float* d_volume, void* stream) {
+  if (!d_cur || !d_prev || !h_depths || !geom || !d_volume)
+    return fail(DFM_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = (int)std::lround((double)H / cost_sample_factor);
+  const int Wo = (int)std::lround((double)W / cost_sample_factor);
+  DevBuf cur, prev, dep;
+  const long long HW = (long long)H * W;
+  DFM_TRY(cur.alloc(HW * C));
+  DFM_TRY(prev.alloc(HW * C));
+  DFM_TRY(dep.alloc(D));
+  CU_TRY(cudaMemcpyAsync(dep.p, h_depths, D * sizeof(float), cudaMemcpyHostToDevice, st));
+  DFM_TRY(to_nhwc(d_cur, cur.p, C, HW, st));
+  DFM_TRY(to_nhwc(d_prev, prev.p, C, HW, st));
+  dfm::WarpLoader wl{};
+  wl.cur = cur.p;
+  wl.prev = prev.p;
+  wl.depths = dep.p;
+  wl.C = C;
+  wl.first = 0;
+  DFM_TRY(make_warp_geom(geom, H, W, cost_sample_factor, feat_sample_factor, &wl.g));
+  const long long V = (long long)D * Ho * Wo;
+  dim3 grid((unsigned)((V + 255) / 256), 2 * C);
+  dfm::cost_volume_kernel<<<grid, 256, 0, st>>>(wl, D, Ho, Wo, d_volume);
+  LAUNCH_CHECK();
+  CU_TRY(cudaStreamSynchronize(st));
+  cur.release();
+  prev.release();
+  dep.release();
+  return DFM_OK;
+}
+
+int dfm_op_conv3d(const float* d_x, int Cin, int Di, int Hi, int Wi, const float* h_w, int Cout,
+                  const int stride[3], const int pad[3], int transposed, int conv_impl,
+                  float* d_y, void* stream) {
+  if (!d_x || !h_w || !d_y || !stride || !pad) return fail(DFM_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvW w;
+  DFM_TRY(set_conv(w, h_w, (long long)27 * Cin * Cout, Cin, Cout, transposed));
+  dfm::ConvGeom g = transposed ? geom_t(Di, Hi, Wi, Cin, Cout)
+                               : geom_s(Di, Hi, Wi, Cin, Cout, stride[0], stride[1], stride[2],
+                                        pad[0], pad[1], pad[2]);
+  const long long Vi = (long long)Di * Hi * Wi, Vo = (long long)g.Do * g.Ho * g.Wo;
+  DevBuf xin, yout;
+  DFM_TRY(xin.alloc(Vi * Cin));
+  DFM_TRY(yout.alloc(Vo * Cout));
+  DFM_TRY(to_nhwc(d_x, xin.p, Cin, Vi, st));
+  int rc = run_conv(src1(term(xin, nullptr, 0)), w, yout.p, g, conv_impl, st);
+  if (rc == DFM_OK) rc = to_ncdhw(yout.p, d_y, Cout, Vo, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  xin.release();
+  yout.release();
+  w.simt.release();
+  w.tc.release();
+  if (rc == DFM_OK && e != cudaSuccess) rc = fail(DFM_ERR_CUDA, cudaGetErrorString(e));
+  return rc;
+}
+
+int dfm_depth_head_forward(const float* d_cost, const float* d_depth_samples, int D, int Ho,
+                           int Wo, int factor, float* d_volume, float* d_softmax,
+                           float* d_preds, void* stream) {
+  if (!d_cost || !d_depth_samples) return fail(DFM_ERR_INVALID, "null argument");
+  if (D < 1 || Ho < 1 || Wo < 1 || factor < 1) return fail(DFM_ERR_INVALID, "bad shape");
+  dim3 grid((Wo * factor + 127) / 128, Ho * factor);
+  dfm::depth_head_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+      d_cost, d_depth_samples, D, Ho, Wo, factor, d_volume, d_softmax, d_preds);
+  LAUNCH_CHECK();
+  return DFM_OK;
+}
+
+}  // extern "C"
+
+#include "neck_api.inc"

@@ -1,0 +1,508 @@
+// CUDA-core (fp32) kernels of the DfM path: layout changes, the generic 3x3x3
+// conv / transposed conv with fused input transform, GroupNorm statistics, the
+// residual "materialise" pass, the 32->1 logit conv, the mono/stereo gate, the
+// DepthHead, the cost-volume materialiser (parity op) and multi-view lifting.
+//
+// The fp32 conv here is the bring-up / cross-check implementation (DFM_CONV_SIMT);
+// the tensor-core implementation lives in conv_tc.cuh.
+#pragma once
+#include "common.cuh"
+
+namespace dfm {
+
+// ---------------------------------------------------------------------------------
+// NCHW [C][HW] -> NHWC [HW][C]   (stereo features arrive NCHW from the 2-D neck)
+// ---------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                    int C, long long HW) {
+  __shared__ float tile[32][33];
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const long long p = p0 + tx;
+    tile[j][tx] = (c < C && p < HW) ? in[(long long)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const long long p = p0 + j;
+    const int c = c0 + tx;
+    if (p < HW && c < C) out[p * C + c] = tile[tx][j];
+  }
+}
+
+// channels-last [V][C] -> NCDHW [C][V]
+__global__ void cl_to_ncdhw_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                   int C, long long V) {
+  __shared__ float tile[32][33];
+  const long long v0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int j = ty; j < 32; j += 8) {
+    const long long v = v0 + j;
+    const int c = c0 + tx;
+    tile[j][tx] = (v < V && c < C) ? in[v * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const long long v = v0 + tx;
+    if (c < C && v < V) out[(long long)c * V + v] = tile[tx][j];
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Input loaders for the SIMT conv: value of (input voxel, channel) after the fused
+// transform.  Bounds are checked by the caller.
+// ---------------------------------------------------------------------------------
+struct SrcLoader {
+  Src s;
+  int C, Hi, Wi;
+  __device__ __forceinline__ float load(int z, int y, int x, int c) const {
+    return load_src(s, ((long long)z * Hi + y) * Wi + x, C, c);
+  }
+};
+
+// First layer: the plane-sweep volume computed on the fly (never stored).
+// channels [0,C) = cur feature at the stride lattice, [C,2C) = prev feature warped
+// onto plane z.  `first` selects the channel window start (0, or C for prev only).
+struct WarpLoader {
+  const float* cur;   // NHWC
+  const float* prev;  // NHWC
+  const float* depths;
+  WarpGeom g;
+  int C;      // channels per frame
+  int first;  // channel offset into the 2C-channel volume
+  __device__ __forceinline__ float load(int z, int y, int x, int c) const {
+    c += first;
+    if (c < C)
+      return __ldg(cur + ((long long)(y * g.step) * g.Wf + x * g.step) * C + c);
+    c -= C;
+    float fx, fy;
+    warp_coord(g, x, y, __ldg(depths + z), fx, fy);
+    const Taps t = bilinear_taps(fx, fy, g.Hf, g.Wf);
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (t.w[i] != 0.f) v = fmaf(t.w[i], __ldg(prev + (long long)t.off[i] * C + c), v);
+    return v;
+  }
+};
+
+// ---------------------------------------------------------------------------------
+// Generic fp32 3x3x3 conv / stride-2 transposed conv, channels-last in and out.
+// One warp owns VOX consecutive output voxels; lane = output channel (mod 32).
+// Weights packed [27][Cin][Cout].
+// ---------------------------------------------------------------------------------
+template <int CIN, int COUT, class Loader>
+__global__ void __launch_bounds__(256)
+conv3d_simt_kernel(Loader ld, const float* __restrict__ wp, float* __restrict__ out,
+                   ConvGeom g) {
+  constexpr int VOX = 8;
+  constexpr int CI = (CIN + 31) / 32, CO = (COUT + 31) / 32;
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nout = (long long)g.Do * g.Ho * g.Wo;
+  const long long v0 = warp_id * VOX;
+  if (v0 >= nout) return;
+
+  int zo[VOX], yo[VOX], xo[VOX];
+  bool vv[VOX];
+#pragma unroll
+  for (int v = 0; v < VOX; ++v) {
+    const long long idx = v0 + v;
+    vv[v] = idx < nout;
+    const long long i2 = vv[v] ? idx : 0;
+    xo[v] = (int)(i2 % g.Wo);
+    yo[v] = (int)((i2 / g.Wo) % g.Ho);
+    zo[v] = (int)(i2 / ((long long)g.Wo * g.Ho));
+  }
+  float acc[CO][VOX];
+#pragma unroll
+  for (int j = 0; j < CO; ++j)
+#pragma unroll
+    for (int v = 0; v < VOX; ++v) acc[j][v] = 0.f;
+
+  for (int tap = 0; tap < 27; ++tap) {
+    const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
+    float xin[CI][VOX];
+    bool any = false;
+#pragma unroll
+    for (int v = 0; v < VOX; ++v) {
+      int zi, yi, xi;
+      bool ok = vv[v];
+      if (!g.transposed) {
+        zi = zo[v] * g.sd + kz - g.pd;
+        yi = yo[v] * g.sh + ky - g.ph;
+        xi = xo[v] * g.sw + kx - g.pw;
+      } else {  // o = 2 i - 1 + k  =>  i = (o + 1 - k) / 2 when even
+        const int tz = zo[v] + 1 - kz, ty = yo[v] + 1 - ky, tx = xo[v] + 1 - kx;
+        ok = ok && !((tz | ty | tx) & 1) && tz >= 0 && ty >= 0 && tx >= 0;
+        zi = tz >> 1;
+        yi = ty >> 1;
+        xi = tx >> 1;
+      }
+      ok = ok && zi >= 0 && zi < g.Di && yi >= 0 && yi < g.Hi && xi >= 0 && xi < g.Wi;
+      any |= ok;
+#pragma unroll
+      for (int j = 0; j < CI; ++j) {
+        const int c = lane + 32 * j;
+        xin[j][v] = (ok && c < CIN) ? ld.load(zi, yi, xi, c) : 0.f;
+      }
+    }
+    if (!any) continue;  // warp-uniform
+    const float* wt = wp + (long long)tap * CIN * COUT;
+#pragma unroll
+    for (int j = 0; j < CI; ++j) {
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) {
+        const int ci = j * 32 + l;
+        if (ci >= CIN) break;
+        float wv[CO];
+#pragma unroll
+        for (int jo = 0; jo < CO; ++jo) {
+          const int co = lane + 32 * jo;
+          wv[jo] = co < COUT ? __ldg(wt + (long long)ci * COUT + co) : 0.f;
+        }
+#pragma unroll
+        for (int v = 0; v < VOX; ++v) {
+          const float xv = __shfl_sync(0xffffffffu, xin[j][v], l);
+#pragma unroll
+          for (int jo = 0; jo < CO; ++jo) acc[jo][v] = fmaf(xv, wv[jo], acc[jo][v]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VOX; ++v) {
+    if (!vv[v]) continue;
+#pragma unroll
+    for (int jo = 0; jo < CO; ++jo) {
+      const int co = lane + 32 * jo;
+      if (co < COUT) out[(v0 + v) * COUT + co] = acc[jo][v];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Per-channel sum / sum-of-squares of a channels-last tensor (GroupNorm statistics,
+// nn.GroupNorm(32, C): conv_modules.py:42-43).  fp64 accumulation across blocks.
+// ---------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256)
+channel_stats_kernel(const float* __restrict__ x, long long V, double* __restrict__ sums) {
+  constexpr int ROWS = 256 / C;  // voxels per block-iteration
+  __shared__ double sh[2][256];
+  const int c = threadIdx.x % C, r = threadIdx.x / C;
+  double s = 0.0, ss = 0.0;
+  for (long long v = (long long)blockIdx.x * ROWS + r; v < V; v += (long long)gridDim.x * ROWS) {
+    const float a = x[v * C + c];
+    s += a;
+    ss += (double)a * a;
+  }
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = ss;
+  __syncthreads();
+  if (r == 0) {
+    for (int k = 1; k < ROWS; ++k) {
+      s += sh[0][k * C + c];
+      ss += sh[1][k * C + c];
+    }
+    atomicAdd(sums + 2 * c, s);
+    atomicAdd(sums + 2 * c + 1, ss);
+  }
+}
+
+// scale/shift of GroupNorm(groups, C) from per-channel sums over `count` voxels:
+// y = (x - mean_g) * rstd_g * gamma[c] + beta[c]  ==  x * scale[c] + shift[c]
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int C, int groups,
+                                   double count, float eps, float* __restrict__ scale,
+                                   float* __restrict__ shift) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  const int cpg = C / groups, g = c / cpg;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < cpg; ++k) {
+    s += sums[2 * (g * cpg + k)];
+    ss += sums[2 * (g * cpg + k) + 1];
+  }
+  const double n = count * cpg;
+  const double mean = s / n;
+  double var = ss / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const double sc = (double)gamma[c] * rstd;
+  scale[c] = (float)sc;
+  shift[c] = (float)((double)beta[c] - mean * sc);
+}
+
+// ---------------------------------------------------------------------------------
+// Materialise a (<= 3 term) sum as a channels-last tensor and/or NCDHW output:
+// cur_cost = cost0 + hourglass(cost0)  (dfm_backbone.py:176-183).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+materialize_kernel(Src s, int C, long long V, float* __restrict__ out_cl,
+                   float* __restrict__ out_ncdhw) {
+  __shared__ float tile[32][33];
+  const long long v0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const long long v = v0 + j;
+    const int c = c0 + tx;
+    float val = 0.f;
+    if (v < V && c < C) {
+      val = load_src(s, v, C, c);
+      if (out_cl) out_cl[v * C + c] = val;
+    }
+    tile[j][tx] = val;
+  }
+  if (!out_ncdhw) return;
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const long long v = v0 + tx;
+    if (c < C && v < V) out_ncdhw[(long long)c * V + v] = tile[tx][j];
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// 3x3x3 conv C -> 1 (nn.Conv3d(cv, 1, 3, 1, 1, bias=False), dfm_backbone.py:128).
+// 8 lanes per output voxel, each lane owns 4 of the 32 input channels.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv3d_c32_to_1_kernel(Src s, const float* __restrict__ w /*[27][32]*/, float* __restrict__ out,
+                       int D, int H, int W) {
+  __shared__ float ws[27 * 32];
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long vox = gid >> 3;
+  const int sub = (int)(gid & 7);
+  const long long V = (long long)D * H * W;
+  const bool live = vox < V;
+  const long long vq = live ? vox : 0;
+  const int x = (int)(vq % W), y = (int)((vq / W) % H), z = (int)(vq / ((long long)W * H));
+  float acc = 0.f;
+  for (int tap = 0; tap < 27; ++tap) {
+    const int zi = z + tap / 9 - 1, yi = y + (tap / 3) % 3 - 1, xi = x + tap % 3 - 1;
+    if (!live || zi < 0 || zi >= D || yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
+    const long long vi = ((long long)zi * H + yi) * W + xi;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = sub * 4 + k;
+      acc = fmaf(load_src(s, vi, 32, c), ws[tap * 32 + c], acc);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (live && sub == 0) out[vox] = acc;
+}
+
+// ---------------------------------------------------------------------------------
+// mono/stereo gate (dfm_backbone.py:135-141): cat the two [D] logit columns of a pixel,
+// 1x1 conv (2D -> D), sigmoid, blend.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+gate_kernel(const float* __restrict__ ls, const float* __restrict__ lm,
+            const float* __restrict__ wagg /*[D][2D]*/, float* __restrict__ cost, int D,
+            int HW) {
+  extern __shared__ float cat[];  // [2D][32]
+  const int p0 = blockIdx.x * 32;
+  const int px = threadIdx.x & 31, dg = threadIdx.x >> 5;
+  for (int j = dg; j < 2 * D; j += 4) {
+    const int p = p0 + px;
+    float v = 0.f;
+    if (p < HW) v = j < D ? ls[(long long)j * HW + p] : lm[(long long)(j - D) * HW + p];
+    cat[j * 32 + px] = v;
+  }
+  __syncthreads();
+  const int p = p0 + px;
+  for (int d = dg; d < D; d += 4) {
+    const float* wr = wagg + (long long)d * 2 * D;
+    float a = 0.f;
+    for (int j = 0; j < 2 * D; ++j) a = fmaf(__ldg(wr + j), cat[j * 32 + px], a);
+    const float wgt = 1.f / (1.f + __expf(-a));
+    const float s = cat[d * 32 + px], m = cat[(D + d) * 32 + px];
+    if (p < HW) cost[(long long)d * HW + p] = wgt * s + (1.f - wgt) * m;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// DepthHead.forward (depth_head.py:190-212): x`f` trilinear upsample with
+// align_corners=True, softmax over depth, expectation.  One thread per full-res pixel;
+// the (y,x)-interpolated logit column is rebuilt on the fly from the low-res logits
+// (L2-resident), the two optional 4-D outputs are written coalesced along x.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float dh_plane(const float* __restrict__ c, long long zoff,
+                                          const int o[4], const float w[4]) {
+  // same association as ATen upsample_trilinear3d:
+  // h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)
+  return w[2] * (w[0] * __ldg(c + zoff + o[0]) + w[1] * __ldg(c + zoff + o[1])) +
+         w[3] * (w[0] * __ldg(c + zoff + o[2]) + w[1] * __ldg(c + zoff + o[3]));
+}
+
+__global__ void __launch_bounds__(128)
+depth_head_kernel(const float* __restrict__ cost, const float* __restrict__ samples, int D,
+                  int Ho, int Wo, int f, float* __restrict__ vol, float* __restrict__ sm,
+                  float* __restrict__ preds) {
+  const int OW = Wo * f, OH = Ho * f, OD = D * f;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y;
+  if (X >= OW) return;
+  const float sx = OW > 1 ? (float)(Wo - 1) / (OW - 1) : 0.f;
+  const float sy = OH > 1 ? (float)(Ho - 1) / (OH - 1) : 0.f;
+  const float sz = OD > 1 ? (float)(D - 1) / (OD - 1) : 0.f;
+  const float fx = sx * X, fy = sy * Y;
+  const int x0 = (int)fx, y0 = (int)fy;
+  const int x1 = x0 + (x0 < Wo - 1 ? 1 : 0), y1 = y0 + (y0 < Ho - 1 ? 1 : 0);
+  const float lx1 = fx - x0, ly1 = fy - y0;
+  const int o[4] = {y0 * Wo + x0, y0 * Wo + x1, y1 * Wo + x0, y1 * Wo + x1};
+  const float w[4] = {1.f - lx1, lx1, 1.f - ly1, ly1};
+  const long long plane = (long long)Ho * Wo;
+  const long long opix = (long long)Y * OW + X, oplane = (long long)OH * OW;
+
+  // pass 1: running max / sum (online softmax) and, if requested, the raw volume
+  float m = -INFINITY, ssum = 0.f, esum = 0.f;
+  int zc = -1;
+  float b0 = 0.f, b1 = 0.f;
+  for (int k = 0; k < OD; ++k) {
+    const float fz = sz * k;
+    const int z0 = (int)fz;
+    const int z1 = z0 + (z0 < D - 1 ? 1 : 0);
+    const float lz1 = fz - z0;
+    if (z0 != zc) {
+      b0 = (z0 == zc + 1 && zc >= 0) ? b1 : dh_plane(cost, z0 * plane, o, w);
+      b1 = z1 == z0 ? b0 : dh_plane(cost, z1 * plane, o, w);
+      zc = z0;
+    }
+    const float v = (1.f - lz1) * b0 + lz1 * b1;
+    if (vol) vol[k * oplane + opix] = v;
+    const float mn = fmaxf(m, v);
+    const float corr = __expf(m - mn), e = __expf(v - mn);
+    ssum = ssum * corr + e;
+    esum = esum * corr + e * __ldg(samples + k);
+    m = mn;
+  }
+  if (preds) preds[opix] = esum / ssum;
+  if (!sm) return;
+  // pass 2: normalised probabilities
+  const float inv = 1.f / ssum;
+  zc = -1;
+  for (int k = 0; k < OD; ++k) {
+    const float fz = sz * k;
+    const int z0 = (int)fz;
+    const int z1 = z0 + (z0 < D - 1 ? 1 : 0);
+    const float lz1 = fz - z0;
+    if (z0 != zc) {
+      b0 = (z0 == zc + 1 && zc >= 0) ? b1 : dh_plane(cost, z0 * plane, o, w);
+      b1 = z1 == z0 ? b0 : dh_plane(cost, z1 * plane, o, w);
+      zc = z0;
+    }
+    const float v = (1.f - lz1) * b0 + lz1 * b1;
+    sm[k * oplane + opix] = __expf(v - m) * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// build_dfm_cost materialised as the reference's NCDHW volume (parity op only).
+// One thread per (voxel, channel); writes are coalesced along x.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cost_volume_kernel(WarpLoader ld, int D, int Ho, int Wo, float* __restrict__ out) {
+  const long long V = (long long)D * Ho * Wo;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (gid >= V) return;
+  const int x = (int)(gid % Wo), y = (int)((gid / Wo) % Ho), z = (int)(gid / ((long long)Wo * Ho));
+  out[(long long)c * V + gid] = ld.load(z, y, x, c);
+}
+
+// ---------------------------------------------------------------------------------
+// Multi-view lifting (multiview_dfm.py:139-209 + point_fusion.py:57-106, nearest tap,
+// valid mask, per-frame valid-count, temporal mean / concat).  One warp per voxel,
+// lane = channel (C = 64 -> 2 per lane).  feats are NHWC per (frame, view); output layout
+// [C_out][Nx][Ny][Nz] with C_out index f*C + c for 'concat'.
+// ---------------------------------------------------------------------------------
+struct LiftParams {
+  float proj[16][16];  // up to 16 (frame, view) matrices, row-major 4x4
+  int img_w[16];
+  int T, Nv, C, Hf, Wf;
+  int nx, ny, nz;
+  float scale_x, scale_y, crop_x, crop_y;
+  int flip, in_h, in_w, concat;
+};
+
+__device__ __forceinline__ int nearest_index(float coord, int size, float norm_size) {
+  // grid_sample(mode='nearest', align_corners=True): unnormalise then nearbyint
+  const float g = coord / norm_size * 2.f - 1.f;
+  const float ix = (g + 1.f) * 0.5f * (float)(size - 1);
+  return (int)nearbyintf(ix);
+}
+
+__global__ void __launch_bounds__(256)
+lift_kernel(LiftParams p, const float* __restrict__ feats, const float* __restrict__ xs,
+            const float* __restrict__ ys, const float* __restrict__ zs, float* __restrict__ out) {
+  const long long nvox = (long long)p.nx * p.ny * p.nz;
+  const long long vox = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (vox >= nvox) return;
+  // anchor order: z-major, then y, then x fastest (reshape [Nz,Ny,Nx] in the caller)
+  const int ix = (int)(vox % p.nx), iy = (int)((vox / p.nx) % p.ny),
+            iz = (int)(vox / ((long long)p.nx * p.ny));
+  const float px = __ldg(xs + ix), py = __ldg(ys + iy), pz = __ldg(zs + iz);
+  const int CL = (p.C + 31) / 32;
+  const long long fstride = (long long)p.C * p.Hf * p.Wf;
+  const long long ovox = ((long long)ix * p.ny + iy) * p.nz + iz;  // [Nx][Ny][Nz]
+  float tot[4] = {0.f, 0.f, 0.f, 0.f};
+  int tot_n = 0;
+  for (int f = 0; f < p.T; ++f) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int nvalid = 0;
+    for (int v = 0; v < p.Nv; ++v) {
+      const int s = f * p.Nv + v;
+      const float* m = p.proj[s];
+      const float a = m[0] * px + m[1] * py + m[2] * pz + m[3];
+      const float b = m[4] * px + m[5] * py + m[6] * pz + m[7];
+      const float d = m[8] * px + m[9] * py + m[10] * pz + m[11];
+      float cx = a / d * p.scale_x - p.crop_x;
+      const float cy = b / d * p.scale_y - p.crop_y;
+      if (p.flip) cx = (float)p.img_w[s] - cx;
+      const bool valid = cx < (float)p.in_w && cx > 0.f && cy < (float)p.in_h && cy > 0.f &&
+                         d > 0.f;
+      if (!valid) continue;
+      ++nvalid;
+      const int sx = nearest_index(cx, p.Wf, (float)p.in_w);
+      const int sy = nearest_index(cy, p.Hf, (float)p.in_h);
+      if (sx < 0 || sx >= p.Wf || sy < 0 || sy >= p.Hf) continue;
+      const float* fp = feats + s * fstride + ((long long)sy * p.Wf + sx) * p.C;  // NHWC
+      for (int j = 0; j < CL; ++j) {
+        const int c = lane + 32 * j;
+        if (c < p.C) acc[j] += __ldg(fp + c);
+      }
+    }
+    if (p.concat) {
+      const float inv = 1.f / (float)max(nvalid, 1);
+      for (int j = 0; j < CL; ++j) {
+        const int c = lane + 32 * j;
+        if (c < p.C)
+          out[((long long)(f * p.C + c)) * nvox + ovox] = nvalid > 0 ? acc[j] * inv : 0.f;
+      }
+    } else {
+      for (int j = 0; j < CL; ++j) tot[j] += nvalid > 0 ? acc[j] : 0.f;
+      tot_n += nvalid;
+    }
+  }
+  if (!p.concat) {
+    const float inv = 1.f / (float)max(tot_n, 1);
+    for (int j = 0; j < CL; ++j) {
+      const int c = lane + 32 * j;
+      if (c < p.C) out[(long long)c * nvox + ovox] = tot_n > 0 ? tot[j] * inv : 0.f;
+    }
+  }
+}
+
+}  // namespace dfm

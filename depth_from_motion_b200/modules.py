@@ -1,0 +1,543 @@
+"""Host-side mirror of the reference's plugin interface for the DfM hot path.
+
+Same class names, constructor arguments, ``state_dict`` keys, injected attributes
+and return values as the reference modules, but ``forward`` hands raw device
+pointers to the C-ABI library (``include/dfm_b200.h``) instead of running chains
+of PyTorch ops:
+
+    DfMBackbone          mmdet3d/models/backbones/dfm_backbone.py:14-214
+    DepthHead            mmdet3d/models/dense_heads/depth_head.py:13-212
+    DfMNeck              mmdet3d/models/necks/dfm_neck.py:10-122
+    OutdoorImVoxelNeck   mmdet3d/models/necks/imvoxel_neck.py:8-68
+    multiview_lift       mmdet3d/models/detectors/multiview_dfm.py:119-209
+
+The ``nn.Conv3d`` / ``nn.GroupNorm`` / ``nn.BatchNorm3d`` children below are
+parameter containers only (they give the exact reference ``state_dict`` layout so
+reference checkpoints load with ``strict=True``); their ``forward`` is never
+called.  There is no PyTorch fallback: without the built library or a B200 the
+modules raise.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import capi
+from .registry import BACKBONES, HEADS, NECKS
+
+_IMPL = {'auto': capi.DFM_CONV_AUTO, 'simt': capi.DFM_CONV_SIMT,
+         'tc': capi.DFM_CONV_TC}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_cuda(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(
+            f'{name} must be a CUDA tensor: depth_from_motion_b200 has no CPU path')
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'{name} must be float32, got {t.dtype}')
+
+
+class _ParamSync:
+    """Uploads parameters to a C handle whenever any of them changed."""
+
+    def __init__(self):
+        self._sig = None
+
+    def signature(self, module):
+        return tuple((k, v.data_ptr(), v._version)
+                     for k, v in module.state_dict(keep_vars=True).items())
+
+    def sync(self, module, set_fn):
+        sig = self.signature(module)
+        if sig == self._sig:
+            return
+        for k, v in module.state_dict().items():
+            if k.endswith('num_batches_tracked'):
+                continue
+            h = v.detach().to('cpu', torch.float32).contiguous()
+            set_fn(k.encode(), ctypes.c_void_p(h.data_ptr()), h.numel())
+        self._sig = sig
+
+
+class _ConvGN(nn.Module):
+    """Parameter layout of mmcv ConvModule(Conv3d, norm=GN): .conv / .gn."""
+
+    def __init__(self, cin, cout, groups):
+        super().__init__()
+        self.conv = nn.Conv3d(cin, cout, 3, 1, 1, bias=False)
+        self.gn = nn.GroupNorm(groups, cout)
+
+
+def _convbn3d(cin, cout, stride, groups):
+    return nn.Sequential(nn.Conv3d(cin, cout, 3, stride, 1, bias=False),
+                         nn.GroupNorm(groups, cout))
+
+
+class _Hourglass(nn.Module):
+    """Parameter layout of models/utils/conv_modules.py:73-127 (gn=True)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Sequential(_convbn3d(c, 2 * c, 2, 32), nn.ReLU(True))
+        self.conv2 = _convbn3d(2 * c, 2 * c, 1, 32)
+        self.conv3 = nn.Sequential(_convbn3d(2 * c, 2 * c, 2, 32), nn.ReLU(True))
+        self.conv4 = nn.Sequential(_convbn3d(2 * c, 2 * c, 1, 32), nn.ReLU(True))
+        self.conv5 = nn.Sequential(
+            nn.ConvTranspose3d(2 * c, 2 * c, 3, padding=1, output_padding=1,
+                               stride=2, bias=False), nn.GroupNorm(32, 2 * c))
+        self.conv6 = nn.Sequential(
+            nn.ConvTranspose3d(2 * c, c, 3, padding=1, output_padding=1,
+                               stride=2, bias=False), nn.GroupNorm(32, c))
+
+
+def geometry_from_meta(img_meta):
+    """img_meta -> dfm_geometry_t (the fields dfm_backbone.py:150-172 reads)."""
+    g = capi.Geometry()
+    cam = np.asarray(img_meta['ori_cam2img'], dtype=np.float64)
+    if cam.shape != (4, 4):
+        pad = np.eye(4)
+        pad[:cam.shape[0], :cam.shape[1]] = cam
+        cam = pad
+    c2p = img_meta['cur2prevs']
+    if isinstance(c2p, torch.Tensor):
+        c2p = c2p.detach().cpu().numpy()
+    c2p = np.asarray(c2p, dtype=np.float64).reshape(-1, 4, 4)[0]
+    g.cam2img[:] = cam.reshape(-1).tolist()
+    g.cur2prev[:] = c2p.reshape(-1).tolist()
+    crop = img_meta['crop_offset']
+    g.crop_x, g.crop_y = float(crop[0]), float(crop[1])
+    sf = img_meta.get('scale_factor', [1.0])
+    g.scale = float(sf[0]) if hasattr(sf, '__len__') else float(sf)
+    g.org_w = float(img_meta['ori_shape'][1])
+    g.flip = int(bool(img_meta.get('flip', False)))
+    return g
+
+
+@BACKBONES.register_module()
+class DfMBackbone(nn.Module):
+    """Drop-in for the reference ``DfMBackbone`` (dfm_backbone.py:14-214)."""
+
+    def __init__(self, in_channels, num_hg=1, cost_sample_factor=4,
+                 feat_sample_factor=1, cv_channels=32,
+                 depth_cfg=dict(mode='UD', num_bins=288, depth_min=2,
+                                depth_max=59.6, downsample_factor=4),
+                 norm_cfg=dict(type='GN', num_groups=32, requires_grad=True),
+                 conv_impl='auto'):
+        super().__init__()
+        assert num_hg == 1, 'Only support num_hg=1 for now.'  # dfm_backbone.py:212
+        assert norm_cfg.get('type') == 'GN', 'the reference hard-codes GN (:37)'
+        self.norm_cfg = norm_cfg
+        self.GN = True
+        self.cost_sample_factor = cost_sample_factor
+        self.feat_sample_factor = feat_sample_factor
+        self.num_hg = num_hg
+        self.cv_channels = cv_channels
+        self.in_channels = in_channels
+        self.depth_cfg = depth_cfg
+        self.conv_impl = conv_impl
+        groups = norm_cfg.get('num_groups', 32)
+        cv = cv_channels
+
+        def pred():
+            return nn.Sequential(_ConvGN(cv, cv, groups),
+                                 nn.Conv3d(cv, 1, 3, 1, 1, bias=False))
+
+        self.dres0 = _ConvGN(2 * in_channels, cv, groups)
+        self.dres1 = _ConvGN(cv, cv, groups)
+        self.hg_stereo = nn.ModuleList([_Hourglass(cv)])
+        self.pred_stereo = nn.ModuleList([pred()])
+        self.dres0_mono = _ConvGN(in_channels, cv, groups)
+        self.dres1_mono = _ConvGN(cv, cv, groups)
+        self.hg_mono = nn.ModuleList([_Hourglass(cv)])
+        self.pred_mono = nn.ModuleList([pred()])
+        self.num_planes = round(depth_cfg['num_bins'] //
+                                depth_cfg['downsample_factor'])
+        self.aggregate_cost = nn.Conv2d(2 * self.num_planes, self.num_planes, 1,
+                                        bias=False)
+        self._handle = None
+        self._handle_key = None
+        self._sync = _ParamSync()
+        self._depth_sig = None
+
+    def init_weights(self):
+        pass
+
+    # ------------------------------------------------------------------
+    def _default_depths(self):
+        """DfM.prepare_depth (detectors/dfm.py:160-168), used when the detector has
+        not injected ``downsampled_depth``."""
+        cfg = self.depth_cfg
+        ds = cfg['downsample_factor']
+        interval = (cfg['depth_max'] - cfg['depth_min']) / cfg['num_bins']
+        d = torch.zeros(cfg['num_bins'] // ds, dtype=torch.float32)
+        for i in range(cfg['num_bins'] // ds):
+            d[i] = (i + 0.5) * ds * interval + cfg['depth_min']
+        return d
+
+    def _ensure_handle(self, h, w):
+        L = capi.lib()
+        key = (h, w, self.conv_impl)
+        if self._handle is not None and self._handle_key == key:
+            return L
+        self.release()
+        desc = capi.BackboneDesc(self.in_channels, self.cv_channels, h, w,
+                                 self.num_planes, self.cost_sample_factor,
+                                 int(self.feat_sample_factor),
+                                 _IMPL[self.conv_impl])
+        hd = ctypes.c_void_p()
+        capi.check(L.dfm_backbone_create(ctypes.byref(desc), ctypes.byref(hd)),
+                   'dfm_backbone_create')
+        self._handle, self._handle_key = hd, key
+        self._sync = _ParamSync()
+        self._depth_sig = None
+        return L
+
+    def release(self):
+        if self._handle is not None:
+            capi.lib().dfm_backbone_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def _prepare(self, h, w):
+        L = self._ensure_handle(h, w)
+        self._sync.sync(
+            self, lambda k, p, n: capi.check(
+                L.dfm_backbone_set_param(self._handle, k, p, n),
+                f'dfm_backbone_set_param({k.decode()})'))
+        depths = getattr(self, 'downsampled_depth', None)
+        if depths is None:
+            depths = self._default_depths()
+        depths = depths.detach().to('cpu', torch.float32).contiguous()
+        sig = depths.numpy().tobytes()
+        if sig != self._depth_sig:
+            capi.check(L.dfm_backbone_set_depths(
+                self._handle, ctypes.c_void_p(depths.data_ptr()),
+                depths.numel()), 'dfm_backbone_set_depths')
+            self._depth_sig = sig
+        return L
+
+    def forward(self, cur_stereo_feats, prev_stereo_feats, img_metas,
+                cur_sem_feats=None):
+        _check_cuda(cur_stereo_feats, 'cur_stereo_feats')
+        _check_cuda(prev_stereo_feats, 'prev_stereo_feats')
+        b, c, h, w = cur_stereo_feats.shape
+        # the reference only supports batch size 1 (dfm_backbone.py:160)
+        assert b == 1, 'only support batch size 1 for now'
+        assert c == self.in_channels
+        assert prev_stereo_feats.shape == cur_stereo_feats.shape
+        L = self._prepare(h, w)
+        cur = cur_stereo_feats.contiguous()
+        prev = prev_stereo_feats.contiguous()
+        geom = geometry_from_meta(img_metas[0])
+        ho = round(h / self.cost_sample_factor)
+        wo = round(w / self.cost_sample_factor)
+        d = self.num_planes
+        dev = cur.device
+        cost = torch.empty((1, 1, d, ho, wo), device=dev, dtype=torch.float32)
+        stereo = torch.empty((1, self.cv_channels, d, ho, wo), device=dev,
+                             dtype=torch.float32)
+        mono = torch.empty_like(stereo)
+        capi.check(L.dfm_backbone_forward(
+            self._handle, _ptr(cur), _ptr(prev), ctypes.byref(geom), _ptr(cost),
+            _ptr(stereo), _ptr(mono), _stream()), 'dfm_backbone_forward')
+        return cost, stereo, mono
+
+    def debug_tensor(self, name, shape):
+        """Channels-last copy of an intermediate (tests only)."""
+        out = torch.empty(shape, device='cuda', dtype=torch.float32)
+        capi.check(capi.lib().dfm_backbone_debug_tensor(
+            self._handle, name.encode(), _ptr(out), out.numel(), _stream()),
+            'dfm_backbone_debug_tensor')
+        return out
+
+
+def build_dfm_cost(cur_feats, prev_feats, depths, feat_sample_factor,
+                   cost_sample_factor, cam2imgs, cur2prevs, img_shape,
+                   flip=False, img_crop_offset=(0, 0), img_scale_factor=1.0):
+    """Same signature as dfm_backbone.py:217-227; materialises the
+    [1, 2C, D, Ho, Wo] volume with the CUDA warp kernel (parity op)."""
+    _check_cuda(cur_feats, 'cur_feats')
+    b, c, h, w = cur_feats.shape
+    assert b == 1
+    meta = dict(ori_cam2img=torch.as_tensor(cam2imgs)[0].cpu().numpy(),
+                cur2prevs=torch.as_tensor(cur2prevs).cpu().numpy(),
+                crop_offset=img_crop_offset, scale_factor=[img_scale_factor],
+                ori_shape=(img_shape[0], img_shape[1], 3), flip=flip)
+    geom = geometry_from_meta(meta)
+    depths = depths.detach().to('cpu', torch.float32).contiguous()
+    d = depths.numel()
+    ho, wo = round(h / cost_sample_factor), round(w / cost_sample_factor)
+    out = torch.empty((1, 2 * c, d, ho, wo), device=cur_feats.device,
+                      dtype=torch.float32)
+    capi.check(capi.lib().dfm_op_build_cost_volume(
+        _ptr(cur_feats.contiguous()), _ptr(prev_feats.contiguous()), c, h, w,
+        ctypes.c_void_p(depths.data_ptr()), d, cost_sample_factor,
+        int(feat_sample_factor), ctypes.byref(geom), _ptr(out), _stream()),
+        'dfm_op_build_cost_volume')
+    return out
+
+
+def conv3d(x, weight, stride=(1, 1, 1), padding=(1, 1, 1), transposed=False,
+           impl='auto'):
+    """3x3x3 conv3d / conv_transpose3d(k3,s2,p1,op1) building block (NCDHW)."""
+    _check_cuda(x, 'x')
+    n, cin, di, hi, wi = x.shape
+    assert n == 1
+    cout = weight.shape[1] if transposed else weight.shape[0]
+    if transposed:
+        do, ho, wo = 2 * di, 2 * hi, 2 * wi
+    else:
+        do = (di + 2 * padding[0] - 3) // stride[0] + 1
+        ho = (hi + 2 * padding[1] - 3) // stride[1] + 1
+        wo = (wi + 2 * padding[2] - 3) // stride[2] + 1
+    y = torch.empty((1, cout, do, ho, wo), device=x.device, dtype=torch.float32)
+    wh = weight.detach().to('cpu', torch.float32).contiguous()
+    st = (ctypes.c_int * 3)(*stride)
+    pd = (ctypes.c_int * 3)(*padding)
+    capi.check(capi.lib().dfm_op_conv3d(
+        _ptr(x.contiguous()), cin, di, hi, wi, ctypes.c_void_p(wh.data_ptr()),
+        cout, st, pd, int(transposed), _IMPL[impl], _ptr(y), _stream()),
+        'dfm_op_conv3d')
+    return y
+
+
+@HEADS.register_module()
+class DepthHead(nn.Module):
+    """Drop-in for the reference ``DepthHead`` forward (depth_head.py:13-212).
+    ``loss`` is training-side PyTorch in the reference and is out of scope
+    (SURVEY.md section 8a row a5)."""
+
+    def __init__(self, depth_cfg, in_channels=32, with_convs=True,
+                 depth_loss=dict(type='ce', loss_weight=1.0),
+                 downsample_factor=4, num_views=5,
+                 norm_cfg=dict(type='GN', num_groups=32, requires_grad=True)):
+        super().__init__()
+        self.in_channels = in_channels
+        self.depth_cfg = depth_cfg
+        self.with_convs = with_convs
+        self.depth_loss = depth_loss
+        self.downsample_factor = downsample_factor
+        self.num_views = num_views
+        self.norm_cfg = norm_cfg
+        self.depth_loss_type = depth_loss['type']
+        self.loss_weight = depth_loss['loss_weight']
+        self.min_depth = depth_cfg['min_depth']
+        self.max_depth = depth_cfg['max_depth']
+        if self.with_convs:
+            self.conv_depth = nn.Conv3d(in_channels, 1, 3, 1, 1, bias=False)
+        self._samples_dev = None
+
+    def forward(self, stereo_features, return_volumes=True):
+        """Returns (depth_volumes, depth_volumes_softmax, depth_preds) like
+        depth_head.py:190-212.  ``return_volumes=False`` skips the two
+        [B,N,fD,fH,fW] outputs (returns None for them)."""
+        _check_cuda(stereo_features, 'stereo_features')
+        if self.with_convs:
+            raise NotImplementedError(
+                'DepthHead(with_convs=True) is not on the shipped DfM path '
+                '(configs/dfm/dfm_r34_1x8_kitti-3d-3class.py:126 uses False)')
+        b, n, d, h, w = stereo_features.shape
+        f = self.downsample_factor
+        samples = self.depth_samples
+        if (self._samples_dev is None or self._samples_dev[0] is not samples
+                or self._samples_dev[1].device != stereo_features.device):
+            self._samples_dev = (samples, samples.detach().to(
+                stereo_features.device, torch.float32).contiguous())
+        sdev = self._samples_dev[1]
+        assert sdev.numel() == f * d
+        x = stereo_features.contiguous()
+        dev = x.device
+        vol = sm = None
+        if return_volumes:
+            vol = torch.empty((b, n, f * d, f * h, f * w), device=dev)
+            sm = torch.empty_like(vol)
+        preds = torch.empty((b, n, f * h, f * w), device=dev)
+        L = capi.lib()
+        for i in range(b * n):
+            bi, ni = divmod(i, n)
+            capi.check(L.dfm_depth_head_forward(
+                _ptr(x[bi, ni]), _ptr(sdev), d, h, w, f,
+                _ptr(vol[bi, ni]) if vol is not None else None,
+                _ptr(sm[bi, ni]) if sm is not None else None,
+                _ptr(preds[bi, ni]), _stream()), 'dfm_depth_head_forward')
+        return vol, sm, preds
+
+
+class _NeckBase(nn.Module):
+    def _make_tower(self, c0, c1, c2, cout):
+        def cm(ci, co, **kw):
+            m = nn.Module()
+            m.conv = nn.Conv3d(ci, co, 3, bias=False, **kw)
+            m.bn = nn.BatchNorm3d(co)
+            return m
+
+        def res(c):
+            m = nn.Module()
+            m.conv0 = cm(c, c, padding=1)
+            m.conv1 = cm(c, c, padding=1)
+            return m
+
+        return nn.Sequential(res(c0), cm(c0, c1, stride=(1, 1, 2), padding=1),
+                             res(c1), cm(c1, c2, stride=(1, 1, 2), padding=1),
+                             res(c2), cm(c2, cout, padding=(1, 1, 0)))
+
+    def _run(self, x, num_frames, conv_impl):
+        _check_cuda(x, 'x')
+        assert not self.training, \
+            'the CUDA necks fold BatchNorm3d running statistics: call .eval()'
+        n, c, nx, ny, nz = x.shape
+        L = capi.lib()
+        key = (nx, ny, nz, conv_impl)
+        if getattr(self, '_handle', None) is None or self._handle_key != key:
+            self.release()
+            desc = capi.NeckDesc(self._c0, self._cout, num_frames, nx, ny, nz,
+                                 _IMPL[conv_impl])
+            hd = ctypes.c_void_p()
+            capi.check(L.dfm_neck_create(ctypes.byref(desc), ctypes.byref(hd)),
+                       'dfm_neck_create')
+            self._handle, self._handle_key = hd, key
+            self._sync = _ParamSync()
+        self._sync.sync(self, lambda k, p, m: capi.check(
+            L.dfm_neck_set_param(self._handle, k, p, m),
+            f'dfm_neck_set_param({k.decode()})'))
+        outs = []
+        for i in range(n):
+            bev = torch.empty((self._cout, ny, nx), device=x.device)
+            capi.check(L.dfm_neck_forward(self._handle, _ptr(x[i].contiguous()),
+                                          _ptr(bev), _stream()),
+                       'dfm_neck_forward')
+            outs.append(bev)
+        return [torch.stack(outs)]
+
+    def release(self):
+        if getattr(self, '_handle', None) is not None:
+            capi.lib().dfm_neck_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def init_weights(self):
+        pass
+
+
+@NECKS.register_module()
+class OutdoorImVoxelNeck(_NeckBase):
+    """Drop-in for imvoxel_neck.py:8-68 (eval mode)."""
+
+    def __init__(self, in_channels, out_channels, norm_cfg=dict(type='BN3d'),
+                 output_bev=True, conv_impl='auto'):
+        super().__init__()
+        assert norm_cfg.get('type') == 'BN3d' and output_bev
+        self.output_bev = output_bev
+        if not isinstance(in_channels, list):
+            in_channels = [in_channels, in_channels * 2, in_channels * 4]
+        self.in_channels = in_channels
+        self._c0, self._cout = in_channels[0], out_channels
+        assert in_channels[1] == 2 * in_channels[0]
+        assert in_channels[2] == 4 * in_channels[0]
+        self.conv_impl = conv_impl
+        self.model = self._make_tower(*in_channels, out_channels)
+        self._handle = None
+
+    def forward(self, x):
+        return self._run(x, 0, self.conv_impl)
+
+
+@NECKS.register_module()
+class DfMNeck(_NeckBase):
+    """Drop-in for dfm_neck.py:10-122 (eval mode)."""
+
+    def __init__(self, in_channels, out_channels, norm_cfg=dict(type='BN3d'),
+                 num_frames=2, conv_impl='auto'):
+        super().__init__()
+        assert norm_cfg.get('type') == 'BN3d'
+        if not isinstance(in_channels, list):
+            in_channels = [in_channels, in_channels * 2, in_channels * 4]
+        self.in_channels = in_channels
+        self.num_frames = num_frames
+        self._c0, self._cout = in_channels[0], out_channels
+        self.conv_impl = conv_impl
+        self.mono_layers = self._make_tower(*in_channels, out_channels)
+        self.stereo_layers = self._make_tower(in_channels[0] * num_frames,
+                                              in_channels[1], in_channels[2],
+                                              out_channels)
+        self.aggregate_layer = nn.Conv2d(2 * out_channels, 1, 1, bias=False)
+        self._handle = None
+
+    def forward(self, x):
+        assert x.shape[1] == self.in_channels[0] * self.num_frames
+        return self._run(x, self.num_frames, self.conv_impl)
+
+
+def aligned_voxel_centers(n_voxels, voxel_range):
+    """Per-axis voxel-centre coordinates exactly as
+    AlignedAnchor3DRangeGenerator.anchors_single_range computes them
+    (core/anchor/anchor_3d_generator.py:283-310, align_corner=False)."""
+    nx, ny, nz = n_voxels
+    r = torch.tensor(voxel_range, dtype=torch.float32)
+    out = []
+    for lo, hi, n in ((r[0], r[3], nx), (r[1], r[4], ny), (r[2], r[5], nz)):
+        c = torch.linspace(lo, hi, n + 1)
+        c = c + (c[1] - c[0]) / 2
+        out.append(c[:n].contiguous())
+    return out
+
+
+def multiview_lift(feats, img_meta, n_voxels, voxel_range, num_views,
+                   num_frames, temporal_aggregate='mean'):
+    """The lifting loop of MultiViewDfM.feature_transformation
+    (multiview_dfm.py:139-209, valid_sample=True) for one sample.
+    feats: [T*Nv, C, Hf, Wf] CUDA -> [C(*T), Nx, Ny, Nz]."""
+    _check_cuda(feats, 'feats')
+    s, c, hf, wf = feats.shape
+    assert s == num_views * num_frames
+    sf = img_meta.get('scale_factor', 1.0)
+    sf = np.atleast_1d(np.asarray(sf, dtype=np.float32))
+    sx, sy = (float(sf[0]), float(sf[1])) if sf.size >= 2 else (float(sf[0]),) * 2
+    crop = img_meta.get('img_crop_offset', (0.0, 0.0))
+    if np.isscalar(crop):
+        crop = (crop, crop)
+    desc = capi.LiftDesc()
+    desc.num_frames, desc.num_views, desc.channels = num_frames, num_views, c
+    desc.feat_h, desc.feat_w = hf, wf
+    desc.n_voxels[:] = list(n_voxels)
+    desc.scale_x, desc.scale_y = sx, sy
+    desc.crop_x, desc.crop_y = float(crop[0]), float(crop[1])
+    desc.flip = int(bool(img_meta.get('flip', False)))
+    desc.input_h, desc.input_w = img_meta['input_shape'][:2]
+    desc.concat = int(temporal_aggregate == 'concat')
+    # the reference converts ori_lidar2img to the feature dtype (fp32) first
+    proj = np.asarray(img_meta['ori_lidar2img'], dtype=np.float32)[:s]
+    proj = np.ascontiguousarray(proj.astype(np.float64).reshape(s, 16))
+    img_w = np.ascontiguousarray(
+        [int(img_meta['img_shape'][i][1]) for i in range(s)], dtype=np.int32)
+    xs, ys, zs = aligned_voxel_centers(n_voxels, voxel_range)
+    cout = c * num_frames if desc.concat else c
+    out = torch.empty((cout, n_voxels[0], n_voxels[1], n_voxels[2]),
+                      device=feats.device, dtype=torch.float32)
+    capi.check(capi.lib().dfm_multiview_lift(
+        ctypes.byref(desc), _ptr(feats.contiguous()),
+        proj.ctypes.data_as(ctypes.c_void_p),
+        img_w.ctypes.data_as(ctypes.c_void_p),
+        ctypes.c_void_p(xs.data_ptr()), ctypes.c_void_p(ys.data_ptr()),
+        ctypes.c_void_p(zs.data_ptr()), _ptr(out), _stream()),
+        'dfm_multiview_lift')
+    return out

@@ -131,3 +131,31 @@ def make_kitti_pair(seed, h, w, num_planes, c=32, sweep=2, flip=False,
     params = make_backbone_params(rng, num_planes, c, 32)
     metas = [make_img_meta(h, w, sweep, flip, crop_offset, scale, ori_shape)]
     return cur, prev, metas, params
+
+
+def make_neck_params(rng, template_state_dict):
+    """Random DfMNeck / OutdoorImVoxelNeck parameters shaped like (and ordered as)
+    ``template_state_dict``; BatchNorm running statistics are randomised so the
+    eval-mode affine is exercised."""
+    out = {}
+    for k, v in template_state_dict.items():
+        shape = tuple(v.shape)
+        if k.endswith('num_batches_tracked'):
+            out[k] = torch.zeros(shape, dtype=v.dtype)
+        elif k.endswith('conv.weight'):
+            fan_in = shape[1] * 27
+            out[k] = torch.from_numpy(_kaiming(rng, shape, fan_in))
+        elif k.endswith('aggregate_layer.weight'):
+            out[k] = torch.from_numpy(_kaiming(rng, shape, shape[1], gain=0.5))
+        elif k.endswith('bn.weight'):
+            out[k] = torch.from_numpy(
+                (0.5 + rng.random_sample(shape)).astype(np.float32))
+        elif k.endswith('bn.bias') or k.endswith('running_mean'):
+            out[k] = torch.from_numpy(
+                (0.2 * rng.standard_normal(shape)).astype(np.float32))
+        elif k.endswith('running_var'):
+            out[k] = torch.from_numpy(
+                (0.5 + rng.random_sample(shape)).astype(np.float32))
+        else:
+            raise KeyError(k)
+    return out

@@ -1,0 +1,200 @@
+/*
+ * dfm_b200.h -- C ABI of the B200-native DfM plane-sweep cost-volume path.
+ *
+ * The reference (Tai-Wang/Depth-from-Motion @ e2321189) has no FFI: its hot path
+ * is a chain of PyTorch calls inside mmcv-registry modules.  This header is the
+ * boundary a maintainer binds instead of those chains; every entry point names the
+ * reference interface it replaces (file:line relative to the reference checkout).
+ * INTEGRATION.md shows the ctypes binding used by depth_from_motion_b200/modules.py
+ * and the ten-line patch that makes the reference's own modules call it.
+ *
+ * Conventions
+ *   - plain C types only; all tensors are dense fp32, layouts stated per argument;
+ *   - pointers named d_* are CUDA device pointers, h_* are host pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     device entry points are asynchronous on that stream, *_host entry points
+ *     synchronise the stream before returning;
+ *   - every function returns DFM_OK (0) or a DFM_ERR_* code; dfm_last_error()
+ *     returns a thread-local human-readable message for the last failure;
+ *   - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef DFM_B200_H_
+#define DFM_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFM_OK 0
+#define DFM_ERR_INVALID 1 /* bad argument / unsupported shape           */
+#define DFM_ERR_CUDA 2    /* CUDA runtime error (message has the cause)  */
+#define DFM_ERR_STATE 3   /* missing parameter, depths not set, ...      */
+#define DFM_ERR_NOGPU 4   /* no sm_100 device visible                    */
+
+/* conv implementation selector (dfm_backbone_desc_t.conv_impl, dfm_op_conv3d) */
+#define DFM_CONV_AUTO 0 /* tcgen05 tensor-core kernels where implemented, SIMT else */
+#define DFM_CONV_SIMT 1 /* fp32 CUDA-core kernels everywhere (bring-up / cross-check) */
+#define DFM_CONV_TC 2   /* tcgen05 only; error if a layer has no tensor-core kernel   */
+
+/* output-selection flags for the *_host entry points */
+#define DFM_OUT_COST 1   /* gated depth logits           [1,1,D,Ho,Wo] */
+#define DFM_OUT_STEREO 2 /* stereo tower feature         [1,32,D,Ho,Wo] */
+#define DFM_OUT_MONO 4   /* mono tower feature           [1,32,D,Ho,Wo] */
+
+const char* dfm_last_error(void);
+int dfm_version(void);
+/* Reports the visible device; DFM_ERR_NOGPU when there is none. */
+int dfm_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* l2_bytes);
+
+/* ------------------------------------------------------------------------------------
+ * Geometry of one (cur, prev) pair -- the img_meta fields DfMBackbone.forward reads
+ * (mmdet3d/models/backbones/dfm_backbone.py:150-172).
+ * ---------------------------------------------------------------------------------- */
+typedef struct dfm_geometry {
+  double cam2img[16];  /* img_metas[0]['ori_cam2img'], 4x4 row-major              */
+  double cur2prev[16]; /* img_metas[0]['cur2prevs'][0], 4x4 row-major            */
+  double crop_x;       /* img_metas[0]['crop_offset'][0]                          */
+  double crop_y;       /* img_metas[0]['crop_offset'][1]                          */
+  double scale;        /* img_metas[0].get('scale_factor', [1.0])[0]             */
+  double org_w;        /* img_metas[0]['ori_shape'][1] (used only when flipped)   */
+  int flip;            /* img_metas[0].get('flip', False)                         */
+  int reserved;
+} dfm_geometry_t;
+
+/* ------------------------------------------------------------------------------------
+ * DfMBackbone  (replaces mmdet3d/models/backbones/dfm_backbone.py:14-314:
+ * build_dfm_cost + dres0/dres1 + hourglass + depth-pred convs + mono/stereo gate)
+ * ---------------------------------------------------------------------------------- */
+typedef struct dfm_backbone dfm_backbone_t;
+
+typedef struct dfm_backbone_desc {
+  int in_channels;        /* DfMBackbone(in_channels=32)                       */
+  int cv_channels;        /* cv_channels=32                                    */
+  int feat_h, feat_w;     /* stereo feature size H x W (full image resolution) */
+  int num_planes;         /* D = depth_cfg.num_bins / depth_cfg.downsample_factor */
+  int cost_sample_factor; /* 4                                                 */
+  int feat_sample_factor; /* 1                                                 */
+  int conv_impl;          /* DFM_CONV_*                                        */
+} dfm_backbone_desc_t;
+
+int dfm_backbone_create(const dfm_backbone_desc_t* desc, dfm_backbone_t** out);
+int dfm_backbone_destroy(dfm_backbone_t* bb);
+/* Upload one parameter by its reference state_dict key (SURVEY.md 8a "State"), e.g.
+ * "dres0.conv.weight" (32,64,3,3,3), "hg_stereo.0.conv5.0.weight" (ConvTranspose3d
+ * layout in x out), "aggregate_cost.weight" (D,2D,1,1).  h_data: host fp32, reference
+ * layout; the library repacks it for its kernels. */
+int dfm_backbone_set_param(dfm_backbone_t* bb, const char* name, const float* h_data,
+                           long long numel);
+/* The injected attribute DfMBackbone.downsampled_depth (detectors/dfm.py:160-168). */
+int dfm_backbone_set_depths(dfm_backbone_t* bb, const float* h_depths, int n);
+/* Number of parameters still missing (0 = ready). */
+int dfm_backbone_missing_params(const dfm_backbone_t* bb);
+long long dfm_backbone_workspace_bytes(const dfm_backbone_t* bb);
+/* DfMBackbone.forward (dfm_backbone.py:143-214), batch 1 (the reference supports
+ * only B=1, :160).  d_cur/d_prev: [1,C,H,W] NCHW.  Outputs (any may be NULL):
+ * d_cost [1,1,D,Ho,Wo], d_stereo / d_mono [1,32,D,Ho,Wo], NCDHW like the reference. */
+int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_prev,
+                         const dfm_geometry_t* geom, float* d_cost, float* d_stereo,
+                         float* d_mono, void* stream);
+/* Same call with HOST buffers: copies the two feature maps host->device, runs the
+ * path, copies the outputs selected by out_flags (DFM_OUT_*) device->host, and
+ * synchronises.  Buffers should be page-locked for full PCIe bandwidth. */
+int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const float* h_prev,
+                              const dfm_geometry_t* geom, int out_flags, float* h_cost,
+                              float* h_stereo, float* h_mono, void* stream);
+/* Device pointer of the gated logits kept inside the handle after a forward
+ * (lets a host-buffer caller chain dfm_depth_head_forward without a round trip). */
+const float* dfm_backbone_cost_device(const dfm_backbone_t* bb);
+/* Test hook: copies a named intermediate (channels-last [D][H][W][C]) to d_out.
+ * Names: "volume" (only kept when conv_impl == DFM_CONV_SIMT), "raw0", "raw1", "c1".."c6",
+ * "cur", "p0", "logit" with suffix "_mono" for the mono tower. */
+int dfm_backbone_debug_tensor(dfm_backbone_t* bb, const char* name, float* d_out,
+                              long long numel, void* stream);
+/* Counters since creation: kernels launched by this library / of which tcgen05. */
+int dfm_launch_counters(long long* launches, long long* tc_launches);
+
+/* ------------------------------------------------------------------------------------
+ * build_dfm_cost alone (dfm_backbone.py:217-314), materialising the reference's
+ * [1,2C,D,Ho,Wo] NCDHW volume.  Parity/bring-up op: the backbone never calls it (the
+ * volume is consumed on the fly), tests use it to pin rows a1/a9 against the oracle.
+ * h_depths: host [D].
+ * ---------------------------------------------------------------------------------- */
+int dfm_op_build_cost_volume(const float* d_cur, const float* d_prev, int C, int H, int W,
+                             const float* h_depths, int D, int cost_sample_factor,
+                             int feat_sample_factor, const dfm_geometry_t* geom,
+                             float* d_volume, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Generic 3x3x3 conv3d / conv_transpose3d building block (the cuDNN calls behind
+ * models/utils/conv_modules.py:27-43,104-127 and mmcv ConvModule(Conv3d)).
+ * d_x: NCDHW [1,Cin,Di,Hi,Wi]; h_w: host weight in the reference layout
+ * ((Cout,Cin,3,3,3) or, transposed, (Cin,Cout,3,3,3)); d_y: NCDHW output.
+ * stride/pad per (D,H,W); transposed uses stride 2, pad 1, output_padding 1.
+ * ---------------------------------------------------------------------------------- */
+int dfm_op_conv3d(const float* d_x, int Cin, int Di, int Hi, int Wi, const float* h_w,
+                  int Cout, const int stride[3], const int pad[3], int transposed,
+                  int conv_impl, float* d_y, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * DepthHead.forward with with_convs=False (mmdet3d/models/dense_heads/depth_head.py:
+ * 190-212): x`factor` trilinear upsample (align_corners) -> softmax over depth ->
+ * expectation over d_depth_samples [factor*D].  d_cost [1,1,D,Ho,Wo].
+ * d_volume / d_softmax [1,1,fD,fHo,fWo] and d_preds [1,1,fHo,fWo]; any may be NULL
+ * (skipping the two 4-D volumes is the fast path when only depth_preds is consumed).
+ * ---------------------------------------------------------------------------------- */
+int dfm_depth_head_forward(const float* d_cost, const float* d_depth_samples, int D, int Ho,
+                           int Wo, int factor, float* d_volume, float* d_softmax,
+                           float* d_preds, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * MultiViewDfM.feature_transformation lifting step (mmdet3d/models/detectors/
+ * multiview_dfm.py:119-209 calling fusion_layers/point_fusion.py:14-106 with
+ * aligned=False, valid_flag=True), one sample: nearest-tap gather of every voxel
+ * centre into every (frame, view), valid-count averaging, temporal 'mean' or 'concat'.
+ * d_feats [T*Nv, C, Hf, Wf]; h_lidar2img [T*Nv][16] row-major; the voxel-centre
+ * coordinates per axis are passed in (the caller computes them exactly as
+ * AlignedAnchor3DRangeGenerator does, core/anchor/anchor_3d_generator.py:283-310),
+ * points are ordered z-major, then y, then x (the generator's permute at :327).  d_volume: [C*(concat?T:1), Nx, Ny, Nz].
+ * ---------------------------------------------------------------------------------- */
+typedef struct dfm_lift_desc {
+  int num_frames, num_views, channels, feat_h, feat_w;
+  int n_voxels[3];            /* Nx, Ny, Nz                                  */
+  float scale_x, scale_y;     /* img_meta['scale_factor'][:2]                */
+  float crop_x, crop_y;       /* img_meta['img_crop_offset']                 */
+  int flip;
+  int input_h, input_w;       /* img_meta['input_shape']                     */
+  int concat;                 /* temporal_aggregate == 'concat'              */
+} dfm_lift_desc_t;
+int dfm_multiview_lift(const dfm_lift_desc_t* desc, const float* d_feats,
+                       const double* h_lidar2img, const int* h_img_w /* [T*Nv] img_shape w */,
+                       const float* h_xs /* [Nx] */, const float* h_ys /* [Ny] */,
+                       const float* h_zs /* [Nz] voxel-centre coordinates */,
+                       float* d_volume, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * DfMNeck / OutdoorImVoxelNeck, eval mode (mmdet3d/models/necks/dfm_neck.py:10-122,
+ * imvoxel_neck.py:8-117): BatchNorm3d folded into per-channel affine.
+ * ---------------------------------------------------------------------------------- */
+typedef struct dfm_neck dfm_neck_t;
+typedef struct dfm_neck_desc {
+  int in_channels;  /* per-frame channels (64)                               */
+  int out_channels; /* 256                                                   */
+  int num_frames;   /* DfMNeck: stereo tower sees in_channels*num_frames; 0 => OutdoorImVoxelNeck */
+  int nx, ny, nz;
+  int conv_impl;
+} dfm_neck_desc_t;
+int dfm_neck_create(const dfm_neck_desc_t* desc, dfm_neck_t** out);
+int dfm_neck_destroy(dfm_neck_t* neck);
+/* Reference state_dict keys: "mono_layers.0.conv0.conv.weight", "...bn.weight/bias/
+ * running_mean/running_var", "stereo_layers...", "aggregate_layer.weight"; for
+ * OutdoorImVoxelNeck the prefix is "model.". */
+int dfm_neck_set_param(dfm_neck_t* neck, const char* name, const float* h_data,
+                       long long numel);
+int dfm_neck_missing_params(const dfm_neck_t* neck);
+/* d_x [1, Cin_total, Nx, Ny, Nz] -> d_bev [1, out_channels, Ny, Nx]. */
+int dfm_neck_forward(dfm_neck_t* neck, const float* d_x, float* d_bev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFM_B200_H_ */

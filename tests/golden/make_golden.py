@@ -1,0 +1,95 @@
+"""Generates the golden fixtures in this directory from the UNMODIFIED reference
+sources (executed verbatim through oracle/ref_loader.py).  Runs only in the build
+container, where /root/reference is mounted:
+
+    python tests/golden/make_golden.py
+
+Inputs are regenerated from fixed NumPy seeds by depth_from_motion_b200.synthetic
+(and stored too, so a fixture is self-contained); outputs are what the
+reference's own DfMBackbone / DepthHead / DfMNeck / OutdoorImVoxelNeck /
+point_sample code returns on CPU in fp32.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from depth_from_motion_b200 import synthetic as syn  # noqa: E402
+from oracle import dfm_oracle as O  # noqa: E402
+from oracle.ref_loader import load_reference  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+KITTI_CASES = {
+    # name: (seed, H, W, D, flip, crop, scale, ori_shape)
+    'kitti_plain': (11, 32, 64, 8, False, (0, 0), 1.0, None),
+    'kitti_aug': (12, 32, 64, 8, True, (10, 40), 1.03, (375, 1242, 3)),
+}
+
+
+def kitti_case(ns, name, spec):
+    seed, h, w, d, flip, crop, scale, ori = spec
+    cur, prev, metas, params = syn.make_kitti_pair(
+        seed, h, w, d, flip=flip, crop_offset=crop, scale=scale, ori_shape=ori)
+    cfg = syn.depth_cfg_for(d)
+    m = ns.DfMBackbone(in_channels=32, depth_cfg=cfg).eval()
+    m.load_state_dict(params, strict=True)
+    m.downsampled_depth = O.downsampled_depth(cfg)
+    head = ns.DepthHead(
+        depth_cfg=dict(mode='UD', num_bins=cfg['num_bins'], min_depth=2,
+                       max_depth=59.6), with_convs=False, num_views=1,
+        depth_loss=dict(type='balanced_focal', loss_weight=1.0, fg_weight=5,
+                        bg_weight=1, alpha=1, gamma=2)).eval()
+    head.depth_samples = O.depth_samples(cfg)
+    head.downsample_factor = 4
+    with torch.no_grad():
+        cost, stereo, mono = m(cur, prev, copy.deepcopy(metas))
+        volume = ns.build_dfm_cost(
+            cur, prev, m.downsampled_depth, 1, 4,
+            torch.as_tensor(np.array([metas[0]['ori_cam2img']]),
+                            dtype=torch.float32),
+            metas[0]['cur2prevs'], metas[0]['ori_shape'][:2], flip,
+            metas[0]['crop_offset'], img_scale_factor=scale)
+        _, sm, preds = head(cost)
+    np.savez_compressed(
+        os.path.join(HERE, name + '.npz'), cur=cur.numpy(), prev=prev.numpy(),
+        volume=volume.numpy().astype(np.float32), cost=cost.numpy(),
+        stereo=stereo.numpy(), mono=mono.numpy(), depth_preds=preds.numpy(),
+        softmax_slice=sm[0, 0, :, ::8, ::8].numpy())
+    print(name, 'cost', tuple(cost.shape), float(cost.abs().max()))
+
+
+def neck_case(ns):
+    rng = np.random.RandomState(21)
+    c0, cout, t = 64, 256, 2
+    nx, ny, nz = 6, 5, 12
+    for name, mod in (('neck_dfm', ns.DfMNeck(c0, cout, num_frames=t)),
+                      ('neck_imvoxel', ns.OutdoorImVoxelNeck(c0, cout))):
+        mod = mod.eval()
+        sd = syn.make_neck_params(rng, mod.state_dict())
+        mod.load_state_dict(sd, strict=True)
+        cin = c0 * t if name == 'neck_dfm' else c0
+        x = torch.from_numpy(
+            rng.standard_normal((1, cin, nx, ny, nz)).astype(np.float32))
+        with torch.no_grad():
+            y = mod(x)[0]
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), x=x.numpy(),
+                            y=y.numpy(), seed=21)
+        print(name, tuple(y.shape), float(y.abs().max()))
+
+
+def main():
+    ns = load_reference()
+    torch.manual_seed(0)
+    for name, spec in KITTI_CASES.items():
+        kitti_case(ns, name, spec)
+    neck_case(ns)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,338 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path, called through
+the C-ABI library, against the oracle / the reference-generated golden fixtures /
+plain fp32 PyTorch ops, plus size-independent properties at the BASELINE.json shape.
+
+Tolerance: BASELINE.json's north_star states 1e-3 relative (fp32).  We use the
+normalised max-norm error  max|a-b| / max|b| <= 1e-3  for end-to-end outputs, and
+much tighter bounds for single ops.
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from depth_from_motion_b200 import capi, modules
+from depth_from_motion_b200 import synthetic as syn
+from oracle import dfm_oracle as O
+from tests.util import GOLDEN, KITTI_CASES, load_kitti_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3  # north_star tolerance
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _fp32_reference():
+    assert torch.cuda.is_available(), 'GPU tests need a B200'
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _backbone(params, cfg, impl):
+    m = modules.DfMBackbone(in_channels=32, depth_cfg=cfg, conv_impl=impl).cuda().eval()
+    m.load_state_dict(params, strict=True)
+    m.downsampled_depth = O.downsampled_depth(cfg)
+    return m
+
+
+def test_library_loads_and_sees_b200():
+    L = capi.lib()
+    import ctypes
+    sm, maj, mnr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    l2 = ctypes.c_longlong()
+    capi.check(L.dfm_device_info(ctypes.byref(sm), ctypes.byref(maj),
+                                 ctypes.byref(mnr), ctypes.byref(l2)), 'info')
+    assert maj.value == 10 and sm.value >= 100
+
+
+@pytest.mark.parametrize('name', sorted(KITTI_CASES))
+def test_cost_volume_matches_reference(name):
+    cur, prev, metas, params, cfg, gold = load_kitti_case(name)
+    spec = KITTI_CASES[name]
+    vol = modules.build_dfm_cost(
+        cur.cuda(), prev.cuda(), O.downsampled_depth(cfg), 1, 4,
+        torch.as_tensor(np.array([metas[0]['ori_cam2img']])),
+        metas[0]['cur2prevs'], metas[0]['ori_shape'][:2], spec[4],
+        metas[0]['crop_offset'], img_scale_factor=spec[6])
+    ref = torch.from_numpy(gold['volume'])
+    assert vol.shape == ref.shape
+    assert rel_err(vol, ref) < TOL
+    # cur half is the exact stride-4 subsample of the cur feature
+    assert torch.equal(vol[0, :32, 3].cpu(), cur[0, :, ::4, ::4])
+
+
+CONV_CASES = [
+    # cin, cout, (D,H,W), stride, pad, transposed
+    (32, 32, (6, 9, 21), (1, 1, 1), (1, 1, 1), False),
+    (64, 32, (4, 8, 16), (1, 1, 1), (1, 1, 1), False),
+    (32, 64, (8, 12, 20), (2, 2, 2), (1, 1, 1), False),
+    (64, 64, (4, 6, 10), (1, 1, 1), (1, 1, 1), False),
+    (64, 64, (8, 8, 12), (2, 2, 2), (1, 1, 1), False),
+    (64, 64, (3, 4, 5), (2, 2, 2), (1, 1, 1), True),
+    (64, 32, (4, 5, 7), (2, 2, 2), (1, 1, 1), True),
+    (64, 128, (5, 4, 12), (1, 1, 2), (1, 1, 1), False),
+    (128, 128, (4, 3, 6), (1, 1, 1), (1, 1, 1), False),
+    (128, 256, (4, 3, 6), (1, 1, 2), (1, 1, 1), False),
+    (256, 256, (4, 3, 3), (1, 1, 1), (1, 1, 0), False),
+]
+
+
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv3d_op_vs_torch(case, impl):
+    cin, cout, dims, stride, pad, tr = case
+    g = torch.Generator().manual_seed(cin * 1000 + cout + dims[0])
+    x = torch.randn((1, cin) + dims, generator=g).cuda()
+    if tr:
+        w = torch.randn((cin, cout, 3, 3, 3), generator=g) * 0.05
+        ref = F.conv_transpose3d(x, w.cuda(), None, 2, 1, 1)
+    else:
+        w = torch.randn((cout, cin, 3, 3, 3), generator=g) * 0.05
+        ref = F.conv3d(x, w.cuda(), None, stride, pad)
+    y = modules.conv3d(x, w, stride, pad, tr, impl=impl)
+    assert y.shape == ref.shape
+    # simt: fp32 FMA chains; auto: bf16x2 split operands on the tensor cores
+    assert rel_err(y, ref) < (2e-5 if impl == 'simt' else 1e-4)
+
+
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+@pytest.mark.parametrize('name', sorted(KITTI_CASES))
+def test_backbone_matches_reference_fixture(name, impl):
+    cur, prev, metas, params, cfg, gold = load_kitti_case(name)
+    m = _backbone(params, cfg, impl)
+    with torch.no_grad():
+        cost, stereo, mono = m(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
+    torch.cuda.synchronize()
+    for got, key in ((cost, 'cost'), (stereo, 'stereo'), (mono, 'mono')):
+        ref = torch.from_numpy(gold[key])
+        assert got.shape == ref.shape
+        e = rel_err(got, ref)
+        print(name, impl, key, 'rel err', e)
+        assert e < TOL, (key, e)
+    launches, tc = capi.launch_counters()
+    assert launches > 0
+
+
+@pytest.mark.parametrize('name', sorted(KITTI_CASES))
+def test_depth_head_matches_reference_fixture(name):
+    cur, prev, metas, params, cfg, gold = load_kitti_case(name)
+    head = modules.DepthHead(
+        depth_cfg=dict(mode='UD', num_bins=cfg['num_bins'], min_depth=2,
+                       max_depth=59.6), with_convs=False, num_views=1,
+        depth_loss=dict(type='balanced_focal', loss_weight=1.0, fg_weight=5,
+                        bg_weight=1, alpha=1, gamma=2))
+    head.depth_samples = O.depth_samples(cfg)
+    head.downsample_factor = 4
+    cost = torch.from_numpy(gold['cost']).cuda()
+    vol, sm, preds = head(cost)
+    rvol, rsm, rpreds = O.depth_head_forward(torch.from_numpy(gold['cost']),
+                                             O.depth_samples(cfg))
+    assert rel_err(vol, rvol) < 1e-5
+    assert float((sm.cpu() - rsm).abs().max()) < 1e-6
+    assert rel_err(preds, torch.from_numpy(gold['depth_preds'])) < 1e-5
+    assert rel_err(preds, rpreds) < 1e-5
+    _, _, p2 = head(cost, return_volumes=False)
+    assert torch.equal(p2, preds)
+
+
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+def test_backbone_midsize_vs_oracle(impl):
+    # config[0]-like case the CPU oracle finishes in seconds: D=16 planes
+    h, w, d = 64, 128, 16
+    cur, prev, metas, params = syn.make_kitti_pair(5, h, w, d)
+    cfg = syn.depth_cfg_for(d)
+    with torch.no_grad():
+        rcost, rst, rmo = O.dfm_backbone_forward(params, cur, prev, metas, cfg)
+    m = _backbone(params, cfg, impl)
+    with torch.no_grad():
+        cost, st, mo = m(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
+    for got, ref, key in ((cost, rcost, 'cost'), (st, rst, 'stereo'), (mo, rmo, 'mono')):
+        e = rel_err(got, ref)
+        print(impl, key, e)
+        assert e < TOL, (key, e)
+
+
+def test_simt_and_tensor_core_paths_agree():
+    h, w, d = 64, 128, 16
+    cur, prev, metas, params = syn.make_kitti_pair(6, h, w, d)
+    cfg = syn.depth_cfg_for(d)
+    outs = {}
+    for impl in ('simt', 'auto'):
+        m = _backbone(params, cfg, impl)
+        with torch.no_grad():
+            outs[impl] = m(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
+    for a, b in zip(outs['simt'], outs['auto']):
+        assert rel_err(a, b) < 2e-4
+
+
+def test_error_behaviour():
+    cfg = syn.depth_cfg_for(8)
+    m = modules.DfMBackbone(in_channels=32, depth_cfg=cfg).cuda().eval()
+    cur = torch.zeros(1, 32, 32, 64)
+    meta = [syn.make_img_meta(32, 64)]
+    with pytest.raises(RuntimeError):  # CPU tensors: there is no CPU path
+        m(cur, cur, meta)
+    with pytest.raises(AssertionError):  # the reference supports B=1 only
+        m(torch.zeros(2, 32, 32, 64).cuda(), torch.zeros(2, 32, 32, 64).cuda(), meta)
+    with pytest.raises(RuntimeError):  # Ho = 36/4 = 9 is not a multiple of 4
+        m(torch.zeros(1, 32, 36, 64).cuda(), torch.zeros(1, 32, 36, 64).cuda(),
+          [syn.make_img_meta(36, 64)])
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json shape: 370x1224 padded to 384x1248, D=112 -- size-independent
+# properties (the CPU oracle would need ~15 s per frame here)
+# ---------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def full_size():
+    h, w, d = 384, 1248, 112
+    cur, prev, metas, params = syn.make_kitti_pair(3, h, w, d,
+                                                   ori_shape=(370, 1224, 3))
+    cfg = syn.depth_cfg_for(d)
+    m = _backbone(params, cfg, 'auto')
+    with torch.no_grad():
+        out = m(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
+    torch.cuda.synchronize()
+    return dict(m=m, cur=cur, prev=prev, metas=metas, cfg=cfg, out=out, d=d, h=h, w=w)
+
+
+def test_full_size_outputs_finite_and_shaped(full_size):
+    cost, st, mo = full_size['out']
+    d = full_size['d']
+    assert cost.shape == (1, 1, d, 96, 312)
+    assert st.shape == (1, 32, d, 96, 312) and mo.shape == st.shape
+    for t in (cost, st, mo):
+        assert bool(torch.isfinite(t).all())
+    assert float(st.std()) > 0.1
+
+
+def test_full_size_mono_tower_ignores_prev_frame(full_size):
+    # the mono tower sees cost_raw[:, :32] only (dfm_backbone.py:189)
+    m = full_size['m']
+    prev2 = torch.roll(full_size['prev'], 7, dims=-1).cuda()
+    with torch.no_grad():
+        cost2, st2, mo2 = m(full_size['cur'].cuda(), prev2,
+                            copy.deepcopy(full_size['metas']))
+    assert torch.equal(mo2, full_size['out'][2])
+    assert not torch.equal(st2, full_size['out'][1])
+
+
+def test_full_size_identity_pose_volume_is_subsample():
+    # cur2prev = I  =>  the warp is the identity: both halves of the volume are the
+    # stride-4 subsample of their feature map on every plane
+    h, w, d = 384, 1248, 112
+    rng = np.random.RandomState(9)
+    cur = syn.smooth_field(rng, 32, h, w).cuda()
+    prev = syn.smooth_field(rng, 32, h, w).cuda()
+    meta = syn.make_img_meta(h, w, ori_shape=(370, 1224, 3))
+    meta['cur2prevs'] = torch.eye(4)[None]
+    cfg = syn.depth_cfg_for(d)
+    vol = modules.build_dfm_cost(cur, prev, O.downsampled_depth(cfg), 1, 4,
+                                 torch.as_tensor(np.array([meta['ori_cam2img']])),
+                                 meta['cur2prevs'], (370, 1224))
+    assert vol.shape == (1, 64, d, 96, 312)
+    sub_c = cur[0, :, ::4, ::4]
+    sub_p = prev[0, :, ::4, ::4]
+    for z in (0, 55, 111):
+        assert torch.equal(vol[0, :32, z], sub_c)
+        assert float((vol[0, 32:, z] - sub_p).abs().max()) < 2e-3
+
+
+def test_full_size_depth_head_properties(full_size):
+    cfg = full_size['cfg']
+    head = modules.DepthHead(
+        depth_cfg=dict(mode='UD', num_bins=cfg['num_bins'], min_depth=2,
+                       max_depth=59.6), with_convs=False, num_views=1,
+        depth_loss=dict(type='ce', loss_weight=1.0))
+    head.depth_samples = O.depth_samples(cfg)
+    head.downsample_factor = 4
+    vol, sm, preds = head(full_size['out'][0])
+    assert sm.shape == (1, 1, 448, 384, 1248)
+    s = sm.sum(2)
+    assert float((s - 1).abs().max()) < 1e-4
+    assert float(preds.min()) > 2.0 and float(preds.max()) < 59.6
+    # trilinear with align_corners reproduces the low-res logits at the corners
+    c = full_size['out'][0]
+    assert torch.allclose(vol[0, 0, 0, 0, 0], c[0, 0, 0, 0, 0])
+    assert torch.allclose(vol[0, 0, -1, -1, -1], c[0, 0, -1, -1, -1])
+    e = (sm * head.depth_samples.cuda()[None, None, :, None, None]).sum(2)
+    assert rel_err(preds, e) < 1e-5
+
+
+# ---------------------------------------------------------------------------
+# Waymo path: lifting + necks
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['neck_dfm', 'neck_imvoxel'])
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+def test_neck_matches_reference_fixture(name, impl):
+    gold = np.load(os.path.join(GOLDEN, name + '.npz'))
+    rng = np.random.RandomState(21)
+    dfm = modules.DfMNeck(64, 256, num_frames=2, conv_impl=impl)
+    imv = modules.OutdoorImVoxelNeck(64, 256, conv_impl=impl)
+    sd_dfm = syn.make_neck_params(rng, dfm.state_dict())
+    rng.standard_normal((1, 128, 6, 5, 12))
+    sd_imv = syn.make_neck_params(rng, imv.state_dict())
+    mod, sd = (dfm, sd_dfm) if name == 'neck_dfm' else (imv, sd_imv)
+    mod.load_state_dict(sd, strict=True)
+    mod = mod.cuda().eval()
+    y = mod(torch.from_numpy(gold['x']).cuda())[0]
+    ref = torch.from_numpy(gold['y'])
+    assert y.shape == ref.shape
+    e = rel_err(y, ref)
+    print(name, impl, e)
+    assert e < TOL
+
+
+def _lift_case(concat, flip):
+    rng = np.random.RandomState(31)
+    t, nv, c, hf, wf = 2, 3, 64, 20, 32
+    in_h, in_w = 80, 128
+    feats = torch.from_numpy(rng.standard_normal((t * nv, c, hf, wf)).astype(np.float32))
+    n_voxels = [12, 10, 4]
+    vrange = [2.0, -10.0, -2.0, 26.0, 10.0, 2.0]
+    mats = []
+    for f in range(t):
+        for v in range(nv):
+            yaw = (v - 1) * 0.6
+            # camera looks along +x (lidar frame), yawed; x_cam = -y_l, y_cam = -z_l, z_cam = x_l
+            r = np.array([[np.cos(yaw), np.sin(yaw), 0], [-np.sin(yaw), np.cos(yaw), 0],
+                          [0, 0, 1]])
+            l2c = np.array([[0, -1, 0], [0, 0, -1], [1, 0, 0]], dtype=np.float64) @ r
+            ext = np.eye(4)
+            ext[:3, :3] = l2c
+            ext[:3, 3] = l2c @ np.array([-0.5 * f, 0.1 * v, 0.3])
+            k = np.array([[60., 0, 64, 0], [0, 60., 40, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+            mats.append(k @ ext)
+    meta = dict(ori_lidar2img=np.array(mats), input_shape=(in_h, in_w),
+                img_shape=[(in_h - 2, in_w - 3, 3)] * (t * nv),
+                scale_factor=np.array([0.98, 1.01, 0.98, 1.01], dtype=np.float32),
+                img_crop_offset=[1.5, 0.5], flip=flip)
+    return feats, meta, n_voxels, vrange, t, nv
+
+
+@pytest.mark.parametrize('concat', [False, True])
+@pytest.mark.parametrize('flip', [False, True])
+def test_multiview_lift_vs_oracle(concat, flip):
+    feats, meta, n_voxels, vrange, t, nv = _lift_case(concat, flip)
+    agg = 'concat' if concat else 'mean'
+    got = modules.multiview_lift(feats.cuda(), meta, n_voxels, vrange, nv, t, agg)
+    xs, ys, zs = modules.aligned_voxel_centers(n_voxels, vrange)
+    zz, yy, xx = torch.meshgrid(zs, ys, xs, indexing='ij')
+    pts = torch.stack([xx, yy, zz], -1).reshape(-1, 3)
+    l2i = [torch.tensor(m, dtype=torch.float32) for m in meta['ori_lidar2img']]
+    ref = O.multiview_lift(feats, pts, n_voxels, l2i, nv, t,
+                           pts.new_tensor(meta['scale_factor'][:2]),
+                           pts.new_tensor(meta['img_crop_offset']), flip,
+                           meta['input_shape'], meta['img_shape'], agg)
+    assert got.shape == ref.shape
+    diff = (got.cpu() - ref).abs().amax(0)  # per voxel
+    # nearest-tap sampling is discontinuous: a voxel whose projection lands within
+    # fp32 rounding of a pixel boundary may pick the neighbouring tap; allow <=0.5 %
+    bad = float((diff > 1e-4).float().mean())
+    print('mismatching voxels', bad)
+    assert bad <= 0.005
+    assert float(ref.abs().sum()) > 0

@@ -1,0 +1,145 @@
+"""CPU tests of the host-side mirror: registry/config plumbing, state_dict
+contract, geometry packing, C-ABI library symbols."""
+import ctypes
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import depth_from_motion_b200 as pkg
+from depth_from_motion_b200 import capi, modules, registry
+from depth_from_motion_b200 import synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference'
+
+
+def test_registry_builds_by_type():
+    cfg = dict(type='DfMBackbone', in_channels=32, cv_channels=32, num_hg=1,
+               cost_sample_factor=4,
+               norm_cfg=dict(type='GN', num_groups=32, requires_grad=True))
+    cfg.update(depth_cfg=syn.depth_cfg_for(72))  # detectors/dfm.py:45-48
+    m = pkg.build_backbone(cfg)
+    assert isinstance(m, modules.DfMBackbone) and m.num_planes == 72
+    assert m.aggregate_cost.weight.shape == (72, 144, 1, 1)
+    n = pkg.build_neck(dict(type='DfMNeck', in_channels=64, out_channels=256,
+                            num_frames=2))
+    assert isinstance(n, modules.DfMNeck)
+    with pytest.raises(KeyError):
+        pkg.build_backbone(dict(type='NoSuchBackbone'))
+
+
+# reference state_dict contract (SURVEY.md section 8a "State")
+EXPECTED_KEYS = {
+    'dres0.conv.weight': (32, 64, 3, 3, 3), 'dres0.gn.weight': (32,),
+    'hg_stereo.0.conv1.0.0.weight': (64, 32, 3, 3, 3),
+    'hg_stereo.0.conv1.0.1.bias': (64,),
+    'hg_stereo.0.conv2.0.weight': (64, 64, 3, 3, 3),
+    'hg_stereo.0.conv5.0.weight': (64, 64, 3, 3, 3),
+    'hg_stereo.0.conv6.0.weight': (64, 32, 3, 3, 3),
+    'pred_stereo.0.0.conv.weight': (32, 32, 3, 3, 3),
+    'pred_stereo.0.1.weight': (1, 32, 3, 3, 3),
+    'dres0_mono.conv.weight': (32, 32, 3, 3, 3),
+    'hg_mono.0.conv4.0.1.weight': (64,),
+    'pred_mono.0.1.weight': (1, 32, 3, 3, 3),
+    'aggregate_cost.weight': (72, 144, 1, 1),
+}
+
+
+def test_state_dict_contract():
+    m = modules.DfMBackbone(in_channels=32, depth_cfg=syn.depth_cfg_for(72))
+    sd = m.state_dict()
+    assert len(sd) == 57
+    assert sum(v.numel() for v in sd.values()) == 1313344
+    for k, shp in EXPECTED_KEYS.items():
+        assert tuple(sd[k].shape) == shp, k
+    params = syn.make_backbone_params(np.random.RandomState(0), 72)
+    m.load_state_dict(params, strict=True)
+    n = modules.DfMNeck(64, 256, num_frames=2)
+    assert sum(v.numel() for k, v in n.state_dict().items()
+               if 'running' not in k and 'tracked' not in k) == 15932160
+    assert 'mono_layers.0.conv0.conv.weight' in n.state_dict()
+    assert 'stereo_layers.5.bn.running_var' in n.state_dict()
+    assert 'model.1.conv.weight' in modules.OutdoorImVoxelNeck(64, 256).state_dict()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not mounted')
+def test_state_dict_matches_reference_modules():
+    from oracle.ref_loader import load_reference
+    ns = load_reference()
+    cfg = syn.depth_cfg_for(16)
+    a = modules.DfMBackbone(in_channels=32, depth_cfg=cfg).state_dict()
+    b = ns.DfMBackbone(in_channels=32, depth_cfg=cfg).state_dict()
+    assert list(a) == list(b)
+    assert all(a[k].shape == b[k].shape for k in a)
+    for ours, ref in ((modules.DfMNeck(64, 256, num_frames=2), ns.DfMNeck(64, 256, num_frames=2)),
+                      (modules.OutdoorImVoxelNeck(64, 256), ns.OutdoorImVoxelNeck(64, 256))):
+        a, b = ours.state_dict(), ref.state_dict()
+        assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not mounted')
+@pytest.mark.parametrize('cfg_name', [
+    'dfm_r34_1x8_kitti-3d-3class.py',
+    'multiview-dfm_r101_dcn_2x16_waymoD5-3d-3class_camsync.py',
+    'multiview-dfm_r101_dcn_2x16_waymoD5-3d-3class_camsync_10sweeps.py'])
+def test_reference_configs_parse_and_build_hot_path(cfg_name):
+    """configs/dfm/*.py load unchanged: parse -> build the hot-path modules by type."""
+    cfg = registry.Config.fromfile(os.path.join(REF, 'configs/dfm', cfg_name))
+    model = cfg.model
+    if model['type'] == 'DfM':
+        bs = dict(model['backbone_stereo'])
+        bs.update(depth_cfg=model['depth_cfg'])
+        m = pkg.build_backbone(bs)
+        assert m.num_planes == 72
+        h = pkg.build_head(dict(model['depth_head']))
+        assert isinstance(h, modules.DepthHead) and not h.with_convs
+    else:
+        n = pkg.build_neck(dict(model['neck_3d']))
+        assert isinstance(n, (modules.DfMNeck, modules.OutdoorImVoxelNeck))
+
+
+def test_geometry_packing():
+    meta = syn.make_img_meta(384, 1248, flip=True, crop_offset=(3, 7), scale=1.25,
+                             ori_shape=(370, 1224, 3))
+    g = modules.geometry_from_meta(meta)
+    assert g.flip == 1 and g.org_w == 1224 and g.scale == 1.25
+    assert (g.crop_x, g.crop_y) == (3.0, 7.0)
+    assert abs(g.cam2img[0] - 721.5377) < 1e-3 and g.cam2img[15] == 1.0
+    assert abs(g.cur2prev[11] - 0.958234025) < 1e-6
+
+
+def test_no_cpu_fallback():
+    m = modules.DfMBackbone(in_channels=32, depth_cfg=syn.depth_cfg_for(8))
+    x = torch.zeros(1, 32, 32, 64)
+    with pytest.raises(RuntimeError):
+        m(x, x, [syn.make_img_meta(32, 64)])
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, 'include', 'dfm_b200.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(dfm_[a-z0-9_]+)\s*\(', txt)))
+
+
+def test_header_and_binding_agree():
+    assert _header_symbols() == sorted(capi.SYMBOLS)
+
+
+@pytest.mark.skipif(shutil.which('nvcc') is None and not capi.library_built(),
+                    reason='library not built and no nvcc')
+def test_library_exports_every_declared_symbol():
+    if not capi.library_built():
+        from depth_from_motion_b200 import build
+        build.build()
+    L = ctypes.CDLL(capi.LIB_PATH)  # dlopen only: no compute call without a GPU
+    for s in _header_symbols():
+        assert hasattr(L, s), s
+    assert L.dfm_version() >= 100
+    out = subprocess.run(['cuobjdump', '-lelf', capi.LIB_PATH], capture_output=True,
+                         text=True).stdout if shutil.which('cuobjdump') else 'sm_100a'
+    assert 'sm_100a' in out

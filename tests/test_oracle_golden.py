@@ -1,0 +1,122 @@
+"""CPU tests: the oracle restatement against (1) the reference's own golden vectors
+for this path and (2) fixtures produced by the unmodified
+reference sources (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from depth_from_motion_b200 import synthetic as syn
+from oracle import dfm_oracle as O
+from tests.util import GOLDEN, KITTI_CASES, load_kitti_case
+
+
+def test_points_img2cam_kat():
+    # reference tests/test_utils/test_utils.py:186-193
+    points = torch.tensor([[0.5764, 0.9109, 0.7576], [0.6656, 0.5498, 0.9813]])
+    cam2img = torch.tensor([[700., 0., 450., 0.], [0., 700., 200., 0.],
+                            [0., 0., 1., 0.]])
+    expected = torch.tensor([[-0.4864, -0.2155, 0.7576],
+                             [-0.6299, -0.2796, 0.9813]])
+    assert torch.allclose(O.points_img2cam(points, cam2img), expected, atol=1e-3)
+
+
+def test_points_cam2img_kat():
+    # reference tests/test_utils/test_box3d.py:1653-1680
+    torch.manual_seed(0)
+    points = torch.rand([5, 3])
+    proj_mat = torch.rand([4, 4])
+    expected = torch.tensor([[0.5832, 0.6496], [0.6146, 0.7910],
+                             [0.6994, 0.7782], [0.5623, 0.6303],
+                             [0.4359, 0.6532]])
+    assert torch.allclose(O.points_cam2img(points, proj_mat), expected, 1e-3)
+    expected_d = torch.tensor([[0.5832, 0.6496, 1.7577], [0.6146, 0.7910, 1.5477],
+                               [0.6994, 0.7782, 2.0091], [0.5623, 0.6303, 1.8739],
+                               [0.4359, 0.6532, 1.2056]])
+    assert torch.allclose(O.points_cam2img(points, proj_mat, with_depth=True),
+                          expected_d, 1e-3)
+
+
+def test_point_sample_kat():
+    # reference tests/test_models/test_fusion/test_point_fusion.py:13-41 (the
+    # no-3D-augmentation half; PointFusion.sample_single -> point_sample with
+    # scale 1, crop 0, no flip, bilinear, align_corners=True)
+    lidar2img = torch.tensor(
+        [[6.0294e+02, -7.0791e+02, -1.2275e+01, -1.7094e+02],
+         [1.7678e+02, 8.8088e+00, -7.0794e+02, -1.0257e+02],
+         [9.9998e-01, -1.5283e-03, -5.2907e-03, -3.2757e-01],
+         [0.0000e+00, 0.0000e+00, 0.0000e+00, 1.0000e+00]])
+    img_feat = torch.arange(370 * 1224)[None, ...].view(
+        370, 1224)[None, None, ...].float() / (370 * 1224)
+    pts = torch.tensor([[8.356, -4.312, -0.445], [11.777, -6.724, -0.564],
+                        [6.453, 2.53, -1.612], [6.227, -3.839, -0.563]])
+    out = O.point_sample(img_feat, pts, lidar2img, pts.new_tensor([1., 1.]),
+                         0, False, (370, 1224), (370, 1224), aligned=True)
+    expected = torch.tensor([0.5560822, 0.5476625, 0.9687978, 0.6241757])
+    assert torch.allclose(expected, out.squeeze(), 1e-4)
+
+
+@pytest.mark.parametrize('name', sorted(KITTI_CASES))
+def test_backbone_matches_reference_fixture(name):
+    cur, prev, metas, params, cfg, gold = load_kitti_case(name)
+    spec = KITTI_CASES[name]
+    with torch.no_grad():
+        vol = O.build_dfm_cost(
+            cur, prev, O.downsampled_depth(cfg), 1, 4,
+            torch.as_tensor(np.array([metas[0]['ori_cam2img']]),
+                            dtype=torch.float32), metas[0]['cur2prevs'],
+            metas[0]['ori_shape'][:2], spec[4], metas[0]['crop_offset'],
+            img_scale_factor=spec[6])
+        cost, stereo, mono = O.dfm_backbone_forward(params, cur, prev, metas, cfg)
+        _, sm, preds = O.depth_head_forward(cost, O.depth_samples(cfg))
+    # same ATen ops, same order, same machine class: tiny tolerance only for
+    # thread-count dependent summation order
+    for got, key in ((vol, 'volume'), (cost, 'cost'), (stereo, 'stereo'),
+                     (mono, 'mono'), (preds, 'depth_preds')):
+        ref = torch.from_numpy(gold[key])
+        assert got.shape == ref.shape, key
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5), key
+    assert torch.allclose(sm[0, 0, :, ::8, ::8],
+                          torch.from_numpy(gold['softmax_slice']), atol=1e-6)
+
+
+def test_generated_inputs_match_stored_inputs():
+    # fixture inputs regenerate bit-identically from their seed
+    for name, spec in KITTI_CASES.items():
+        seed, h, w, d = spec[:4]
+        cur, prev, _, _ = syn.make_kitti_pair(seed, h, w, d)
+        gold = np.load(os.path.join(GOLDEN, name + '.npz'))
+        assert np.array_equal(cur.numpy(), gold['cur'])
+        assert np.array_equal(prev.numpy(), gold['prev'])
+
+
+@pytest.mark.parametrize('name', ['neck_dfm', 'neck_imvoxel'])
+def test_neck_matches_reference_fixture(name):
+    from depth_from_motion_b200 import modules
+    gold = np.load(os.path.join(GOLDEN, name + '.npz'))
+    rng = np.random.RandomState(21)
+    dfm = modules.DfMNeck(64, 256, num_frames=2)
+    imv = modules.OutdoorImVoxelNeck(64, 256)
+    # make_golden draws the DfMNeck parameters first, then its input, then the
+    # OutdoorImVoxelNeck parameters: replay the same stream
+    sd_dfm = syn.make_neck_params(rng, dfm.state_dict())
+    x_dfm = rng.standard_normal((1, 128, 6, 5, 12)).astype(np.float32)
+    sd_imv = syn.make_neck_params(rng, imv.state_dict())
+    x = torch.from_numpy(gold['x'])
+    if name == 'neck_dfm':
+        assert np.array_equal(x_dfm, gold['x'])
+        with torch.no_grad():
+            y = O.dfm_neck_forward(sd_dfm, x, 64)[0]
+    else:
+        with torch.no_grad():
+            y = O.imvoxel_neck_forward(sd_imv, x)[0]
+    assert torch.allclose(y, torch.from_numpy(gold['y']), rtol=1e-4, atol=1e-4)
+
+
+def test_depth_tables():
+    cfg = syn.depth_cfg_for(72)
+    d = O.downsampled_depth(cfg)
+    assert d.shape == (72,) and abs(float(d[0]) - (2 + 0.5 * 4 * 0.2)) < 1e-5
+    s = O.depth_samples(cfg)
+    assert s.shape == (288,) and abs(float(s[-1]) - (59.6 - 0.1)) < 1e-4
