@@ -21,6 +21,7 @@ DFM_OUT_COST, DFM_OUT_STEREO, DFM_OUT_MONO = 1, 2, 4
 # header against this list and against the built library)
 SYMBOLS = (
     'dfm_last_error', 'dfm_version', 'dfm_device_info', 'dfm_launch_counters',
+    'dfm_sync_check', 'dfm_profile_enable', 'dfm_profile_report',
     'dfm_backbone_create', 'dfm_backbone_destroy', 'dfm_backbone_set_param',
     'dfm_backbone_set_depths', 'dfm_backbone_missing_params',
     'dfm_backbone_workspace_bytes', 'dfm_backbone_forward',
@@ -87,6 +88,9 @@ def lib():
     L.dfm_version.restype = c_int
     L.dfm_device_info.argtypes = [ip, ip, ip, POINTER(c_longlong)]
     L.dfm_launch_counters.argtypes = [POINTER(c_longlong), POINTER(c_longlong)]
+    L.dfm_sync_check.argtypes = [vp]
+    L.dfm_profile_enable.argtypes = [c_int]
+    L.dfm_profile_report.argtypes = [c_char_p, c_int]
     L.dfm_backbone_create.argtypes = [POINTER(BackboneDesc), POINTER(vp)]
     L.dfm_backbone_destroy.argtypes = [vp]
     L.dfm_backbone_set_param.argtypes = [vp, c_char_p, vp, c_longlong]
@@ -125,6 +129,23 @@ def check(rc, what):
     if rc != DFM_OK:
         msg = lib().dfm_last_error().decode('utf-8', 'replace')
         raise RuntimeError(f'{what} failed (code {rc}): {msg}')
+
+
+def sync_check(stream=None):
+    """Synchronise and raise on any asynchronous kernel failure."""
+    check(lib().dfm_sync_check(c_void_p(stream or 0)), 'dfm_sync_check')
+
+
+def profile_enable(on=True):
+    check(lib().dfm_profile_enable(int(on)), 'dfm_profile_enable')
+
+
+def profile_report():
+    """dict: kernel class -> {launches, ms, flops} since the last report."""
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().dfm_profile_report(buf, len(buf)), 'dfm_profile_report')
+    return json.loads(buf.value.decode() or '{}')
 
 
 def launch_counters():

@@ -46,6 +46,54 @@ int fail(int code, const std::string& msg) {
     CU_TRY(cudaGetLastError());              \
   } while (0)
 
+// ---- optional per-launch device timing (bench.py roofline) ----
+struct ProfRec {
+  std::string cls;
+  cudaEvent_t e0, e1;
+  double flops;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {
+  bool on;
+  ProfRec r;
+  cudaStream_t st;
+  ProfScope(const std::string& cls, double flops, cudaStream_t s) : on(g_prof_on), st(s) {
+    if (!on) return;
+    r.cls = cls;
+    r.flops = flops;
+    r.e0 = prof_event();
+    r.e1 = prof_event();
+    cudaEventRecord(r.e0, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.e1, st);
+    g_prof.push_back(r);
+  }
+};
+double conv_flops(const dfm::ConvGeom& g) {
+  const double vout = (double)g.Do * g.Ho * g.Wo;
+  // a transposed stride-2 conv touches 27/8 taps per output voxel on average
+  return 2.0 * vout * g.Cin * g.Cout * (g.transposed ? 27.0 / 8.0 : 27.0);
+}
+std::string conv_class(const char* kind, const dfm::ConvGeom& g, const char* loader) {
+  return std::string(kind) + "<" + std::to_string(g.Cin) + "->" + std::to_string(g.Cout) +
+         (g.transposed ? ",T" : g.sd == 2 ? ",s2" : ",s1") + "," + loader + ">@" +
+         std::to_string(g.Do) + "x" + std::to_string(g.Ho) + "x" + std::to_string(g.Wo);
+}
+
 struct DevBuf {
   float* p = nullptr;
   size_t n = 0;
@@ -221,12 +269,14 @@ int run_conv(const dfm::Src& s, const ConvW& w, float* out, const dfm::ConvGeom&
     return fail(DFM_ERR_INVALID, "conv3d: no tensor-core kernel for this layer");
   if (impl != DFM_CONV_SIMT && tc_ok) {
     std::string err;
+    ProfScope ps(conv_class("conv_tc", g, "src"), conv_flops(g), st);
     if (!dfm::tc_conv_src(s, w.tc, out, g, st, &err)) return fail(DFM_ERR_CUDA, err);
     g_launches.fetch_add(1);
     g_tc_launches.fetch_add(1);
     return DFM_OK;
   }
   dfm::SrcLoader ld{s, g.Cin, g.Hi, g.Wi};
+  ProfScope ps(conv_class("conv_simt", g, "src"), conv_flops(g), st);
   return conv_simt_dispatch(ld, w, out, g, st);
 }
 
@@ -237,11 +287,13 @@ int run_conv_warp(const dfm::WarpLoader& ld, const ConvW& w, float* out, const d
     return fail(DFM_ERR_INVALID, "conv3d(warp): no tensor-core kernel for this layer");
   if (impl != DFM_CONV_SIMT && tc_ok) {
     std::string err;
+    ProfScope ps(conv_class("conv_tc", g, "warp"), conv_flops(g), st);
     if (!dfm::tc_conv_warp(ld, w.tc, out, g, st, &err)) return fail(DFM_ERR_CUDA, err);
     g_launches.fetch_add(1);
     g_tc_launches.fetch_add(1);
     return DFM_OK;
   }
+  ProfScope ps(conv_class("conv_simt", g, "warp"), conv_flops(g), st);
   return conv_simt_dispatch(ld, w, out, g, st);
 }
 
@@ -563,6 +615,50 @@ int dfm_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* l2_b
   return DFM_OK;
 }
 
+int dfm_sync_check(void* stream) {
+  CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  CU_TRY(cudaGetLastError());
+  if (dfm::tc_consume_error())
+    return fail(DFM_ERR_CUDA, "tensor-core conv kernel: mbarrier hand-over timed out");
+  return DFM_OK;
+}
+
+int dfm_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return DFM_OK;
+}
+
+int dfm_profile_report(char* buf, int cap) {
+  if (!buf || cap < 3) return fail(DFM_ERR_INVALID, "null/short buffer");
+  CU_TRY(cudaDeviceSynchronize());
+  std::map<std::string, std::pair<long long, std::pair<double, double>>> agg;
+  for (ProfRec& r : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    auto& a = agg[r.cls];
+    a.first += 1;
+    a.second.first += ms;
+    a.second.second += r.flops;
+    g_event_pool.push_back(r.e0);
+    g_event_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char tmp[512];
+    snprintf(tmp, sizeof tmp, "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e}",
+             first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second.first,
+             kv.second.second.second);
+    js += tmp;
+    first = false;
+  }
+  js += "}";
+  strncpy(buf, js.c_str(), cap - 1);
+  buf[cap - 1] = 0;
+  return DFM_OK;
+}
+
 int dfm_launch_counters(long long* launches, long long* tc_launches) {
   if (launches) *launches = g_launches.load();
   if (tc_launches) *tc_launches = g_tc_launches.load();
@@ -760,6 +856,8 @@ int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const floa
   tmp_s.release();
   tmp_m.release();
   if (rc == DFM_OK && e != cudaSuccess) rc = fail(DFM_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == DFM_OK && dfm::tc_consume_error())
+    rc = fail(DFM_ERR_CUDA, "tensor-core conv kernel: mbarrier hand-over timed out");
   return rc;
 }
 
@@ -834,6 +932,8 @@ int dfm_op_conv3d(const float* d_x, int Cin, int Di, int Hi, int Wi, const float
   w.simt.release();
   w.tc.release();
   if (rc == DFM_OK && e != cudaSuccess) rc = fail(DFM_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == DFM_OK && dfm::tc_consume_error())
+    rc = fail(DFM_ERR_CUDA, "tensor-core conv kernel: mbarrier hand-over timed out");
   return rc;
 }
 

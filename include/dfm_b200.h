@@ -110,6 +110,15 @@ const float* dfm_backbone_cost_device(const dfm_backbone_t* bb);
  * "cur", "p0", "logit" with suffix "_mono" for the mono tower. */
 int dfm_backbone_debug_tensor(dfm_backbone_t* bb, const char* name, float* d_out,
                               long long numel, void* stream);
+/* Synchronises `stream` and reports asynchronous failures of this library's kernels
+ * (CUDA errors, or an mbarrier hand-over that timed out inside a tensor-core kernel). */
+int dfm_sync_check(void* stream);
+/* Per-kernel device timing: when enabled, every conv launch is bracketed by CUDA events
+ * on its own stream.  dfm_profile_report synchronises the device, writes one JSON object
+ * {"<kernel class>": {"launches": n, "ms": total, "flops": algorithmic}, ...} into buf
+ * (NUL-terminated, truncated to cap) and clears the record. */
+int dfm_profile_enable(int on);
+int dfm_profile_report(char* buf, int cap);
 /* Counters since creation: kernels launched by this library / of which tcgen05. */
 int dfm_launch_counters(long long* launches, long long* tc_launches);
 

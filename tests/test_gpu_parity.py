@@ -106,7 +106,7 @@ def test_backbone_matches_reference_fixture(name, impl):
     m = _backbone(params, cfg, impl)
     with torch.no_grad():
         cost, stereo, mono = m(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
-    torch.cuda.synchronize()
+    capi.sync_check()
     for got, key in ((cost, 'cost'), (stereo, 'stereo'), (mono, 'mono')):
         ref = torch.from_numpy(gold[key])
         assert got.shape == ref.shape
@@ -150,6 +150,7 @@ def test_backbone_midsize_vs_oracle(impl):
     m = _backbone(params, cfg, impl)
     with torch.no_grad():
         cost, st, mo = m(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
+    capi.sync_check()
     for got, ref, key in ((cost, rcost, 'cost'), (st, rst, 'stereo'), (mo, rmo, 'mono')):
         e = rel_err(got, ref)
         print(impl, key, e)
@@ -196,7 +197,7 @@ def full_size():
     m = _backbone(params, cfg, 'auto')
     with torch.no_grad():
         out = m(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
-    torch.cuda.synchronize()
+    capi.sync_check()
     return dict(m=m, cur=cur, prev=prev, metas=metas, cfg=cfg, out=out, d=d, h=h, w=w)
 
 
