@@ -55,62 +55,212 @@ inline float bf16_bits_to_float(uint16_t b) {
   return f;
 }
 
-constexpr int TC_BX = 8, TC_BY = 16;          // output tile (x, y)
-constexpr int TC_PX = TC_BX + 2, TC_PY = TC_BY + 2;
-constexpr int TC_ROWS = 186;                   // 180 brick rows padded (== 2 mod 8)
-constexpr int TC_CG = 32;                      // channels per pipeline stage
-constexpr int TC_STAGE_BYTES = 2 * (TC_CG / 8) * TC_ROWS * 16;  // hi + lo
-constexpr int TC_NSTAGE = 4;
-constexpr int TC_NSLOT = 8;
-constexpr int TC_THREADS = 288;
+// ----------------------------------------------------------------------------------
+// modes and compile-time geometry
+// ----------------------------------------------------------------------------------
+enum { TC_S1 = 0, TC_S2 = 1, TC_T = 2 };
+constexpr int TC_BX = 8, TC_BY = 16;  // M tile: 8 (x) * 16 (y) = 128 accumulator rows
+constexpr int TC_NSLOT_MAX = 16;
+constexpr int TC_LOAD_THREADS = 256;
+constexpr int TC_THREADS = 128 + TC_LOAD_THREADS + 32;  // epilogue | loaders | MMA issuer
+constexpr int TC_MAXOPS = 9, TC_MAXBLK = 32;
 
-inline bool tc_supported(int Cin, int Cout, int transposed) {
-  if (transposed) return false;
+template <int MODE>
+struct TcMode;
+template <>
+struct TcMode<TC_S1> {  // out(x,y,z) <- in(x+dx-1, y+dy-1, z+dz-1)
+  static constexpr int PXB = 10, PYB = 18, PITCH = 10, ROWS = 186, CG = 32, NSTAGE = 4;
+  static constexpr int SLOT_BLOCKS = 1, NSLOT = 16;
+  __host__ __device__ static int zo_of(int zi, int dz) { return zi + dz; }
+  __host__ __device__ static int zi_first(int zo) { return zo - 1; }
+  __host__ __device__ static int zi_last(int zo) { return zo + 1; }
+  __host__ __device__ static int ptype(int) { return 0; }
+};
+template <>
+struct TcMode<TC_S2> {  // out(x,y,z) <- in(2x+dx-1, 2y+dy-1, 2z+dz-1); x/y parity arrays
+  static constexpr int PXB = 17, PYB = 33, PITCH = 9, ROWS = 620, CG = 16, NSTAGE = 3;
+  static constexpr int SLOT_BLOCKS = 1, NSLOT = 16;
+  __host__ __device__ static int zo_of(int zi, int dz) { return (zi >> 1) + dz; }
+  __host__ __device__ static int zi_first(int zo) { return 2 * zo - 1; }
+  __host__ __device__ static int zi_last(int zo) { return 2 * zo + 1; }
+  __host__ __device__ static int ptype(int zi) { return zi & 1; }
+};
+template <>
+struct TcMode<TC_T> {  // ConvTranspose3d(k3,s2,p1,op1): out(2m+p) <- in(m + s), 8 parity classes
+  static constexpr int PXB = 9, PYB = 17, PITCH = 9, ROWS = 154, CG = 32, NSTAGE = 4;
+  static constexpr int SLOT_BLOCKS = 4, NSLOT = 8;  // 4 (px,py) classes per output plane
+  __host__ __device__ static int zo_of(int zi, int dz) { return 2 * zi + dz; }
+  __host__ __device__ static int zi_first(int zo) { return zo >> 1; }
+  __host__ __device__ static int zi_last(int zo) { return (zo + 1) >> 1; }
+  __host__ __device__ static int ptype(int) { return 0; }
+};
+
+inline int tc_mode_of(const ConvGeom& g) {
+  if (g.transposed) return TC_T;
+  if (g.sd == 1 && g.sh == 1 && g.sw == 1 && g.pd == 1 && g.ph == 1 && g.pw == 1) return TC_S1;
+  if (g.sd == 2 && g.sh == 2 && g.sw == 2 && g.pd == 1 && g.ph == 1 && g.pw == 1 &&
+      g.Di % 2 == 0 && g.Hi % 2 == 0 && g.Wi % 2 == 0)
+    return TC_S2;
+  return -1;
+}
+inline bool tc_supported(int Cin, int Cout, int /*transposed*/) {
   if (Cin != 32 && Cin != 64) return false;
   const int ncta = 1024 / Cin;
   return Cout % ncta == 0 && Cout <= 64;
 }
-inline bool tc_geom_supported(const ConvGeom& g) {
-  return !g.transposed && g.sd == 1 && g.sh == 1 && g.sw == 1 && g.pd == 1 && g.ph == 1 &&
-         g.pw == 1 && g.Do == g.Di && g.Ho == g.Hi && g.Wo == g.Wi;
+inline bool tc_geom_supported(const ConvGeom& g) { return tc_mode_of(g) >= 0; }
+
+// One MMA "op" = one A view (tap shift of the brick) against a weight image whose
+// NCTA-row blocks land in consecutive accumulator column blocks.
+struct TcOp {
+  uint32_t a_off;   // byte offset of the A view inside a stage (hi array)
+  uint32_t b_off;   // byte offset of this op's weight image (hi half) in smem
+  uint32_t b_lbo;   // bytes between 8-channel chunks of the weight image
+  uint16_t blk0, blk1;
+  // static decomposition into MMAs when every output plane is live and nothing is fresh:
+  // run = nblk | first block << 4 | (dz+1) of first plane << 8 | colblk << 10 |
+  //       blocks per plane << 12 | planes << 16
+  uint32_t nruns;
+  uint32_t runs[3];
+};
+struct TcBlk {
+  int8_t dz;        // output plane relative to zo_of(zi, 0)
+  uint8_t colblk;   // column block inside the accumulator slot
+  uint8_t tap;      // 27-tap index (kz*9 + ky*3 + kx) of the weights in this block
+  uint8_t pad;
+};
+struct TcProgram {
+  int nops;
+  uint32_t need;    // mask of (dz+1) values this plane type writes
+  TcOp ops[TC_MAXOPS];
+  TcBlk blks[TC_MAXBLK];
+};
+
+// host: the op list of one input-plane type
+template <int MODE>
+inline void tc_build_program(int ptype, int Cin, int ncta, uint32_t* w_cursor, TcProgram* pr) {
+  using M = TcMode<MODE>;
+  pr->nops = 0;
+  pr->need = 0;
+  int nb = 0;
+  auto add_op = [&](int a_rows, std::vector<TcBlk> blks) {
+    TcOp& op = pr->ops[pr->nops++];
+    op.a_off = (uint32_t)a_rows * 16;
+    op.b_off = *w_cursor;
+    op.b_lbo = (uint32_t)blks.size() * ncta * 16;
+    op.blk0 = (uint16_t)nb;
+    for (TcBlk b : blks) pr->blks[nb++] = b;
+    op.blk1 = (uint16_t)nb;
+    *w_cursor += (uint32_t)(Cin / 8) * op.b_lbo;
+    // static runs: maximal groups of blocks that are consecutive in (plane, colblk)
+    // order with SLOT_BLOCKS column blocks per plane
+    op.nruns = 0;
+    size_t i = 0;
+    while (i < blks.size()) {
+      size_t e = i + 1;
+      auto lin = [&](const TcBlk& b) { return (b.dz + 1) * M::SLOT_BLOCKS + b.colblk; };
+      while (e < blks.size() && lin(blks[e]) == lin(blks[i]) + (int)(e - i)) ++e;
+      const int nblk = (int)(e - i);
+      int planes = 1, bpp = nblk;
+      if (blks[e - 1].dz != blks[i].dz) {  // spans planes: must cover whole slots
+        planes = blks[e - 1].dz - blks[i].dz + 1;
+        bpp = nblk / planes;
+      }
+      op.runs[op.nruns++] = (uint32_t)nblk | ((uint32_t)i << 4) |
+                            ((uint32_t)(blks[i].dz + 1) << 8) | ((uint32_t)blks[i].colblk << 10) |
+                            ((uint32_t)bpp << 12) | ((uint32_t)planes << 16);
+      pr->need |= ((1u << planes) - 1u) << (blks[i].dz + 1);
+      i = e;
+    }
+  };
+  if (MODE == TC_S1) {
+    for (int t = 0; t < 9; ++t) {
+      const int dy = t / 3, dx = t % 3;
+      // planes z-1, z, z+1 receive kz = 2, 1, 0
+      add_op(dy * M::PITCH + dx, {TcBlk{-1, 0, (uint8_t)(18 + t), 0}, TcBlk{0, 0, (uint8_t)(9 + t), 0},
+                                  TcBlk{1, 0, (uint8_t)t, 0}});
+    }
+  } else if (MODE == TC_S2) {
+    for (int t = 0; t < 9; ++t) {
+      const int dy = t / 3, dx = t % 3;
+      const int a_rows = (((dx & 1) * 2 + (dy & 1)) * 17 + (dy >> 1)) * M::PITCH + (dx >> 1);
+      if (ptype == 0)  // zi = 2q: kz = 1 -> zo = q
+        add_op(a_rows, {TcBlk{0, 0, (uint8_t)(9 + t), 0}});
+      else             // zi = 2q+1: kz = 2 -> zo = q, kz = 0 -> zo = q+1
+        add_op(a_rows, {TcBlk{0, 0, (uint8_t)(18 + t), 0}, TcBlk{1, 0, (uint8_t)t, 0}});
+    }
+  } else {
+    // class order inside a slot: (px,py) = (0,0), (1,0), (1,1), (0,1) so that every
+    // shift's class set is a contiguous column range
+    const int cls_px[4] = {0, 1, 1, 0}, cls_py[4] = {0, 0, 1, 1};
+    for (int sh = 0; sh < 4; ++sh) {
+      const int sx = sh & 1, sy = sh >> 1;
+      std::vector<TcBlk> blks;
+      for (int dz = -1; dz <= 1; ++dz) {
+        // out plane 2zi+dz: dz=-1 uses kz=0 (this plane is its m+1 input), 0 -> kz=1, +1 -> kz=2
+        const int kz = dz + 1;
+        for (int c = 0; c < 4; ++c) {
+          const int px = cls_px[c], py = cls_py[c];
+          // o = 2i - 1 + k: p=0 -> k=1,s=0 ; p=1 -> (k=2,s=0) or (k=0,s=1)
+          int kx, ky;
+          if (px == 0) { if (sx) continue; kx = 1; } else kx = sx ? 0 : 2;
+          if (py == 0) { if (sy) continue; ky = 1; } else ky = sy ? 0 : 2;
+          blks.push_back(TcBlk{(int8_t)dz, (uint8_t)c, (uint8_t)(kz * 9 + ky * 3 + kx), 0});
+        }
+      }
+      add_op(sy * M::PITCH + sx, blks);
+    }
+  }
 }
 
 struct TcWeights {
   uint8_t* dev = nullptr;  // [nsplit][image bytes]
-  int Cin = 0, Cout = 0, ncta = 0, nsplit = 0;
-  size_t image_bytes = 0;
+  int Cin = 0, Cout = 0, ncta = 0, nsplit = 0, mode = -1;
+  uint32_t image_bytes = 0, hi_bytes = 0;
+  TcProgram prog[2];
 
   bool ready() const { return dev != nullptr; }
   void release() {
     if (dev) cudaFree(dev);
     dev = nullptr;
   }
-  // packed: [27][Cin][Cout] fp32 (tap = kz*9 + ky*3 + kx)
-  bool build(const float* packed, int cin, int cout, std::string* err) {
+  // packed: [27][Cin][Cout] fp32 (tap = kz*9 + ky*3 + kx; transposed weights are
+  // already in "o = 2i - 1 + k" orientation)
+  template <int MODE>
+  bool build_mode(const float* packed, int cin, int cout, std::string* err) {
     release();
+    mode = MODE;
     Cin = cin;
     Cout = cout;
     ncta = 1024 / cin;
     nsplit = cout / ncta;
-    const int kch = cin / 8, nrow = 3 * ncta;
-    const size_t tap_bytes = (size_t)kch * nrow * 16;  // one (dy,dx) tap, hi or lo
-    image_bytes = 2 * 9 * tap_bytes;
+    uint32_t cursor = 0;
+    const int ntypes = MODE == TC_S2 ? 2 : 1;
+    for (int t = 0; t < ntypes; ++t) tc_build_program<MODE>(t, cin, ncta, &cursor, &prog[t]);
+    hi_bytes = cursor;
+    image_bytes = 2 * hi_bytes;
     std::vector<uint16_t> img((size_t)nsplit * image_bytes / 2);
+    const int kch = cin / 8;
     for (int s = 0; s < nsplit; ++s)
-      for (int hl = 0; hl < 2; ++hl)
-        for (int t = 0; t < 9; ++t)
+      for (int t = 0; t < ntypes; ++t)
+        for (int o = 0; o < prog[t].nops; ++o) {
+          const TcOp& op = prog[t].ops[o];
+          const int nblk = op.blk1 - op.blk0;
           for (int kc = 0; kc < kch; ++kc)
-            for (int r = 0; r < nrow; ++r)
-              for (int e = 0; e < 8; ++e) {
-                const int kz = 2 - r / ncta;  // rows [kz=2 | kz=1 | kz=0] <-> planes z-1,z,z+1
-                const int co = s * ncta + r % ncta, ci = kc * 8 + e;
-                const float w = packed[((size_t)(kz * 9 + t) * cin + ci) * cout + co];
-                const uint16_t hi = bf16_rn_bits(w);
-                const uint16_t lo = bf16_rn_bits(w - bf16_bits_to_float(hi));
-                const size_t off = (size_t)s * image_bytes / 2 +
-                                   ((((size_t)hl * 9 + t) * kch + kc) * nrow + r) * 8 + e;
-                img[off] = hl ? lo : hi;
-              }
+            for (int b = 0; b < nblk; ++b)
+              for (int j = 0; j < ncta; ++j)
+                for (int e = 0; e < 8; ++e) {
+                  const int tap = prog[t].blks[op.blk0 + b].tap;
+                  const int ci = kc * 8 + e, co = s * ncta + j;
+                  const float w = packed[((size_t)tap * cin + ci) * cout + co];
+                  const uint16_t hi = bf16_rn_bits(w);
+                  const uint16_t lo = bf16_rn_bits(w - bf16_bits_to_float(hi));
+                  const size_t off = (size_t)s * image_bytes / 2 + op.b_off / 2 +
+                                     ((size_t)kc * nblk * ncta + (size_t)b * ncta + j) * 8 + e;
+                  img[off] = hi;
+                  img[off + hi_bytes / 2] = lo;
+                }
+        }
     if (cudaMalloc(&dev, img.size() * 2) != cudaSuccess ||
         cudaMemcpy(dev, img.data(), img.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
       if (err) *err = "TcWeights: device upload failed";
@@ -118,6 +268,11 @@ struct TcWeights {
       return false;
     }
     return true;
+  }
+  bool build(const float* packed, int cin, int cout, int m, std::string* err) {
+    if (m == TC_S1) return build_mode<TC_S1>(packed, cin, cout, err);
+    if (m == TC_S2) return build_mode<TC_S2>(packed, cin, cout, err);
+    return build_mode<TC_T>(packed, cin, cout, err);
   }
 };
 
@@ -147,6 +302,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     if (ok) return;
   }
   atomicExch(err, 1);
+}
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, int* err,
+                                                unsigned long long& acc, bool timed) {
+  if (!timed) {
+    mbar_wait(bar, parity, err);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, err);
+  acc += (unsigned long long)(clock64() - t0);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// bump the 14-bit start-address field of a descriptor (low word only: no carry into the
+// LBO field as long as the operand stays inside the 256 KB shared window)
+__device__ __forceinline__ void desc_add(uint64_t& d, uint32_t inc16) {
+  asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tadd.u32 lo, lo, %1;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t}\n"
+      : "+l"(d)
+      : "r"(inc16));
+}
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
+  return ((uint64_t)hi << 32) | lo;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile(
@@ -197,6 +380,19 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
+// zero NC accumulator columns of this warp's 32 TMEM lanes
+template <int NC>
+__device__ __forceinline__ void tmem_zero(uint32_t taddr) {
+#pragma unroll
+  for (int c = 0; c < NC; c += 16) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};\n" ::"r"(taddr + c),
+        "r"(0u)
+        : "memory");
+  }
+}
+
 __device__ __forceinline__ void split_store(const float v[8], uint8_t* hi_dst, uint8_t* lo_dst) {
   uint32_t h[4], l[4];
 #pragma unroll
@@ -212,21 +408,34 @@ __device__ __forceinline__ void split_store(const float v[8], uint8_t* hi_dst, u
 }
 
 // ----------------------------------------------------------------------------------
-// loaders: 8 consecutive channels [c0, c0+8) of input voxel (z, y, x), in bounds
+// loaders: 8 consecutive channels [c0, c0+8) of input voxel (z, y, x), in bounds.
+// issue() only starts the global loads (so several items are in flight per thread),
+// finish() applies the fused transform.
 // ----------------------------------------------------------------------------------
 struct SrcLoader8 {
   Src s;
   int C, H, W;
-  __device__ __forceinline__ void load8(int z, int y, int x, int c0, float v[8]) const {
+  static constexpr int BATCH = 3;
+  struct Raw {
+    float4 a[2][2];
+  };
+  __device__ __forceinline__ void issue(int z, int y, int x, int c0, Raw& r) const {
     const long long base = (((long long)z * H + y) * W + x) * C + c0;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (t < s.n) {
+        r.a[t][0] = __ldg(reinterpret_cast<const float4*>(s.t[t].x + base));
+        r.a[t][1] = __ldg(reinterpret_cast<const float4*>(s.t[t].x + base) + 1);
+      }
+  }
+  __device__ __forceinline__ void finish(const Raw& r, int c0, float v[8]) const {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       if (t < s.n) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(s.t[t].x + base));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(s.t[t].x + base) + 1);
-        float u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float u[8] = {r.a[t][0].x, r.a[t][0].y, r.a[t][0].z, r.a[t][0].w,
+                      r.a[t][1].x, r.a[t][1].y, r.a[t][1].z, r.a[t][1].w};
         if (s.t[t].scale) {
           const float4 s0 = __ldg(reinterpret_cast<const float4*>(s.t[t].scale + c0));
           const float4 s1 = __ldg(reinterpret_cast<const float4*>(s.t[t].scale + c0) + 1);
@@ -254,14 +463,19 @@ struct SrcLoader8 {
 
 struct WarpLoader8 {
   WarpLoader w;
-  __device__ __forceinline__ void load8(int z, int y, int x, int c0, float v[8]) const {
+  static constexpr int BATCH = 1;
+  struct Raw {
+    float4 t[4][2];
+    float wt[4];
+  };
+  __device__ __forceinline__ void issue(int z, int y, int x, int c0, Raw& r) const {
     c0 += w.first;
-    if (c0 < w.C) {
+    if (c0 < w.C) {  // cur half: exact stride-lattice fetch, single tap of weight 1
       const float* p = w.cur + ((long long)(y * w.g.step) * w.g.Wf + x * w.g.step) * w.C + c0;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      r.t[0][0] = __ldg(reinterpret_cast<const float4*>(p));
+      r.t[0][1] = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      r.wt[0] = 1.f;
+      r.wt[1] = r.wt[2] = r.wt[3] = 0.f;
       return;
     }
     c0 -= w.C;
@@ -269,17 +483,25 @@ struct WarpLoader8 {
     warp_coord(w.g, x, y, __ldg(w.depths + z), fx, fy);
     const Taps t = bilinear_taps(fx, fy, w.g.Hf, w.g.Wf);
 #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      r.wt[k] = t.w[k];
+      if (t.w[k] != 0.f) {
+        const float* p = w.prev + (long long)t.off[k] * w.C + c0;
+        r.t[k][0] = __ldg(reinterpret_cast<const float4*>(p));
+        r.t[k][1] = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      }
+    }
+  }
+  __device__ __forceinline__ void finish(const Raw& r, int, float v[8]) const {
+#pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (t.w[k] != 0.f) {
-        const float* p = w.prev + (long long)t.off[k] * w.C + c0;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-        v[0] = fmaf(t.w[k], a.x, v[0]); v[1] = fmaf(t.w[k], a.y, v[1]);
-        v[2] = fmaf(t.w[k], a.z, v[2]); v[3] = fmaf(t.w[k], a.w, v[3]);
-        v[4] = fmaf(t.w[k], b.x, v[4]); v[5] = fmaf(t.w[k], b.y, v[5]);
-        v[6] = fmaf(t.w[k], b.z, v[6]); v[7] = fmaf(t.w[k], b.w, v[7]);
+      if (r.wt[k] != 0.f) {
+        v[0] = fmaf(r.wt[k], r.t[k][0].x, v[0]); v[1] = fmaf(r.wt[k], r.t[k][0].y, v[1]);
+        v[2] = fmaf(r.wt[k], r.t[k][0].z, v[2]); v[3] = fmaf(r.wt[k], r.t[k][0].w, v[3]);
+        v[4] = fmaf(r.wt[k], r.t[k][1].x, v[4]); v[5] = fmaf(r.wt[k], r.t[k][1].y, v[5]);
+        v[6] = fmaf(r.wt[k], r.t[k][1].z, v[6]); v[7] = fmaf(r.wt[k], r.t[k][1].w, v[7]);
       }
     }
   }
@@ -288,10 +510,18 @@ struct WarpLoader8 {
 struct TcParams {
   const uint8_t* wimg;
   float* out;
-  int D, H, W, Cout;
+  double* stats;        // [Cout][2] sum / sum of squares of the raw conv output, or null
+  int Di, Hi, Wi;       // input volume
+  int Do, Ho, Wo, Cout; // output volume
+  int Mx, My;           // extent of the M grid (output grid; input grid for transposed)
   int tiles_x, tiles_y, nsplit, nseg, seg_len;
   int n_items;
+  uint32_t w_bytes, w_hi_bytes;
   int* err;
+  unsigned long long* role_cycles;  // optional [grid][8] role wait/busy cycle counters
+  int dbg;  // diagnosis only (DFM_TC_DEBUG): 1 loaders skip work, 2 epilogue skips, 4 no MMA,
+            // 8 loaders skip the proxy fence
+  TcProgram prog[2];
 };
 
 struct TcItem {
@@ -308,51 +538,57 @@ __device__ __forceinline__ TcItem tc_decode(const TcParams& p, int item) {
   it.x0 = tx * TC_BX;
   it.y0 = ty * TC_BY;
   it.z_lo = seg * p.seg_len;
-  it.z_hi = min(p.D, it.z_lo + p.seg_len);
+  it.z_hi = min(p.Do, it.z_lo + p.seg_len);
   return it;
 }
 
 // ----------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------
-template <int CIN, int NCTA, class Loader>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_s1_kernel(TcParams p, Loader ld) {
-  constexpr int KCH = CIN / 8;                      // 16-byte channel chunks of the weights
-  constexpr int NCG = CIN / TC_CG;                  // pipeline stages per input plane
-  constexpr int NROW = 3 * NCTA;                    // weight image rows (3 dz slots)
-  constexpr uint32_t TAP_BYTES = KCH * NROW * 16;   // one (dy,dx) tap, hi or lo
-  constexpr uint32_t W_BYTES = 2 * 9 * TAP_BYTES;
-  constexpr uint32_t A_LBO = TC_ROWS * 16, A_SBO = TC_PX * 16;
-  constexpr uint32_t A_HL = (TC_CG / 8) * TC_ROWS * 16;  // hi -> lo array offset in a stage
-  constexpr uint32_t B_LBO = NROW * 16, B_SBO = 128;
-  constexpr uint32_t TMEM_COLS = TC_NSLOT * NCTA;   // 256 or 128 (power of two >= 32)
+template <int MODE, int CIN, int NCTA, class Loader>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p,
+                                                                 const Loader ld) {
+  using M = TcMode<MODE>;
+  constexpr int NCH = M::CG / 8;                 // 16-byte channel chunks per stage
+  constexpr int NCG = CIN / M::CG;               // pipeline stages per input plane
+  constexpr uint32_t A_LBO = M::ROWS * 16;
+  constexpr uint32_t A_SBO = (MODE == TC_S2 ? 1 : 1) * M::PITCH * 16;
+  constexpr uint32_t A_HL = NCH * M::ROWS * 16;  // hi -> lo array offset in a stage
+  constexpr uint32_t STAGE_BYTES = 2 * A_HL;
+  constexpr uint32_t B_SBO = 128;
+  constexpr int SLOT_COLS = M::SLOT_BLOCKS * NCTA;
+  constexpr int TC_NSLOT = M::NSLOT;
+  constexpr uint32_t TMEM_COLS = TC_NSLOT * SLOT_COLS;  // 256 / 512
+  constexpr int NPOS = M::PXB * M::PYB;
+  constexpr int NITEM = (NPOS * NCH + TC_LOAD_THREADS - 1) / TC_LOAD_THREADS;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_s = smem;
-  uint8_t* a_s = smem + W_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + TC_NSTAGE * TC_STAGE_BYTES);
-  // bars: [0,NSTAGE) full_a, [NSTAGE,2NSTAGE) empty_a, then NSLOT full_acc, NSLOT empty_acc
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NSTAGE + 2 * TC_NSLOT);
+  uint8_t* a_s = smem + p.w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + M::NSTAGE * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * M::NSTAGE + 2 * M::NSLOT);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // shfl broadcast: tells the compiler the warp index is warp-uniform, so the role
+  // branches below are convergent and the MMA warp can use the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const uint32_t bar0 = smem_u32(bars);
   auto full_a = [&](int s) { return bar0 + 8u * s; };
-  auto empty_a = [&](int s) { return bar0 + 8u * (TC_NSTAGE + s); };
-  auto full_acc = [&](int s) { return bar0 + 8u * (2 * TC_NSTAGE + s); };
-  auto empty_acc = [&](int s) { return bar0 + 8u * (2 * TC_NSTAGE + TC_NSLOT + s); };
+  auto empty_a = [&](int s) { return bar0 + 8u * (M::NSTAGE + s); };
+  auto full_acc = [&](int s) { return bar0 + 8u * (2 * M::NSTAGE + s); };
+  auto empty_acc = [&](int s) { return bar0 + 8u * (2 * M::NSTAGE + TC_NSLOT + s); };
+  constexpr int MMA_WARP = TC_THREADS / 32 - 1;
 
-  // resident weights of this CTA's output-channel group (blockIdx.x % nsplit is constant
-  // over the items of a CTA because gridDim.x is a multiple of nsplit)
-  {
+  {  // resident weights of this CTA's output-channel group
     const int split = blockIdx.x % p.nsplit;
-    const uint4* src = reinterpret_cast<const uint4*>(p.wimg + (size_t)split * W_BYTES);
+    const uint4* src = reinterpret_cast<const uint4*>(p.wimg + (size_t)split * p.w_bytes);
     uint4* dst = reinterpret_cast<uint4*>(w_s);
-    for (uint32_t i = tid; i < W_BYTES / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+    for (uint32_t i = tid; i < p.w_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < TC_NSTAGE; ++s) {
-      mbar_init(full_a(s), 128);
+    for (int s = 0; s < M::NSTAGE; ++s) {
+      mbar_init(full_a(s), TC_LOAD_THREADS / 32);  // one arrival per loader warp
       mbar_init(empty_a(s), 1);
     }
     for (int s = 0; s < TC_NSLOT; ++s) {
@@ -361,7 +597,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_s1_kernel(TcParams p, L
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
                  "r"(TMEM_COLS));
@@ -371,125 +607,300 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_s1_kernel(TcParams p, L
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // Accumulators are always accumulated into (no "overwrite" MMA, which would force the
+  // dz-merged MMA to be split at the plane that starts a new accumulator): the epilogue
+  // re-zeroes a slot right after draining it, and all slots start at zero.
+  if (warp < 4) {
+    for (uint32_t c = 0; c < TMEM_COLS; c += 64)
+      tmem_zero<64>(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < MMA_WARP) {
     // ============================ loaders ============================
     const int lt = tid - 128;
-    constexpr int NITEM = (TC_PX * TC_PY * (TC_CG / 8) + 127) / 128;  // 720 / 128 -> 6
+    const int chunk = lt % NCH;
     uint32_t stage_ctr = 0;
+    const bool timed = p.role_cycles != nullptr && lt == 0;
+    unsigned long long t_wait_e = 0;
+    const long long t_begin = clock64();
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const TcItem it = tc_decode(p, item);
       int soff[NITEM], gx[NITEM], gy[NITEM];
       bool inb[NITEM], live[NITEM];
 #pragma unroll
       for (int k = 0; k < NITEM; ++k) {
-        const int i = lt + k * 128;
-        live[k] = i < TC_PX * TC_PY * (TC_CG / 8);
-        const int chunk = i % (TC_CG / 8), pos = i / (TC_CG / 8);
-        const int bx = pos % TC_PX, by = pos / TC_PX;
-        gx[k] = it.x0 - 1 + bx;
-        gy[k] = it.y0 - 1 + by;
-        inb[k] = live[k] && gx[k] >= 0 && gx[k] < p.W && gy[k] >= 0 && gy[k] < p.H;
-        soff[k] = (chunk * TC_ROWS + pos) * 16;
+        const int i = lt + k * TC_LOAD_THREADS;
+        live[k] = i < NPOS * NCH;
+        const int pos = i / NCH;
+        const int bx = pos % M::PXB, by = pos / M::PXB;
+        int row;
+        if (MODE == TC_S1) {
+          gx[k] = it.x0 - 1 + bx;
+          gy[k] = it.y0 - 1 + by;
+          row = by * M::PITCH + bx;
+        } else if (MODE == TC_S2) {
+          gx[k] = 2 * it.x0 - 1 + bx;
+          gy[k] = 2 * it.y0 - 1 + by;
+          row = (((bx & 1) * 2 + (by & 1)) * 17 + (by >> 1)) * M::PITCH + (bx >> 1);
+        } else {
+          gx[k] = it.x0 + bx;
+          gy[k] = it.y0 + by;
+          row = by * M::PITCH + bx;
+        }
+        inb[k] = live[k] && gx[k] >= 0 && gx[k] < p.Wi && gy[k] >= 0 && gy[k] < p.Hi;
+        soff[k] = (chunk * M::ROWS + row) * 16;
       }
-      const int chunk = lt % (TC_CG / 8);
-      const int zi0 = max(it.z_lo - 1, 0), zi1 = min(it.z_hi, p.D - 1);
+      const int zi0 = max(M::zi_first(it.z_lo), 0);
+      const int zi1 = min(M::zi_last(it.z_hi - 1), p.Di - 1);
       for (int zi = zi0; zi <= zi1; ++zi) {
 #pragma unroll 1
         for (int cg = 0; cg < NCG; ++cg, ++stage_ctr) {
-          const int s = stage_ctr % TC_NSTAGE;
-          mbar_wait(empty_a(s), ((stage_ctr / TC_NSTAGE) & 1) ^ 1, p.err);
-          uint8_t* st = a_s + s * TC_STAGE_BYTES;
+          const int s = stage_ctr % M::NSTAGE;
+          mbar_wait_timed(empty_a(s), ((stage_ctr / M::NSTAGE) & 1) ^ 1, p.err, t_wait_e, timed);
+          uint8_t* st = a_s + s * STAGE_BYTES;
+          const int c0 = cg * M::CG + chunk * 8;
+          if (!(p.dbg & 1))
 #pragma unroll
-          for (int k = 0; k < NITEM; ++k) {
-            if (!live[k]) continue;
-            float v[8];
-            if (inb[k]) {
-              ld.load8(zi, gy[k], gx[k], cg * TC_CG + chunk * 8, v);
-            } else {
+          for (int k0 = 0; k0 < NITEM; k0 += Loader::BATCH) {
+            typename Loader::Raw raw[Loader::BATCH];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            for (int b = 0; b < Loader::BATCH; ++b)
+              if (k0 + b < NITEM && inb[k0 + b]) ld.issue(zi, gy[k0 + b], gx[k0 + b], c0, raw[b]);
+#pragma unroll
+            for (int b = 0; b < Loader::BATCH; ++b) {
+              if (k0 + b < NITEM && live[k0 + b]) {
+                float v[8];
+                if (inb[k0 + b]) {
+                  ld.finish(raw[b], c0, v);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                }
+                split_store(v, st + soff[k0 + b], st + A_HL + soff[k0 + b]);
+              }
             }
-            split_store(v, st + soff[k], st + A_HL + soff[k]);
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(full_a(s));
+          if (!(p.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_a(s));
         }
       }
     }
-  } else if (warp == 8) {
+    if (timed) {
+      unsigned long long* rc = p.role_cycles + (size_t)blockIdx.x * 8;
+      rc[3] = (unsigned long long)(clock64() - t_begin);
+      rc[4] = t_wait_e;
+    }
+  } else if (warp == MMA_WARP) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    // One thread issues every MMA, so its scalar overhead per MMA must stay far below
+    // the ~47-56 cycles an MMA occupies the tensor pipe: descriptors are split into a
+    // constant high word and a low word that only needs integer adds, per-plane slot
+    // state is hoisted out of the op loop.  The whole warp executes the (warp-uniform)
+    // control flow so the compiler keeps descriptors in uniform registers; only the
+    // tcgen05 instructions themselves are predicated on lane 0.
+    {
+      const bool timed = p.role_cycles != nullptr;
+      const bool issuer = lane == 0;
+      unsigned long long t_wait_a = 0, t_wait_acc = 0;
+      const long long t_begin = clock64();
       const uint32_t w_base = smem_u32(w_s), a_base = smem_u32(a_s);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably uniform
+      constexpr uint32_t A_LBO16 = A_LBO >> 4, A_HL16 = A_HL >> 4;
+      const uint32_t a_desc_hi = (A_SBO >> 4) | (1u << 14);  // SBO | version
+      const uint32_t b_desc_hi = (B_SBO >> 4) | (1u << 14);
+      const uint32_t w_hi16 = p.w_hi_bytes >> 4;
       uint32_t stage_ctr = 0, plane_ctr = 0;  // plane_ctr: running index of output planes
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const TcItem it = tc_decode(p, item);
-        const int zi0 = max(it.z_lo - 1, 0), zi1 = min(it.z_hi, p.D - 1);
-        // output plane zo of this item lives in slot (plane_base + zo - z_lo) % NSLOT
-        const uint32_t plane_base = plane_ctr;
+        const int zi0 = max(M::zi_first(it.z_lo), 0);
+        const int zi1 = min(M::zi_last(it.z_hi - 1), p.Di - 1);
+        const uint32_t plane_base = plane_ctr;  // slot of output plane zo: (base + zo - z_lo) % NSLOT
         for (int zi = zi0; zi <= zi1; ++zi) {
-          const int zo_a = max(zi - 1, it.z_lo), zo_b = min(zi + 1, it.z_hi - 1);
-          // a slot is fresh when this is the first input plane that touches it
-          for (int zo = zo_a; zo <= zo_b; ++zo) {
-            if (zi == max(zo - 1, zi0)) {
-              const uint32_t j = plane_base + (zo - it.z_lo);
-              mbar_wait(empty_acc(j % TC_NSLOT), ((j / TC_NSLOT) & 1) ^ 1, p.err);
+          const TcProgram& pr = p.prog[M::ptype(zi)];
+          // per-plane state of the (up to) three output planes this input plane feeds
+          uint32_t vmask = 0, fmask = 0, colbase[3];
+#pragma unroll
+          for (int dz = -1; dz <= 1; ++dz) {
+            const int zo = M::zo_of(zi, dz);
+            const uint32_t j = plane_base + (uint32_t)(zo - it.z_lo);
+            colbase[dz + 1] = (j % TC_NSLOT) * SLOT_COLS;
+            if (zo >= it.z_lo && zo < it.z_hi) {
+              vmask |= 1u << (dz + 1);
+              if (zi == max(M::zi_first(zo), zi0)) {
+                fmask |= 1u << (dz + 1);
+                // a slot that starts with this input plane must have been drained
+                mbar_wait_timed(empty_acc(j % TC_NSLOT), ((j / TC_NSLOT) & 1) ^ 1, p.err,
+                                t_wait_acc, timed);
+              }
             }
           }
+          const bool regular = (vmask & pr.need) == pr.need;
+          // bit k: the slot ring wraps between the planes dz = k-1 and dz = k
+          const uint32_t wrapmask = (colbase[1] != colbase[0] + SLOT_COLS ? 1u : 0u) |
+                                    (colbase[2] != colbase[1] + SLOT_COLS ? 2u : 0u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
           for (int cg = 0; cg < NCG; ++cg, ++stage_ctr) {
-            const int s = stage_ctr % TC_NSTAGE;
-            mbar_wait(full_a(s), (stage_ctr / TC_NSTAGE) & 1, p.err);
+            const int s = stage_ctr % M::NSTAGE;
+            mbar_wait_timed(full_a(s), (stage_ctr / M::NSTAGE) & 1, p.err, t_wait_a, timed);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_st = a_base + s * TC_STAGE_BYTES;
-#pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t a_tap = a_st + ((tap / 3) * TC_PX + tap % 3) * 16;
-              const uint32_t b_tap = w_base + tap * TAP_BYTES + (cg * (TC_CG / 8)) * B_LBO;
-              // runs of output planes with the same fresh state, not crossing the ring end
-              int zo = zo_a;
-              while (zo <= zo_b) {
-                const bool fresh = (cg == 0 && tap == 0) && (zi == max(zo - 1, zi0));
-                const uint32_t j0 = plane_base + (zo - it.z_lo);
-                int zend = zo;
-                while (zend + 1 <= zo_b &&
-                       ((cg == 0 && tap == 0) && (zi == max(zend, zi0))) == fresh &&
-                       (j0 + (zend + 1 - zo)) % TC_NSLOT != 0)
-                  ++zend;
-                const int nrun = zend - zo + 1;
-                const uint32_t n0 = (uint32_t)(zo - (zi - 1)) * NCTA;  // first weight-image row
-                const uint32_t d_tmem = tmem_base + (j0 % TC_NSLOT) * NCTA;
-                const uint32_t idesc = idesc_bf16(nrun * NCTA);
+            const uint32_t a_lo_stage =
+                (((a_base + s * STAGE_BYTES) >> 4) & 0x3FFF) | (A_LBO16 << 16);
+            bool done = false;
+            if constexpr (MODE == TC_S1) {
+              // Stride-1 issue sequence: the live output planes form one contiguous range
+              // of the three dz slots, cut only where the accumulator ring wraps.  Per piece
+              // a rolled loop over the 9 taps with persistent descriptors whose low words
+              // are bumped by uniform adds (the issuing warp is serial in scalar work +
+              // ~47 cycles per tcgen05.mma issue, so scalar work per MMA must be ~1 op).
+              constexpr uint32_t B_LBO16 = 3 * NCTA;               // weight image rows
+              constexpr uint32_t TAP16 = (CIN / 8) * B_LBO16;      // one tap, 16-byte units
+              constexpr int NKS = M::CG / 16;
+              const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFF) + (uint32_t)(cg * NCH) * B_LBO16 +
+                                     (B_LBO16 << 16);
+              // first / one-past-last live plane index (0..3) of this input plane
+              const int pa = (vmask & 1u) ? 0 : (vmask & 2u) ? 1 : 2;
+              const int pb = (vmask & 4u) ? 3 : (vmask & 2u) ? 2 : 1;
+              int first = pa;
+              while (first < pb) {
+                int last = first + 1;  // exclusive
+                while (last < pb && !((wrapmask >> (last - 1)) & 1u)) ++last;
+                const uint32_t cb0 = first == 0 ? colbase[0] : first == 1 ? colbase[1] : colbase[2];
+                const uint32_t d0 = tmem_u + cb0;
+                const uint32_t idesc = idesc_bf16((last - first) * NCTA);
+                uint64_t da[NKS][2], db[NKS][2];
 #pragma unroll
-                for (int ks = 0; ks < TC_CG / 16; ++ks) {
-                  const uint32_t a_hi = a_tap + 2 * ks * A_LBO, a_lo = a_hi + A_HL;
-                  const uint32_t b_hi = b_tap + 2 * ks * B_LBO + n0 * 16;
-                  const uint32_t b_lo = b_hi + 9 * TAP_BYTES;
-                  const uint64_t dah = umma_desc(a_hi, A_LBO, A_SBO);
-                  const uint64_t dal = umma_desc(a_lo, A_LBO, A_SBO);
-                  const uint64_t dbh = umma_desc(b_hi, B_LBO, B_SBO);
-                  const uint64_t dbl = umma_desc(b_lo, B_LBO, B_SBO);
-                  umma_bf16(d_tmem, dah, dbh, idesc, (fresh && ks == 0) ? 0u : 1u);
-                  umma_bf16(d_tmem, dal, dbh, idesc, 1u);
-                  umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+                for (int ks = 0; ks < NKS; ++ks) {
+                  da[ks][0] = pack64(a_lo_stage + 2 * ks * A_LBO16, a_desc_hi);
+                  da[ks][1] = pack64(a_lo_stage + 2 * ks * A_LBO16 + A_HL16, a_desc_hi);
+                  const uint32_t bl = b_lo0 + 2 * ks * B_LBO16 + (uint32_t)first * NCTA;
+                  db[ks][0] = pack64(bl, b_desc_hi);
+                  db[ks][1] = pack64(bl + w_hi16, b_desc_hi);
                 }
-                zo = zend + 1;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                  if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ++ks) {
+                      umma_bf16(d0, da[ks][0], db[ks][0], idesc, 1u);
+                      umma_bf16(d0, da[ks][1], db[ks][0], idesc, 1u);
+                      umma_bf16(d0, da[ks][0], db[ks][1], idesc, 1u);
+                    }
+                  }
+                  const uint32_t ainc = (tap == 2 || tap == 5) ? (uint32_t)(M::PITCH - 2) : 1u;
+#pragma unroll
+                  for (int ks = 0; ks < NKS; ++ks) {
+                    desc_add(da[ks][0], ainc);
+                    desc_add(da[ks][1], ainc);
+                    desc_add(db[ks][0], TAP16);
+                    desc_add(db[ks][1], TAP16);
+                  }
+                }
+                first = last;
+              }
+              done = true;
+            }
+            if (!done) {
+#pragma unroll 1
+            for (int o = 0; o < pr.nops; ++o) {
+              const TcOp op = pr.ops[o];
+              const uint32_t a_lo_op = a_lo_stage + (op.a_off >> 4);
+              const uint32_t b_lbo16 = op.b_lbo >> 4;
+              const uint32_t b_lo_op = (((w_base + op.b_off) >> 4) & 0x3FFF) +
+                                       (uint32_t)(cg * NCH) * b_lbo16 + (b_lbo16 << 16);
+              const uint32_t fm = 0u;  // accumulators are pre-zeroed: always accumulate
+              auto issue = [&](uint32_t col0, uint32_t blk_rel, uint32_t nblk, uint32_t fresh) {
+                const uint32_t idesc = idesc_bf16((int)(nblk * NCTA));
+                const uint32_t d_tmem = tmem_u + col0;
+                const uint32_t b_lo_run = b_lo_op + blk_rel * NCTA;
+#pragma unroll
+                for (int ks = 0; ks < M::CG / 16; ++ks) {
+                  const uint64_t dah = pack64(a_lo_op + 2 * ks * A_LBO16, a_desc_hi);
+                  const uint64_t dal = pack64(a_lo_op + 2 * ks * A_LBO16 + A_HL16, a_desc_hi);
+                  const uint64_t dbh = pack64(b_lo_run + 2 * ks * b_lbo16, b_desc_hi);
+                  const uint64_t dbl = pack64(b_lo_run + 2 * ks * b_lbo16 + w_hi16, b_desc_hi);
+                  if (elect_one()) {
+                    umma_bf16(d_tmem, dah, dbh, idesc, (fresh && ks == 0) ? 0u : 1u);
+                    umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+                    umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+                  }
+                }
+              };
+              if (regular && fm == 0) {
+                // fast path: the host-precomputed runs, split only where the slot ring wraps
+                for (uint32_t r = 0; r < op.nruns; ++r) {
+                  const uint32_t rc = op.runs[r];
+                  const uint32_t nblk = rc & 15u, bs = (rc >> 4) & 15u, dzc = (rc >> 8) & 3u;
+                  const uint32_t cb = (rc >> 10) & 3u, bpp = (rc >> 12) & 15u, npl = (rc >> 16) & 3u;
+                  uint32_t p0 = npl;
+                  if (npl == 3u) {
+                    if (wrapmask & 1u) p0 = 1u; else if (wrapmask & 2u) p0 = 2u;
+                  } else if (npl == 2u) {
+                    if (wrapmask & (1u << dzc)) p0 = 1u;
+                  }
+                  const uint32_t cbase = dzc == 0u ? colbase[0] : dzc == 1u ? colbase[1] : colbase[2];
+                  if (p0 == npl) {
+                    issue(cbase + cb * NCTA, bs, nblk, 0u);
+                  } else {
+                    issue(cbase + cb * NCTA, bs, p0 * bpp, 0u);
+                    const uint32_t d2 = dzc + p0;
+                    const uint32_t cbase2 = d2 == 1u ? colbase[1] : colbase[2];
+                    issue(cbase2 + cb * NCTA, bs + p0 * bpp, (npl - p0) * bpp, 0u);
+                  }
+                }
+              } else {
+                int b = op.blk0;
+                while (b < op.blk1) {
+                  const TcBlk bk = pr.blks[b];
+                  const uint32_t bit = 1u << (bk.dz + 1);
+                  if (!(vmask & bit)) {
+                    ++b;
+                    continue;
+                  }
+                  const uint32_t fresh = fm & bit;
+                  const uint32_t col0 = colbase[bk.dz + 1] + bk.colblk * NCTA;
+                  int e = b + 1;
+                  while (e < op.blk1 && (e - b) * NCTA < 256) {
+                    const TcBlk bn = pr.blks[e];
+                    const uint32_t bitn = 1u << (bn.dz + 1);
+                    if (!(vmask & bitn) || ((fm & bitn) != 0) != (fresh != 0) ||
+                        colbase[bn.dz + 1] + bn.colblk * NCTA != col0 + (uint32_t)(e - b) * NCTA)
+                      break;
+                    ++e;
+                  }
+                  issue(col0, (uint32_t)(b - op.blk0), (uint32_t)(e - b), fresh);
+                  b = e;
+                }
               }
             }
-            umma_commit(empty_a(s));  // stage may be refilled once these MMAs retire
+            }
+            if (elect_one()) umma_commit(empty_a(s));  // stage refillable once these MMAs retire
+            __syncwarp();
           }
-          // completed output planes
-          if (zi - 1 >= it.z_lo) {
-            const uint32_t j = plane_base + (zi - 1 - it.z_lo);
-            umma_commit(full_acc(j % TC_NSLOT));
-          }
-          if (zi == zi1 && zi <= it.z_hi - 1) {
-            const uint32_t j = plane_base + (zi - it.z_lo);
-            umma_commit(full_acc(j % TC_NSLOT));
+          // output planes whose last contribution was this input plane
+#pragma unroll
+          for (int dz = -1; dz <= 1; ++dz) {
+            const int zo = M::zo_of(zi, dz);
+            if ((vmask >> (dz + 1)) & 1u) {
+              if (zi == min(M::zi_last(zo), zi1)) {
+                const uint32_t j = plane_base + (uint32_t)(zo - it.z_lo);
+                if (elect_one()) umma_commit(full_acc(j % TC_NSLOT));
+              }
+            }
           }
         }
         plane_ctr += it.z_hi - it.z_lo;
+      }
+      if (timed && issuer) {
+        unsigned long long* rc = p.role_cycles + (size_t)blockIdx.x * 8;
+        rc[0] = (unsigned long long)(clock64() - t_begin);
+        rc[1] = t_wait_a;
+        rc[2] = t_wait_acc;
       }
     }
     __syncwarp();
@@ -497,35 +908,94 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_s1_kernel(TcParams p, L
     // ============================ epilogue (warps 0-3) ============================
     uint32_t plane_ctr = 0;
     const int m = warp * 32 + lane;  // accumulator row == TMEM lane
+    const bool timed = p.role_cycles != nullptr && tid == 0;
+    unsigned long long t_wait_f = 0;
+    const long long t_begin = clock64();
+    float ssum[NCTA], ssq[NCTA];
+#pragma unroll
+    for (int i = 0; i < NCTA; ++i) ssum[i] = ssq[i] = 0.f;
+    int cur_split = -1;
+    auto flush_stats = [&]() {
+      if (!p.stats || cur_split < 0) return;
+#pragma unroll
+      for (int i = 0; i < NCTA; ++i) {
+        double a = ssum[i], b = ssq[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) {
+          atomicAdd(p.stats + 2 * (cur_split * NCTA + i), a);
+          atomicAdd(p.stats + 2 * (cur_split * NCTA + i) + 1, b);
+        }
+        ssum[i] = ssq[i] = 0.f;
+      }
+    };
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const TcItem it = tc_decode(p, item);
-      const int x = it.x0 + (m & 7), y = it.y0 + (m >> 3);
-      const bool ok = x < p.W && y < p.H;
+      cur_split = it.split;
+      const int mx = it.x0 + (m & 7), my = it.y0 + (m >> 3);
+      const bool ok = mx < p.Mx && my < p.My;
       for (int zo = it.z_lo; zo < it.z_hi; ++zo, ++plane_ctr) {
         const int slot = plane_ctr % TC_NSLOT;
-        mbar_wait(full_acc(slot), (plane_ctr / TC_NSLOT) & 1, p.err);
+        mbar_wait_timed(full_acc(slot), (plane_ctr / TC_NSLOT) & 1, p.err, t_wait_f, timed);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t r[NCTA];
-        tmem_ld<NCTA>(tmem_base + ((uint32_t)(warp * 32) << 16) + slot * NCTA, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_acc(slot));
-        if (ok) {
-          float4* dst = reinterpret_cast<float4*>(
-              p.out + (((long long)zo * p.H + y) * p.W + x) * p.Cout + it.split * NCTA);
+        if (p.dbg & 2) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty_acc(slot));
+          continue;
+        }
 #pragma unroll
-          for (int q = 0; q < NCTA / 4; ++q)
-            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                 __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+        for (int cb = 0; cb < M::SLOT_BLOCKS; ++cb) {
+          uint32_t r[NCTA];
+          tmem_ld<NCTA>(tmem_base + ((uint32_t)(warp * 32) << 16) + slot * SLOT_COLS + cb * NCTA, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tmem_zero<NCTA>(tmem_base + ((uint32_t)(warp * 32) << 16) + slot * SLOT_COLS + cb * NCTA);
+          if (cb == M::SLOT_BLOCKS - 1) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_acc(slot));
+          }
+          if (ok) {
+            int xo = mx, yo = my;
+            if (MODE == TC_T) {  // class order (0,0), (1,0), (1,1), (0,1)
+              xo = 2 * mx + ((cb == 1 || cb == 2) ? 1 : 0);
+              yo = 2 * my + (cb >= 2 ? 1 : 0);
+            }
+            float4* dst = reinterpret_cast<float4*>(
+                p.out + (((long long)zo * p.Ho + yo) * p.Wo + xo) * p.Cout + it.split * NCTA);
+#pragma unroll
+            for (int q = 0; q < NCTA / 4; ++q)
+              dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            if (p.stats) {
+#pragma unroll
+              for (int i = 0; i < NCTA; ++i) {
+                const float v = __uint_as_float(r[i]);
+                ssum[i] += v;
+                ssq[i] = fmaf(v, v, ssq[i]);
+              }
+            }
+          }
         }
       }
+      // a CTA keeps one output-channel group, so one flush per item keeps the fp32
+      // partial sums short (<= planes-per-item * classes values per thread)
+      flush_stats();
+    }
+    if (timed) {
+      unsigned long long* rc = p.role_cycles + (size_t)blockIdx.x * 8;
+      rc[5] = (unsigned long long)(clock64() - t_begin);
+      rc[6] = t_wait_f;
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8)
+  if (warp == MMA_WARP)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(TMEM_COLS));
 }
@@ -556,56 +1026,70 @@ inline int tc_consume_error() {
   }
   return h;
 }
+inline int tc_sm_count() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return cached;
+}
 
-template <int CIN, int NCTA, class Loader>
-bool tc_launch(const Loader& ld, const TcWeights& w, float* out, const ConvGeom& g,
-               cudaStream_t st, std::string* err) {
-  constexpr int KCH = CIN / 8, NROW = 3 * NCTA;
-  constexpr size_t W_BYTES = (size_t)2 * 9 * KCH * NROW * 16;
-  const size_t smem = W_BYTES + (size_t)TC_NSTAGE * TC_STAGE_BYTES +
-                      (2 * TC_NSTAGE + 2 * TC_NSLOT) * 8 + 16;
-  static bool attr_set = false;
-  auto kern = conv_tc_s1_kernel<CIN, NCTA, Loader>;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess) {
-      if (err) *err = "conv_tc: cannot reserve shared memory";
+template <int MODE, int CIN, int NCTA, class Loader>
+bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
+               const ConvGeom& g, cudaStream_t st, std::string* err) {
+  using M = TcMode<MODE>;
+  constexpr size_t STAGE_BYTES = (size_t)2 * (M::CG / 8) * M::ROWS * 16;
+  const size_t smem = w.image_bytes + M::NSTAGE * STAGE_BYTES +
+                      (2 * M::NSTAGE + 2 * M::NSLOT) * 8 + 16;
+  auto kern = conv_tc_kernel<MODE, CIN, NCTA, Loader>;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    if (smem > 232448 ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) {
+      if (err) *err = "conv_tc: cannot reserve " + std::to_string(smem) + " B of shared memory";
       return false;
     }
-    attr_set = true;
+    attr_smem = smem;
   }
-  int sms = 148;
-  {
-    static int cached = 0;
-    if (!cached) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    }
-    sms = cached;
-  }
+  const int sms = tc_sm_count();
   TcParams p{};
   p.wimg = w.dev;
   p.out = out;
-  p.D = g.Do;
-  p.H = g.Ho;
-  p.W = g.Wo;
+  p.stats = stats;
+  p.Di = g.Di; p.Hi = g.Hi; p.Wi = g.Wi;
+  p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
   p.Cout = g.Cout;
-  p.tiles_x = (g.Wo + TC_BX - 1) / TC_BX;
-  p.tiles_y = (g.Ho + TC_BY - 1) / TC_BY;
+  p.Mx = MODE == TC_T ? g.Wi : g.Wo;
+  p.My = MODE == TC_T ? g.Hi : g.Ho;
+  p.tiles_x = (p.Mx + TC_BX - 1) / TC_BX;
+  p.tiles_y = (p.My + TC_BY - 1) / TC_BY;
   p.nsplit = w.nsplit;
+  p.w_bytes = w.image_bytes;
+  p.w_hi_bytes = w.hi_bytes;
+  p.prog[0] = w.prog[0];
+  p.prog[1] = w.prog[1];
   const int base = p.tiles_x * p.tiles_y * p.nsplit;
   const int grid_cap = std::max(p.nsplit, sms / p.nsplit * p.nsplit);
-  // z segments: balance the persistent grid against the two halo planes a cut costs
+  // z segments (in output planes; even lengths for the transposed conv): balance the
+  // persistent grid against the halo planes a cut costs
+  const int unit = MODE == TC_T ? 2 : 1;
+  const int halo = MODE == TC_S1 ? 2 : 1;
   int best_seg = 1;
   double best_cost = 1e30;
-  for (int ns = 1; ns <= std::min(g.Do, 16); ++ns) {
-    const int len = (g.Do + ns - 1) / ns;
+  p.seg_len = g.Do;
+  for (int ns = 1; ns <= std::min(g.Do / unit, 16); ++ns) {
+    int len = (g.Do + ns - 1) / ns;
+    len = (len + unit - 1) / unit * unit;
     const int nseg = (g.Do + len - 1) / len;
     const long long items = (long long)base * nseg;
     const long long grid = std::min<long long>(items, grid_cap);
     const long long rounds = (items + grid - 1) / grid;
-    const double cost = (double)rounds * (len + 2);
+    const double planes_in = MODE == TC_S2 ? 2.0 * len + 1 : MODE == TC_T ? len / 2.0 + 1 : len + 2;
+    const double cost = (double)rounds * planes_in;
+    (void)halo;
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best_seg = nseg;
@@ -617,7 +1101,29 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, const ConvGeom&
   p.err = tc_err_flag().get();
   int grid = std::min(p.n_items, grid_cap);
   grid = std::max(p.nsplit, grid / p.nsplit * p.nsplit);
+  static const bool role_dbg = getenv("DFM_TC_ROLE_CYCLES") != nullptr;
+  static const int dbg_flags = getenv("DFM_TC_DEBUG") ? atoi(getenv("DFM_TC_DEBUG")) : 0;
+  p.dbg = dbg_flags;
+  static unsigned long long* role_buf = nullptr;
+  if (role_dbg) {
+    if (!role_buf) cudaMalloc(&role_buf, 1024 * 8 * sizeof(unsigned long long));
+    cudaMemsetAsync(role_buf, 0, 1024 * 8 * sizeof(unsigned long long), st);
+    p.role_cycles = role_buf;
+  }
   kern<<<grid, TC_THREADS, smem, st>>>(p, ld);
+  if (role_dbg) {  // debugging aid: synchronous, prints mean cycles per role
+    cudaStreamSynchronize(st);
+    std::vector<unsigned long long> h((size_t)grid * 8);
+    cudaMemcpy(h.data(), role_buf, h.size() * 8, cudaMemcpyDeviceToHost);
+    double a[8] = {0};
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)b * 8 + k] / grid;
+    fprintf(stderr,
+            "[tc mode=%d cin=%d ncta=%d grid=%d items=%d seg=%d] mma: total %.0f wait_full_a %.0f "
+            "wait_empty_acc %.0f | load: total %.0f wait_empty_a %.0f | epi: total %.0f "
+            "wait_full_acc %.0f\n",
+            MODE, CIN, NCTA, grid, p.n_items, p.seg_len, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+  }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("conv_tc launch: ") + cudaGetErrorString(e);
@@ -627,27 +1133,45 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, const ConvGeom&
 }
 
 template <class Loader>
-bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, const ConvGeom& g,
-                 cudaStream_t st, std::string* err) {
-  if (g.Cin == 32) return tc_launch<32, 32, Loader>(ld, w, out, g, st, err);
-  if (g.Cin == 64) return tc_launch<64, 16, Loader>(ld, w, out, g, st, err);
-  if (err) *err = "conv_tc: unsupported Cin";
+bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats,
+                 const ConvGeom& g, cudaStream_t st, std::string* err) {
+  const int mode = tc_mode_of(g);
+  if (mode != w.mode) {
+    if (err) *err = "conv_tc: weight image was built for a different conv mode";
+    return false;
+  }
+#define TC_CASE(MD, CI, NC) \
+  if (mode == MD && g.Cin == CI) return tc_launch<MD, CI, NC, Loader>(ld, w, out, stats, g, st, err)
+  TC_CASE(TC_S1, 32, 32);
+  TC_CASE(TC_S1, 64, 16);
+  TC_CASE(TC_S2, 32, 32);
+  TC_CASE(TC_S2, 64, 16);
+  TC_CASE(TC_T, 64, 16);
+#undef TC_CASE
+  if (err) *err = "conv_tc: unsupported (mode, Cin)";
   return false;
 }
 
-inline bool tc_conv_src(const Src& s, const TcWeights& w, float* out, const ConvGeom& g,
-                        cudaStream_t st, std::string* err) {
+inline bool tc_conv_src(const Src& s, const TcWeights& w, float* out, double* stats,
+                        const ConvGeom& g, cudaStream_t st, std::string* err) {
   if (s.n > 2) {
     if (err) *err = "conv_tc: at most two input terms";
     return false;
   }
   SrcLoader8 ld{s, g.Cin, g.Hi, g.Wi};
-  return tc_dispatch(ld, w, out, g, st, err);
+  return tc_dispatch(ld, w, out, stats, g, st, err);
 }
-inline bool tc_conv_warp(const WarpLoader& wl, const TcWeights& w, float* out,
+inline bool tc_conv_warp(const WarpLoader& wl, const TcWeights& w, float* out, double* stats,
                          const ConvGeom& g, cudaStream_t st, std::string* err) {
+  if (tc_mode_of(g) != TC_S1) {
+    if (err) *err = "conv_tc: the warp loader feeds stride-1 convs only";
+    return false;
+  }
   WarpLoader8 ld{wl};
-  return tc_dispatch(ld, w, out, g, st, err);
+  if (g.Cin == 32) return tc_launch<TC_S1, 32, 32, WarpLoader8>(ld, w, out, stats, g, st, err);
+  if (g.Cin == 64) return tc_launch<TC_S1, 64, 16, WarpLoader8>(ld, w, out, stats, g, st, err);
+  if (err) *err = "conv_tc: unsupported Cin";
+  return false;
 }
 
 }  // namespace dfm

@@ -163,7 +163,9 @@ int upload(DevBuf& b, const float* h, size_t n) {
   return DFM_OK;
 }
 
-int set_conv(ConvW& cw, const float* h, long long numel, int Cin, int Cout, int transposed) {
+// tc_mode: dfm::TC_S1 / TC_S2 / TC_T, or -1 for "no tensor-core kernel for this layer"
+int set_conv(ConvW& cw, const float* h, long long numel, int Cin, int Cout, int transposed,
+             int tc_mode) {
   if (numel != (long long)27 * Cin * Cout)
     return fail(DFM_ERR_INVALID, "conv weight has wrong element count");
   cw.Cin = Cin;
@@ -171,9 +173,10 @@ int set_conv(ConvW& cw, const float* h, long long numel, int Cin, int Cout, int 
   cw.transposed = transposed;
   const std::vector<float> p = repack_simt(h, Cin, Cout, transposed);
   DFM_TRY(upload(cw.simt, p.data(), p.size()));
-  if (dfm::tc_supported(Cin, Cout, transposed)) {
+  cw.tc.release();
+  if (tc_mode >= 0 && dfm::tc_supported(Cin, Cout, transposed)) {
     std::string err;
-    if (!cw.tc.build(p.data(), Cin, Cout, &err)) return fail(DFM_ERR_CUDA, err);
+    if (!cw.tc.build(p.data(), Cin, Cout, tc_mode, &err)) return fail(DFM_ERR_CUDA, err);
   }
   return DFM_OK;
 }
@@ -261,40 +264,11 @@ int conv_simt_dispatch(const L& ld, const ConvW& w, float* out, const dfm::ConvG
                                    ", " + std::to_string(g.Cout) + ")");
 }
 
-// conv with a Src-transform input; picks the tensor-core kernel when allowed/available
-int run_conv(const dfm::Src& s, const ConvW& w, float* out, const dfm::ConvGeom& g, int impl,
-             cudaStream_t st) {
-  const bool tc_ok = w.tc.ready() && dfm::tc_geom_supported(g);
-  if (impl == DFM_CONV_TC && !tc_ok)
-    return fail(DFM_ERR_INVALID, "conv3d: no tensor-core kernel for this layer");
-  if (impl != DFM_CONV_SIMT && tc_ok) {
-    std::string err;
-    ProfScope ps(conv_class("conv_tc", g, "src"), conv_flops(g), st);
-    if (!dfm::tc_conv_src(s, w.tc, out, g, st, &err)) return fail(DFM_ERR_CUDA, err);
-    g_launches.fetch_add(1);
-    g_tc_launches.fetch_add(1);
-    return DFM_OK;
-  }
-  dfm::SrcLoader ld{s, g.Cin, g.Hi, g.Wi};
-  ProfScope ps(conv_class("conv_simt", g, "src"), conv_flops(g), st);
-  return conv_simt_dispatch(ld, w, out, g, st);
-}
-
-int run_conv_warp(const dfm::WarpLoader& ld, const ConvW& w, float* out, const dfm::ConvGeom& g,
-                  int impl, cudaStream_t st) {
-  const bool tc_ok = w.tc.ready() && dfm::tc_geom_supported(g);
-  if (impl == DFM_CONV_TC && !tc_ok)
-    return fail(DFM_ERR_INVALID, "conv3d(warp): no tensor-core kernel for this layer");
-  if (impl != DFM_CONV_SIMT && tc_ok) {
-    std::string err;
-    ProfScope ps(conv_class("conv_tc", g, "warp"), conv_flops(g), st);
-    if (!dfm::tc_conv_warp(ld, w.tc, out, g, st, &err)) return fail(DFM_ERR_CUDA, err);
-    g_launches.fetch_add(1);
-    g_tc_launches.fetch_add(1);
-    return DFM_OK;
-  }
-  ProfScope ps(conv_class("conv_simt", g, "warp"), conv_flops(g), st);
-  return conv_simt_dispatch(ld, w, out, g, st);
+int gn_finalize(Norm& n, long long V, int groups, cudaStream_t st) {
+  dfm::gn_finalize_kernel<<<1, 64, 0, st>>>(n.sums, n.gamma.p, n.beta.p, n.C, groups, (double)V,
+                                           1e-5f, n.scale.p, n.shift.p);
+  LAUNCH_CHECK();
+  return DFM_OK;
 }
 
 int run_gn(const float* raw, long long V, Norm& n, int groups, cudaStream_t st) {
@@ -307,10 +281,52 @@ int run_gn(const float* raw, long long V, Norm& n, int groups, cudaStream_t st) 
   else
     return fail(DFM_ERR_INVALID, "GroupNorm: unsupported channel count");
   LAUNCH_CHECK();
-  dfm::gn_finalize_kernel<<<1, 64, 0, st>>>(n.sums, n.gamma.p, n.beta.p, n.C, groups, (double)V,
-                                           1e-5f, n.scale.p, n.shift.p);
-  LAUNCH_CHECK();
-  return DFM_OK;
+  return gn_finalize(n, V, groups, st);
+}
+
+// conv + (optionally) the GroupNorm statistics of its raw output.  The tensor-core kernel
+// accumulates the per-channel sums in its epilogue; the fp32 SIMT path runs a reduction
+// pass afterwards.
+template <class L, class TCFN>
+int run_conv_impl(const L& simt_loader, TCFN tc_fn, const char* loader_name, const ConvW& w,
+                  float* out, const dfm::ConvGeom& g, int impl, Norm* gn, cudaStream_t st) {
+  const long long V = (long long)g.Do * g.Ho * g.Wo;
+  const bool tc_ok = w.tc.ready() && dfm::tc_mode_of(g) == w.tc.mode;
+  if (impl == DFM_CONV_TC && !tc_ok)
+    return fail(DFM_ERR_INVALID, "conv3d: no tensor-core kernel for this layer");
+  if (impl != DFM_CONV_SIMT && tc_ok) {
+    std::string err;
+    if (gn) CU_TRY(cudaMemsetAsync(gn->sums, 0, 2 * gn->C * sizeof(double), st));
+    {
+      ProfScope ps(conv_class("conv_tc", g, loader_name), conv_flops(g), st);
+      if (!tc_fn(gn ? gn->sums : nullptr, &err)) return fail(DFM_ERR_CUDA, err);
+    }
+    g_launches.fetch_add(1);
+    g_tc_launches.fetch_add(1);
+    return gn ? gn_finalize(*gn, V, 32, st) : DFM_OK;
+  }
+  {
+    ProfScope ps(conv_class("conv_simt", g, loader_name), conv_flops(g), st);
+    DFM_TRY(conv_simt_dispatch(simt_loader, w, out, g, st));
+  }
+  return gn ? run_gn(out, V, *gn, 32, st) : DFM_OK;
+}
+
+int run_conv(const dfm::Src& s, const ConvW& w, float* out, const dfm::ConvGeom& g, int impl,
+             cudaStream_t st, Norm* gn = nullptr) {
+  dfm::SrcLoader ld{s, g.Cin, g.Hi, g.Wi};
+  return run_conv_impl(
+      ld, [&](double* stats, std::string* err) {
+        return dfm::tc_conv_src(s, w.tc, out, stats, g, st, err);
+      }, "src", w, out, g, impl, gn, st);
+}
+
+int run_conv_warp(const dfm::WarpLoader& ld, const ConvW& w, float* out, const dfm::ConvGeom& g,
+                  int impl, cudaStream_t st, Norm* gn = nullptr) {
+  return run_conv_impl(
+      ld, [&](double* stats, std::string* err) {
+        return dfm::tc_conv_warp(ld, w.tc, out, stats, g, st, err);
+      }, "warp", w, out, g, impl, gn, st);
 }
 
 int to_nhwc(const float* in, float* out, int C, long long HW, cudaStream_t st) {
@@ -498,23 +514,28 @@ int tower_set_param(Tower& t, bool mono, int cin0, int cv, const std::string& na
   const std::string hg = mono ? "hg_mono.0" : "hg_stereo.0";
   const std::string pr = mono ? "pred_mono.0" : "pred_stereo.0";
   *handled = true;
-  if (name == "dres0" + sfx + ".conv.weight") return set_conv(t.dres0, h, numel, cin0, cv, 0);
-  if (name == "dres1" + sfx + ".conv.weight") return set_conv(t.dres1, h, numel, cv, cv, 0);
+  if (name == "dres0" + sfx + ".conv.weight")
+    return set_conv(t.dres0, h, numel, cin0, cv, 0, dfm::TC_S1);
+  if (name == "dres1" + sfx + ".conv.weight")
+    return set_conv(t.dres1, h, numel, cv, cv, 0, dfm::TC_S1);
   if (name == "dres0" + sfx + ".gn.weight" || name == "dres0" + sfx + ".gn.bias")
     return set_norm_param(t.g0, name, h, numel);
   if (name == "dres1" + sfx + ".gn.weight" || name == "dres1" + sfx + ".gn.bias")
     return set_norm_param(t.g1, name, h, numel);
-  struct HG { const char* key; ConvW* w; Norm* n; int ci, co, tr; };
-  const HG hgs[] = {{"conv1.0", &t.c1, &t.gc1, cv, 2 * cv, 0},    {"conv2", &t.c2, &t.gc2, 2 * cv, 2 * cv, 0},
-                    {"conv3.0", &t.c3, &t.gc3, 2 * cv, 2 * cv, 0}, {"conv4.0", &t.c4, &t.gc4, 2 * cv, 2 * cv, 0},
-                    {"conv5", &t.c5, &t.gc5, 2 * cv, 2 * cv, 1},   {"conv6", &t.c6, &t.gc6, 2 * cv, cv, 1}};
+  struct HG { const char* key; ConvW* w; Norm* n; int ci, co, tr, mode; };
+  const HG hgs[] = {{"conv1.0", &t.c1, &t.gc1, cv, 2 * cv, 0, dfm::TC_S2},
+                    {"conv2", &t.c2, &t.gc2, 2 * cv, 2 * cv, 0, dfm::TC_S1},
+                    {"conv3.0", &t.c3, &t.gc3, 2 * cv, 2 * cv, 0, dfm::TC_S2},
+                    {"conv4.0", &t.c4, &t.gc4, 2 * cv, 2 * cv, 0, dfm::TC_S1},
+                    {"conv5", &t.c5, &t.gc5, 2 * cv, 2 * cv, 1, dfm::TC_T},
+                    {"conv6", &t.c6, &t.gc6, 2 * cv, cv, 1, dfm::TC_T}};
   for (const HG& e : hgs) {
     const std::string base = hg + "." + e.key;
-    if (name == base + ".0.weight") return set_conv(*e.w, h, numel, e.ci, e.co, e.tr);
+    if (name == base + ".0.weight") return set_conv(*e.w, h, numel, e.ci, e.co, e.tr, e.mode);
     if (name == base + ".1.weight" || name == base + ".1.bias")
       return set_norm_param(*e.n, name, h, numel);
   }
-  if (name == pr + ".0.conv.weight") return set_conv(t.p0, h, numel, cv, cv, 0);
+  if (name == pr + ".0.conv.weight") return set_conv(t.p0, h, numel, cv, cv, 0, dfm::TC_S1);
   if (name == pr + ".0.gn.weight" || name == pr + ".0.gn.bias")
     return set_norm_param(t.gp0, name, h, numel);
   if (name == pr + ".1.weight") {
@@ -538,39 +559,29 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
 
   // dres0 on the on-the-fly volume
   dfm::ConvGeom g = geom_s(D, Ho, Wo, cin0, cv, 1, 1, 1, 1, 1, 1);
-  DFM_TRY(run_conv_warp(wl, t.dres0, t.raw0.p, g, impl, st));
-  DFM_TRY(run_gn(t.raw0.p, V, t.g0, 32, st));
+  DFM_TRY(run_conv_warp(wl, t.dres0, t.raw0.p, g, impl, st, &t.g0));
   // dres1 (GN, no act) on relu(gn(raw0))
   g = geom_s(D, Ho, Wo, cv, cv, 1, 1, 1, 1, 1, 1);
-  DFM_TRY(run_conv(src1(term(t.raw0, &t.g0, 1)), t.dres1, t.raw1.p, g, impl, st));
-  DFM_TRY(run_gn(t.raw1.p, V, t.g1, 32, st));
+  DFM_TRY(run_conv(src1(term(t.raw0, &t.g0, 1)), t.dres1, t.raw1.p, g, impl, st, &t.g1));
   // cost0 = gn1(raw1) + relu(gn0(raw0)) is never stored: consumers re-evaluate it
   const dfm::Term T1 = term(t.raw1, &t.g1, 0), T0 = term(t.raw0, &t.g0, 1);
   // hourglass (conv_modules.py:129-149)
   g = geom_s(D, Ho, Wo, cv, 2 * cv, 2, 2, 2, 1, 1, 1);
-  DFM_TRY(run_conv(src2(T1, T0), t.c1, t.b1.p, g, impl, st));
+  DFM_TRY(run_conv(src2(T1, T0), t.c1, t.b1.p, g, impl, st, &t.gc1));
   const int D2 = g.Do, H2 = g.Ho, W2 = g.Wo;
-  const long long V2 = (long long)D2 * H2 * W2;
-  DFM_TRY(run_gn(t.b1.p, V2, t.gc1, 32, st));
   g = geom_s(D2, H2, W2, 2 * cv, 2 * cv, 1, 1, 1, 1, 1, 1);
-  DFM_TRY(run_conv(src1(term(t.b1, &t.gc1, 1)), t.c2, t.b2.p, g, impl, st));
-  DFM_TRY(run_gn(t.b2.p, V2, t.gc2, 32, st));
+  DFM_TRY(run_conv(src1(term(t.b1, &t.gc1, 1)), t.c2, t.b2.p, g, impl, st, &t.gc2));
   g = geom_s(D2, H2, W2, 2 * cv, 2 * cv, 2, 2, 2, 1, 1, 1);
-  DFM_TRY(run_conv(src1(term(t.b2, &t.gc2, 1)), t.c3, t.b3.p, g, impl, st));
+  DFM_TRY(run_conv(src1(term(t.b2, &t.gc2, 1)), t.c3, t.b3.p, g, impl, st, &t.gc3));
   const int D4 = g.Do, H4 = g.Ho, W4 = g.Wo;
-  const long long V4 = (long long)D4 * H4 * W4;
-  DFM_TRY(run_gn(t.b3.p, V4, t.gc3, 32, st));
   g = geom_s(D4, H4, W4, 2 * cv, 2 * cv, 1, 1, 1, 1, 1, 1);
-  DFM_TRY(run_conv(src1(term(t.b3, &t.gc3, 1)), t.c4, t.b4.p, g, impl, st));
-  DFM_TRY(run_gn(t.b4.p, V4, t.gc4, 32, st));
+  DFM_TRY(run_conv(src1(term(t.b3, &t.gc3, 1)), t.c4, t.b4.p, g, impl, st, &t.gc4));
   g = geom_t(D4, H4, W4, 2 * cv, 2 * cv);
-  DFM_TRY(run_conv(src1(term(t.b4, &t.gc4, 1)), t.c5, t.b5.p, g, impl, st));
-  DFM_TRY(run_gn(t.b5.p, V2, t.gc5, 32, st));
+  DFM_TRY(run_conv(src1(term(t.b4, &t.gc4, 1)), t.c5, t.b5.p, g, impl, st, &t.gc5));
   // post = relu(gn5(conv5) + pre),  pre = relu(gn2(conv2))
   g = geom_t(D2, H2, W2, 2 * cv, cv);
   DFM_TRY(run_conv(src2(term(t.b5, &t.gc5, 0), term(t.b2, &t.gc2, 1), 1), t.c6, t.b6.p, g, impl,
-                   st));
-  DFM_TRY(run_gn(t.b6.p, V, t.gc6, 32, st));
+                   st, &t.gc6));
   // cur_cost = cost0 + gn6(conv6): channels-last copy for the pred conv + NCDHW output
   {
     dim3 grid((unsigned)((V + 31) / 32), (cv + 31) / 32), block(32, 8);
@@ -580,8 +591,7 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
   }
   // depth prediction module (dfm_backbone.py:118-128)
   g = geom_s(D, Ho, Wo, cv, cv, 1, 1, 1, 1, 1, 1);
-  DFM_TRY(run_conv(src1(term(t.cur, nullptr, 0)), t.p0, t.p0b.p, g, impl, st));
-  DFM_TRY(run_gn(t.p0b.p, V, t.gp0, 32, st));
+  DFM_TRY(run_conv(src1(term(t.cur, nullptr, 0)), t.p0, t.p0b.p, g, impl, st, &t.gp0));
   {
     const long long threads = V * 8;
     dfm::conv3d_c32_to_1_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
@@ -915,10 +925,11 @@ int dfm_op_conv3d(const float* d_x, int Cin, int Di, int Hi, int Wi, const float
   if (!d_x || !h_w || !d_y || !stride || !pad) return fail(DFM_ERR_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   ConvW w;
-  DFM_TRY(set_conv(w, h_w, (long long)27 * Cin * Cout, Cin, Cout, transposed));
   dfm::ConvGeom g = transposed ? geom_t(Di, Hi, Wi, Cin, Cout)
                                : geom_s(Di, Hi, Wi, Cin, Cout, stride[0], stride[1], stride[2],
                                         pad[0], pad[1], pad[2]);
+  DFM_TRY(set_conv(w, h_w, (long long)27 * Cin * Cout, Cin, Cout, transposed,
+                   dfm::tc_mode_of(g)));
   const long long Vi = (long long)Di * Hi * Wi, Vo = (long long)g.Do * g.Ho * g.Wo;
   DevBuf xin, yout;
   DFM_TRY(xin.alloc(Vi * Cin));

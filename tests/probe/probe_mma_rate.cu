@@ -17,7 +17,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
 
-__global__ void __launch_bounds__(128, 1) rate(int N, int iters, int distinct_a, long long* cycles, int* status) {
+__global__ void __launch_bounds__(128, 1) rate(int N, int iters, int distinct_a, int nchain, long long* cycles, int* status) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -42,14 +42,16 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int iters, int distinct_a,
     uint64_t ad[4], bd = make_desc(b_base, 256 * 16, 128);
     for (int j = 0; j < 4; ++j)
       ad[j] = make_desc(a_base + (distinct_a ? j * 6144 + j * 16 : 0), 186 * 16, 10 * 16);
-    const uint32_t c0 = tmem_base, c1 = tmem_base + 256;
+    // nchain independent accumulators (dependent-accumulate chains) used round-robin
+    uint32_t cc[8];
+    for (int j = 0; j < 8; ++j) cc[j] = tmem_base + (uint32_t)((j % nchain) * (nchain > 2 ? 128 : 256));
     t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < iters; it += 8) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"((j & 1) ? c1 : c0), "l"(ad[j & 3]), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(cc[j]), "l"(ad[j & 3]), "l"(bd), "r"(idesc), "r"(1u) : "memory");
       }
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -72,21 +74,22 @@ int main() {
   long long* dc; int* ds; CK(cudaMalloc(&dc, sms * 8)); CK(cudaMalloc(&ds, 4));
   CK(cudaFuncSetAttribute(rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   const int iters = 20000;
-  for (int distinct = 0; distinct < 2; ++distinct)
-    for (int N : {16, 32, 48, 64, 96, 128, 192, 256}) {
+  for (int nchain : {1, 2, 4})
+    for (int N : {32, 64, 96, 128}) {
+      const int distinct = 1;
       CK(cudaMemset(ds, 0, 4));
       cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-      rate<<<sms, 128, 64 * 1024>>>(N, 2000, distinct, dc, ds);  // warm-up
+      rate<<<sms, 128, 64 * 1024>>>(N, 2000, distinct, nchain, dc, ds);  // warm-up
       CK(cudaDeviceSynchronize());
       cudaEventRecord(e0);
-      rate<<<sms, 128, 64 * 1024>>>(N, iters, distinct, dc, ds);
+      rate<<<sms, 128, 64 * 1024>>>(N, iters, distinct, nchain, dc, ds);
       cudaEventRecord(e1);
       CK(cudaDeviceSynchronize());
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       long long hc[256]; int st; CK(cudaMemcpy(hc, dc, sms * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, ds, 4, cudaMemcpyDeviceToHost));
       double avg = 0; for (int i = 0; i < sms; ++i) avg += hc[i]; avg /= sms;
       const double flops = 2.0 * 128 * N * 16 * (double)iters * sms;
-      printf("distinctA=%d N=%3d  cycles/MMA=%7.2f  time=%.3f ms  %.1f TFLOP/s (bf16)  timeout=%d\n", distinct, N, avg / iters, ms, flops / (ms * 1e-3) / 1e12, st);
+      printf("chains=%d distinctA=%d N=%3d  cycles/MMA=%7.2f  time=%.3f ms  %.1f TFLOP/s (bf16)  timeout=%d\n", nchain, distinct, N, avg / iters, ms, flops / (ms * 1e-3) / 1e12, st);
     }
   return 0;
 }
