@@ -519,6 +519,7 @@ struct TcParams {
   uint32_t w_bytes, w_hi_bytes;
   int* err;
   unsigned long long* role_cycles;  // optional [grid][8] role wait/busy cycle counters
+  int store1;  // epilogue stores only output channel 0, densely ([V] floats): the Cout=1 conv
   int dbg;  // diagnosis only (DFM_TC_DEBUG): 1 loaders skip work, 2 epilogue skips, 4 no MMA,
             // 8 loaders skip the proxy fence
   TcProgram prog[2];
@@ -965,12 +966,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               xo = 2 * mx + ((cb == 1 || cb == 2) ? 1 : 0);
               yo = 2 * my + (cb >= 2 ? 1 : 0);
             }
-            float4* dst = reinterpret_cast<float4*>(
-                p.out + (((long long)zo * p.Ho + yo) * p.Wo + xo) * p.Cout + it.split * NCTA);
+            if (p.store1) {
+              p.out[((long long)zo * p.Ho + yo) * p.Wo + xo] = __uint_as_float(r[0]);
+            } else {
+              float4* dst = reinterpret_cast<float4*>(
+                  p.out + (((long long)zo * p.Ho + yo) * p.Wo + xo) * p.Cout + it.split * NCTA);
 #pragma unroll
-            for (int q = 0; q < NCTA / 4; ++q)
-              dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+              for (int q = 0; q < NCTA / 4; ++q)
+                dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            }
             if (p.stats) {
 #pragma unroll
               for (int i = 0; i < NCTA; ++i) {
@@ -1038,7 +1043,7 @@ inline int tc_sm_count() {
 
 template <int MODE, int CIN, int NCTA, class Loader>
 bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
-               const ConvGeom& g, cudaStream_t st, std::string* err) {
+               const ConvGeom& g, cudaStream_t st, std::string* err, int store1 = 0) {
   using M = TcMode<MODE>;
   constexpr size_t STAGE_BYTES = (size_t)2 * (M::CG / 8) * M::ROWS * 16;
   const size_t smem = w.image_bytes + M::NSTAGE * STAGE_BYTES +
@@ -1059,6 +1064,7 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
   p.wimg = w.dev;
   p.out = out;
   p.stats = stats;
+  p.store1 = store1;
   p.Di = g.Di; p.Hi = g.Hi; p.Wi = g.Wi;
   p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
   p.Cout = g.Cout;
@@ -1134,14 +1140,15 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
 
 template <class Loader>
 bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats,
-                 const ConvGeom& g, cudaStream_t st, std::string* err) {
+                 const ConvGeom& g, cudaStream_t st, std::string* err, int store1 = 0) {
   const int mode = tc_mode_of(g);
   if (mode != w.mode) {
     if (err) *err = "conv_tc: weight image was built for a different conv mode";
     return false;
   }
 #define TC_CASE(MD, CI, NC) \
-  if (mode == MD && g.Cin == CI) return tc_launch<MD, CI, NC, Loader>(ld, w, out, stats, g, st, err)
+  if (mode == MD && g.Cin == CI) \
+    return tc_launch<MD, CI, NC, Loader>(ld, w, out, stats, g, st, err, store1)
   TC_CASE(TC_S1, 32, 32);
   TC_CASE(TC_S1, 64, 16);
   TC_CASE(TC_S2, 32, 32);
@@ -1153,13 +1160,13 @@ bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats
 }
 
 inline bool tc_conv_src(const Src& s, const TcWeights& w, float* out, double* stats,
-                        const ConvGeom& g, cudaStream_t st, std::string* err) {
+                        const ConvGeom& g, cudaStream_t st, std::string* err, int store1 = 0) {
   if (s.n > 2) {
     if (err) *err = "conv_tc: at most two input terms";
     return false;
   }
   SrcLoader8 ld{s, g.Cin, g.Hi, g.Wi};
-  return tc_dispatch(ld, w, out, stats, g, st, err);
+  return tc_dispatch(ld, w, out, stats, g, st, err, store1);
 }
 inline bool tc_conv_warp(const WarpLoader& wl, const TcWeights& w, float* out, double* stats,
                          const ConvGeom& g, cudaStream_t st, std::string* err) {

@@ -422,6 +422,7 @@ int make_warp_geom(const dfm_geometry_t* gm, int Hf, int Wf, int csf, int fsf, d
 struct Tower {
   ConvW dres0, dres1, c1, c2, c3, c4, c5, c6, p0;
   DevBuf p1w;  // [27][32]
+  ConvW p1tc;  // the 32->1 logit conv zero-padded to 32 output channels for the tensor cores
   Norm g0, g1, gc1, gc2, gc3, gc4, gc5, gc6, gp0;
   DevBuf raw0, raw1, b1, b2, b3, b4, b5, b6, cur, p0b, logit;
 };
@@ -469,7 +470,7 @@ void tower_release(Tower& t) {
     b->release();
   for (Norm* n : {&t.g0, &t.g1, &t.gc1, &t.gc2, &t.gc3, &t.gc4, &t.gc5, &t.gc6, &t.gp0})
     n->release();
-  for (ConvW* c : {&t.dres0, &t.dres1, &t.c1, &t.c2, &t.c3, &t.c4, &t.c5, &t.c6, &t.p0}) {
+  for (ConvW* c : {&t.dres0, &t.dres1, &t.c1, &t.c2, &t.c3, &t.c4, &t.c5, &t.c6, &t.p0, &t.p1tc}) {
     c->simt.release();
     c->tc.release();
   }
@@ -543,6 +544,10 @@ int tower_set_param(Tower& t, bool mono, int cin0, int cv, const std::string& na
     std::vector<float> p((size_t)27 * cv);  // (1,cv,3,3,3) -> [tap][c]
     for (int c = 0; c < cv; ++c)
       for (int k = 0; k < 27; ++k) p[(size_t)k * cv + c] = h[(size_t)c * 27 + k];
+    std::vector<float> padded((size_t)cv * cv * 27, 0.f);  // (Cout=cv, Cin, 27), only co = 0 set
+    for (int c = 0; c < cv; ++c)
+      for (int k = 0; k < 27; ++k) padded[(size_t)c * 27 + k] = h[(size_t)c * 27 + k];
+    DFM_TRY(set_conv(t.p1tc, padded.data(), (long long)padded.size(), cv, cv, 0, dfm::TC_S1));
     return upload(t.p1w, p.data(), p.size());
   }
   *handled = false;
@@ -592,8 +597,17 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
   // depth prediction module (dfm_backbone.py:118-128)
   g = geom_s(D, Ho, Wo, cv, cv, 1, 1, 1, 1, 1, 1);
   DFM_TRY(run_conv(src1(term(t.cur, nullptr, 0)), t.p0, t.p0b.p, g, impl, st, &t.gp0));
-  {
+  if (impl != DFM_CONV_SIMT && t.p1tc.tc.ready()) {
+    std::string err;
+    ProfScope ps(conv_class("conv_tc_cout1", g, "src"), 2.0 * V * cv * 27, st);
+    if (!dfm::tc_conv_src(src1(term(t.p0b, &t.gp0, 1)), t.p1tc.tc, t.logit.p, nullptr, g, st, &err,
+                          /*store1=*/1))
+      return fail(DFM_ERR_CUDA, err);
+    g_launches.fetch_add(1);
+    g_tc_launches.fetch_add(1);
+  } else {
     const long long threads = V * 8;
+    ProfScope ps(conv_class("conv_simt_cout1", g, "src"), 2.0 * V * cv * 27, st);
     dfm::conv3d_c32_to_1_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
         src1(term(t.p0b, &t.gp0, 1)), t.p1w.p, t.logit.p, D, Ho, Wo);
     LAUNCH_CHECK();
