@@ -206,10 +206,8 @@ def run_ours(args):
         capi.profile_enable(False)
         l1, tc1 = capi.launch_counters()
         capi.sync_check()
-    t = torch.tensor([ms], device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    from depth_from_motion_b200.sharding import reduce_step_time
+    ms_total = reduce_step_time(ms, 'cuda')
     fps = world * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
@@ -245,11 +243,9 @@ def run_ours(args):
         e2e_step(i)
     ee1.record()
     barrier()
-    t2 = torch.tensor([max(ee0.elapsed_time(ee1), (time.perf_counter() - t0) * 1e3)],
-                      device='cuda')
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_fps = world * args.steps / (float(t2.item()) * 1e-3)
+    e2e_ms = reduce_step_time(max(ee0.elapsed_time(ee1), (time.perf_counter() - t0) * 1e3),
+                              'cuda')
+    e2e_fps = world * args.steps / (e2e_ms * 1e-3)
     h2d = 2 * C * H * W * 4
     d2h = (D * HO * WO + H * W) * 4
 

@@ -415,7 +415,7 @@ __device__ __forceinline__ void split_store(const float v[8], uint8_t* hi_dst, u
 struct SrcLoader8 {
   Src s;
   int C, H, W;
-  static constexpr int BATCH = 3;
+  static constexpr int BATCH = 0;  // every item of a thread in flight at once
   struct Raw {
     float4 a[2][2];
   };
@@ -664,15 +664,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           mbar_wait_timed(empty_a(s), ((stage_ctr / M::NSTAGE) & 1) ^ 1, p.err, t_wait_e, timed);
           uint8_t* st = a_s + s * STAGE_BYTES;
           const int c0 = cg * M::CG + chunk * 8;
+          constexpr int LB = Loader::BATCH == 0 ? NITEM : Loader::BATCH;  // 0: all in flight
           if (!(p.dbg & 1))
 #pragma unroll
-          for (int k0 = 0; k0 < NITEM; k0 += Loader::BATCH) {
-            typename Loader::Raw raw[Loader::BATCH];
+          for (int k0 = 0; k0 < NITEM; k0 += LB) {
+            typename Loader::Raw raw[LB];
 #pragma unroll
-            for (int b = 0; b < Loader::BATCH; ++b)
+            for (int b = 0; b < LB; ++b)
               if (k0 + b < NITEM && inb[k0 + b]) ld.issue(zi, gy[k0 + b], gx[k0 + b], c0, raw[b]);
 #pragma unroll
-            for (int b = 0; b < Loader::BATCH; ++b) {
+            for (int b = 0; b < LB; ++b) {
               if (k0 + b < NITEM && live[k0 + b]) {
                 float v[8];
                 if (inb[k0 + b]) {
@@ -803,6 +804,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   }
                 }
                 first = last;
+              }
+              done = true;
+            }
+            if constexpr (MODE == TC_S2) {
+              // Stride-2 issue sequence (one K step per 16-channel stage).  Even input planes
+              // feed one output plane (kz = 1); odd planes feed two (kz = 2 -> zo, kz = 0 ->
+              // zo + 1) with one N = 2*NCTA MMA when their slots are contiguous.
+              constexpr uint32_t KCH16 = CIN / 8;
+              const uint32_t odd = (uint32_t)zi & 1u;
+              const uint32_t nimg = odd ? 2u : 1u;                 // blocks per weight image
+              const uint32_t b_lbo16 = nimg * NCTA;
+              const uint32_t tap16 = KCH16 * b_lbo16;
+              const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFF) + (odd ? 9u * KCH16 * NCTA : 0u) +
+                                     (uint32_t)(cg * NCH) * b_lbo16 + (b_lbo16 << 16);
+              auto run = [&](uint32_t col, uint32_t brow16, uint32_t nblk) {
+                const uint32_t d0 = tmem_u + col;
+                const uint32_t idesc = idesc_bf16((int)(nblk * NCTA));
+                uint64_t dbh = pack64(b_lo0 + brow16, b_desc_hi);
+                uint64_t dbl = pack64(b_lo0 + brow16 + w_hi16, b_desc_hi);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                  const int dy = tap / 3, dx = tap % 3;
+                  const uint32_t a16 =
+                      (uint32_t)((((dx & 1) * 2 + (dy & 1)) * 17 + (dy >> 1)) * M::PITCH + (dx >> 1));
+                  const uint64_t dah = pack64(a_lo_stage + a16, a_desc_hi);
+                  const uint64_t dal = pack64(a_lo_stage + a16 + A_HL16, a_desc_hi);
+                  if (elect_one()) {
+                    umma_bf16(d0, dah, dbh, idesc, 1u);
+                    umma_bf16(d0, dal, dbh, idesc, 1u);
+                    umma_bf16(d0, dah, dbl, idesc, 1u);
+                  }
+                  desc_add(dbh, tap16);
+                  desc_add(dbl, tap16);
+                }
+              };
+              if (!odd) {
+                if (vmask & 2u) run(colbase[1], 0u, 1u);
+              } else if ((vmask & 6u) == 6u && !(wrapmask & 2u)) {
+                run(colbase[1], 0u, 2u);
+              } else {
+                if (vmask & 2u) run(colbase[1], 0u, 1u);
+                if (vmask & 4u) run(colbase[2], NCTA, 1u);
               }
               done = true;
             }
