@@ -153,6 +153,7 @@ def run_ours(args):
         raise SystemExit('bench.py needs a B200: there is no CPU path (use --impl reference)')
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = 'WARN'  # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     capi.lib()
 

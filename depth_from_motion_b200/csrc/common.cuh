@@ -18,7 +18,14 @@ struct Term {
   const float* scale;
   const float* shift;
   int relu;
+  // > 0: x holds only three planes -- z = 0, any interior z, z = zcls - 1 -- of a tensor
+  // that is constant along z except at its two ends (the cur-frame half of the plane-sweep
+  // volume and everything computed from it alone); zcls is the logical depth.
+  int zcls;
 };
+__device__ __forceinline__ int term_plane(const Term& t, int z) {
+  return t.zcls > 0 ? (z == 0 ? 0 : (z == t.zcls - 1 ? 2 : 1)) : z;
+}
 
 // value = outer_act( sum_i term_i )
 struct Src {
@@ -52,12 +59,14 @@ struct ConvGeom {
   int transposed;  // ConvTranspose3d(k3, s2, p1, op1)
 };
 
-__device__ __forceinline__ float load_src(const Src& s, long long vox, int C, int c) {
+// (z, pos): plane index and in-plane voxel index; HW: voxels per plane
+__device__ __forceinline__ float load_src(const Src& s, int z, long long pos, long long HW, int C,
+                                          int c) {
   float v = 0.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     if (i < s.n) {
-      float a = __ldg(s.t[i].x + vox * C + c);
+      float a = __ldg(s.t[i].x + ((long long)term_plane(s.t[i], z) * HW + pos) * C + c);
       if (s.t[i].scale) a = fmaf(a, __ldg(s.t[i].scale + c), __ldg(s.t[i].shift + c));
       if (s.t[i].relu) a = fmaxf(a, 0.f);
       v += a;

@@ -412,28 +412,30 @@ __device__ __forceinline__ void split_store(const float v[8], uint8_t* hi_dst, u
 // issue() only starts the global loads (so several items are in flight per thread),
 // finish() applies the fused transform.
 // ----------------------------------------------------------------------------------
+template <int NT>  // number of input terms (compile-time: sizes the in-flight registers)
 struct SrcLoader8 {
   Src s;
   int C, H, W;
-  static constexpr int BATCH = 0;  // every item of a thread in flight at once
+  // items of a thread in flight at once: at most 12 float4 (48 registers) of raw loads
+  static constexpr int BATCH = 6 / NT;
   struct Raw {
-    float4 a[2][2];
+    float4 a[NT][2];
   };
   __device__ __forceinline__ void issue(int z, int y, int x, int c0, Raw& r) const {
-    const long long base = (((long long)z * H + y) * W + x) * C + c0;
+    const long long inpl = ((long long)y * W + x) * C + c0, plane = (long long)H * W * C;
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
-      if (t < s.n) {
-        r.a[t][0] = __ldg(reinterpret_cast<const float4*>(s.t[t].x + base));
-        r.a[t][1] = __ldg(reinterpret_cast<const float4*>(s.t[t].x + base) + 1);
-      }
+    for (int t = 0; t < NT; ++t) {
+      const float* px = s.t[t].x + term_plane(s.t[t], z) * plane + inpl;
+      r.a[t][0] = __ldg(reinterpret_cast<const float4*>(px));
+      r.a[t][1] = __ldg(reinterpret_cast<const float4*>(px) + 1);
+    }
   }
   __device__ __forceinline__ void finish(const Raw& r, int c0, float v[8]) const {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      if (t < s.n) {
+    for (int t = 0; t < NT; ++t) {
+      {
         float u[8] = {r.a[t][0].x, r.a[t][0].y, r.a[t][0].z, r.a[t][0].w,
                       r.a[t][1].x, r.a[t][1].y, r.a[t][1].z, r.a[t][1].w};
         if (s.t[t].scale) {
@@ -519,6 +521,12 @@ struct TcParams {
   uint32_t w_bytes, w_hi_bytes;
   int* err;
   unsigned long long* role_cycles;  // optional [grid][8] role wait/busy cycle counters
+  const float* addend;  // optional [3][Ho][Wo][Cout] added to the output by z class (0, interior,
+                        // Do-1): the z-invariant cur-frame contribution of the first layer
+  // statistics weight of output planes [zw_lo, zw_hi): the planes that stand for the
+  // (longer) z-invariant interior of a shortened volume
+  int zw_lo, zw_hi;
+  float zw;
   int store1;  // epilogue stores only output channel 0, densely ([V] floats): the Cout=1 conv
   int dbg;  // diagnosis only (DFM_TC_DEBUG): 1 loaders skip work, 2 epilogue skips, 4 no MMA,
             // 8 loaders skip the proxy fence
@@ -561,7 +569,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   constexpr int TC_NSLOT = M::NSLOT;
   constexpr uint32_t TMEM_COLS = TC_NSLOT * SLOT_COLS;  // 256 / 512
   constexpr int NPOS = M::PXB * M::PYB;
-  constexpr int NITEM = (NPOS * NCH + TC_LOAD_THREADS - 1) / TC_LOAD_THREADS;
+  // two loader groups (even / odd loader warps) fill alternate stages: while one group
+  // waits for its global loads the other transforms and stores -> two stages in flight
+  constexpr int LGROUPS = 2;
+  constexpr int LG_THREADS = TC_LOAD_THREADS / LGROUPS;
+  constexpr int NITEM = (NPOS * NCH + LG_THREADS - 1) / LG_THREADS;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_s = smem;
@@ -589,7 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   }
   if (tid == 0) {
     for (int s = 0; s < M::NSTAGE; ++s) {
-      mbar_init(full_a(s), TC_LOAD_THREADS / 32);  // one arrival per loader warp
+      mbar_init(full_a(s), LG_THREADS / 32);  // one arrival per loader warp of the group
       mbar_init(empty_a(s), 1);
     }
     for (int s = 0; s < TC_NSLOT; ++s) {
@@ -622,10 +634,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   if (warp >= 4 && warp < MMA_WARP) {
     // ============================ loaders ============================
-    const int lt = tid - 128;
+    const int lgrp = (warp - 4) & (LGROUPS - 1);
+    const int lt = ((warp - 4) / LGROUPS) * 32 + lane;  // thread index inside the group
     const int chunk = lt % NCH;
     uint32_t stage_ctr = 0;
-    const bool timed = p.role_cycles != nullptr && lt == 0;
+    const bool timed = p.role_cycles != nullptr && tid == 128;
     unsigned long long t_wait_e = 0;
     const long long t_begin = clock64();
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -634,7 +647,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       bool inb[NITEM], live[NITEM];
 #pragma unroll
       for (int k = 0; k < NITEM; ++k) {
-        const int i = lt + k * TC_LOAD_THREADS;
+        const int i = lt + k * LG_THREADS;
         live[k] = i < NPOS * NCH;
         const int pos = i / NCH;
         const int bx = pos % M::PXB, by = pos / M::PXB;
@@ -660,11 +673,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       for (int zi = zi0; zi <= zi1; ++zi) {
 #pragma unroll 1
         for (int cg = 0; cg < NCG; ++cg, ++stage_ctr) {
+          if ((int)(stage_ctr & (LGROUPS - 1)) != lgrp) continue;
           const int s = stage_ctr % M::NSTAGE;
           mbar_wait_timed(empty_a(s), ((stage_ctr / M::NSTAGE) & 1) ^ 1, p.err, t_wait_e, timed);
           uint8_t* st = a_s + s * STAGE_BYTES;
           const int c0 = cg * M::CG + chunk * 8;
-          constexpr int LB = Loader::BATCH == 0 ? NITEM : Loader::BATCH;  // 0: all in flight
+          constexpr int LB = Loader::BATCH < NITEM ? Loader::BATCH : NITEM;
           if (!(p.dbg & 1))
 #pragma unroll
           for (int k0 = 0; k0 < NITEM; k0 += LB) {
@@ -1009,6 +1023,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               xo = 2 * mx + ((cb == 1 || cb == 2) ? 1 : 0);
               yo = 2 * my + (cb >= 2 ? 1 : 0);
             }
+            if (p.addend) {
+              const int cls = zo == 0 ? 0 : (zo == p.Do - 1 ? 2 : 1);
+              const float4* ad = reinterpret_cast<const float4*>(
+                  p.addend + (((long long)cls * p.Ho + yo) * p.Wo + xo) * p.Cout + it.split * NCTA);
+#pragma unroll
+              for (int q = 0; q < NCTA / 4; ++q) {
+                const float4 a4 = __ldg(ad + q);
+                r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + a4.x);
+                r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + a4.y);
+                r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + a4.z);
+                r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + a4.w);
+              }
+            }
             if (p.store1) {
               p.out[((long long)zo * p.Ho + yo) * p.Wo + xo] = __uint_as_float(r[0]);
             } else {
@@ -1020,11 +1047,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                      __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
             }
             if (p.stats) {
+              const float wz = (zo >= p.zw_lo && zo < p.zw_hi) ? p.zw : 1.f;
 #pragma unroll
               for (int i = 0; i < NCTA; ++i) {
                 const float v = __uint_as_float(r[i]);
-                ssum[i] += v;
-                ssq[i] = fmaf(v, v, ssq[i]);
+                ssum[i] = fmaf(wz, v, ssum[i]);
+                ssq[i] = fmaf(wz * v, v, ssq[i]);
               }
             }
           }
@@ -1084,9 +1112,15 @@ inline int tc_sm_count() {
   return cached;
 }
 
+struct TcOpts {
+  int store1 = 0;
+  const float* addend = nullptr;
+  int zw_lo = 0, zw_hi = 0;
+  float zw = 1.f;
+};
 template <int MODE, int CIN, int NCTA, class Loader>
 bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
-               const ConvGeom& g, cudaStream_t st, std::string* err, int store1 = 0) {
+               const ConvGeom& g, cudaStream_t st, std::string* err, TcOpts opt = TcOpts()) {
   using M = TcMode<MODE>;
   constexpr size_t STAGE_BYTES = (size_t)2 * (M::CG / 8) * M::ROWS * 16;
   const size_t smem = w.image_bytes + M::NSTAGE * STAGE_BYTES +
@@ -1107,7 +1141,11 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
   p.wimg = w.dev;
   p.out = out;
   p.stats = stats;
-  p.store1 = store1;
+  p.store1 = opt.store1;
+  p.addend = opt.addend;
+  p.zw_lo = opt.zw_lo;
+  p.zw_hi = opt.zw_hi;
+  p.zw = opt.zw;
   p.Di = g.Di; p.Hi = g.Hi; p.Wi = g.Wi;
   p.Do = g.Do; p.Ho = g.Ho; p.Wo = g.Wo;
   p.Cout = g.Cout;
@@ -1183,7 +1221,7 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
 
 template <class Loader>
 bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats,
-                 const ConvGeom& g, cudaStream_t st, std::string* err, int store1 = 0) {
+                 const ConvGeom& g, cudaStream_t st, std::string* err, TcOpts opt = TcOpts()) {
   const int mode = tc_mode_of(g);
   if (mode != w.mode) {
     if (err) *err = "conv_tc: weight image was built for a different conv mode";
@@ -1191,7 +1229,7 @@ bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats
   }
 #define TC_CASE(MD, CI, NC) \
   if (mode == MD && g.Cin == CI) \
-    return tc_launch<MD, CI, NC, Loader>(ld, w, out, stats, g, st, err, store1)
+    return tc_launch<MD, CI, NC, Loader>(ld, w, out, stats, g, st, err, opt)
   TC_CASE(TC_S1, 32, 32);
   TC_CASE(TC_S1, 64, 16);
   TC_CASE(TC_S2, 32, 32);
@@ -1203,23 +1241,31 @@ bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats
 }
 
 inline bool tc_conv_src(const Src& s, const TcWeights& w, float* out, double* stats,
-                        const ConvGeom& g, cudaStream_t st, std::string* err, int store1 = 0) {
-  if (s.n > 2) {
-    if (err) *err = "conv_tc: at most two input terms";
-    return false;
+                        const ConvGeom& g, cudaStream_t st, std::string* err,
+                        TcOpts opt = TcOpts()) {
+  if (s.n == 1) {
+    SrcLoader8<1> ld{s, g.Cin, g.Hi, g.Wi};
+    return tc_dispatch(ld, w, out, stats, g, st, err, opt);
   }
-  SrcLoader8 ld{s, g.Cin, g.Hi, g.Wi};
-  return tc_dispatch(ld, w, out, stats, g, st, err, store1);
+  if (s.n == 2) {
+    SrcLoader8<2> ld{s, g.Cin, g.Hi, g.Wi};
+    return tc_dispatch(ld, w, out, stats, g, st, err, opt);
+  }
+  SrcLoader8<3> ld{s, g.Cin, g.Hi, g.Wi};
+  return tc_dispatch(ld, w, out, stats, g, st, err, opt);
 }
 inline bool tc_conv_warp(const WarpLoader& wl, const TcWeights& w, float* out, double* stats,
-                         const ConvGeom& g, cudaStream_t st, std::string* err) {
+                         const ConvGeom& g, cudaStream_t st, std::string* err,
+                         TcOpts opt = TcOpts()) {
   if (tc_mode_of(g) != TC_S1) {
     if (err) *err = "conv_tc: the warp loader feeds stride-1 convs only";
     return false;
   }
   WarpLoader8 ld{wl};
-  if (g.Cin == 32) return tc_launch<TC_S1, 32, 32, WarpLoader8>(ld, w, out, stats, g, st, err);
-  if (g.Cin == 64) return tc_launch<TC_S1, 64, 16, WarpLoader8>(ld, w, out, stats, g, st, err);
+  if (g.Cin == 32)
+    return tc_launch<TC_S1, 32, 32, WarpLoader8>(ld, w, out, stats, g, st, err, opt);
+  if (g.Cin == 64)
+    return tc_launch<TC_S1, 64, 16, WarpLoader8>(ld, w, out, stats, g, st, err, opt);
   if (err) *err = "conv_tc: unsupported Cin";
   return false;
 }

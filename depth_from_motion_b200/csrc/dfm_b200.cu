@@ -181,12 +181,13 @@ int set_conv(ConvW& cw, const float* h, long long numel, int Cin, int Cout, int 
   return DFM_OK;
 }
 
-dfm::Term term(const DevBuf& x, const Norm* nrm, int relu) {
+dfm::Term term(const DevBuf& x, const Norm* nrm, int relu, int zcls = 0) {
   dfm::Term t;
   t.x = x.p;
   t.scale = nrm ? nrm->scale.p : nullptr;
   t.shift = nrm ? nrm->shift.p : nullptr;
   t.relu = relu;
+  t.zcls = zcls;
   return t;
 }
 
@@ -287,10 +288,18 @@ int run_gn(const float* raw, long long V, Norm& n, int groups, cudaStream_t st) 
 // conv + (optionally) the GroupNorm statistics of its raw output.  The tensor-core kernel
 // accumulates the per-channel sums in its epilogue; the fp32 SIMT path runs a reduction
 // pass afterwards.
+// ZW: the statistics weighting of a z-shortened volume (see tower_forward); count_planes is
+// the number of output planes the statistics stand for (0: g.Do)
+struct ZW {
+  int lo = 0, hi = 0;
+  float w = 1.f;
+  int count_planes = 0;
+};
 template <class L, class TCFN>
 int run_conv_impl(const L& simt_loader, TCFN tc_fn, const char* loader_name, const ConvW& w,
-                  float* out, const dfm::ConvGeom& g, int impl, Norm* gn, cudaStream_t st) {
-  const long long V = (long long)g.Do * g.Ho * g.Wo;
+                  float* out, const dfm::ConvGeom& g, int impl, Norm* gn, cudaStream_t st,
+                  const ZW& zw = ZW()) {
+  const long long V = (long long)(zw.count_planes ? zw.count_planes : g.Do) * g.Ho * g.Wo;
   const bool tc_ok = w.tc.ready() && dfm::tc_mode_of(g) == w.tc.mode;
   if (impl == DFM_CONV_TC && !tc_ok)
     return fail(DFM_ERR_INVALID, "conv3d: no tensor-core kernel for this layer");
@@ -313,19 +322,29 @@ int run_conv_impl(const L& simt_loader, TCFN tc_fn, const char* loader_name, con
 }
 
 int run_conv(const dfm::Src& s, const ConvW& w, float* out, const dfm::ConvGeom& g, int impl,
-             cudaStream_t st, Norm* gn = nullptr) {
+             cudaStream_t st, Norm* gn = nullptr, const ZW& zw = ZW()) {
   dfm::SrcLoader ld{s, g.Cin, g.Hi, g.Wi};
+  if (zw.count_planes && (impl == DFM_CONV_SIMT || !w.tc.ready()))
+    return fail(DFM_ERR_INVALID, "z-shortened volumes exist only on the tensor-core path");
   return run_conv_impl(
       ld, [&](double* stats, std::string* err) {
-        return dfm::tc_conv_src(s, w.tc, out, stats, g, st, err);
-      }, "src", w, out, g, impl, gn, st);
+        dfm::TcOpts o;
+        o.zw_lo = zw.lo;
+        o.zw_hi = zw.hi;
+        o.zw = zw.w;
+        return dfm::tc_conv_src(s, w.tc, out, stats, g, st, err, o);
+      }, "src", w, out, g, impl, gn, st, zw);
 }
 
 int run_conv_warp(const dfm::WarpLoader& ld, const ConvW& w, float* out, const dfm::ConvGeom& g,
-                  int impl, cudaStream_t st, Norm* gn = nullptr) {
+                  int impl, cudaStream_t st, Norm* gn = nullptr, const float* addend = nullptr) {
+  if (addend && (impl == DFM_CONV_SIMT || !w.tc.ready()))
+    return fail(DFM_ERR_INVALID, "the z-class addend exists only on the tensor-core path");
   return run_conv_impl(
       ld, [&](double* stats, std::string* err) {
-        return dfm::tc_conv_warp(ld, w.tc, out, stats, g, st, err);
+        dfm::TcOpts o;
+        o.addend = addend;
+        return dfm::tc_conv_warp(ld, w.tc, out, stats, g, st, err, o);
       }, "warp", w, out, g, impl, gn, st);
 }
 
@@ -423,6 +442,11 @@ struct Tower {
   ConvW dres0, dres1, c1, c2, c3, c4, c5, c6, p0;
   DevBuf p1w;  // [27][32]
   ConvW p1tc;  // the 32->1 logit conv zero-padded to 32 output channels for the tensor cores
+  // z-invariance of the cur-frame half: dres0 split into its cur- and
+  // prev-channel halves (stereo); the cur contribution is computed on 5 replicated planes
+  // and kept as 3 z-class planes (first / interior / last)
+  ConvW d0cur, d0prev;
+  DevBuf cls5, cls3;
   Norm g0, g1, gc1, gc2, gc3, gc4, gc5, gc6, gp0;
   DevBuf raw0, raw1, b1, b2, b3, b4, b5, b6, cur, p0b, logit;
 };
@@ -449,9 +473,10 @@ int tower_alloc(Tower& t, int D, int Ho, int Wo, int cv) {
   DFM_TRY(t.b4.alloc(V4 * 2 * cv));
   DFM_TRY(t.b5.alloc(V2 * 2 * cv));
   DFM_TRY(t.b6.alloc(V * cv));
-  DFM_TRY(t.cur.alloc(V * cv));
   DFM_TRY(t.p0b.alloc(V * cv));
   DFM_TRY(t.logit.alloc(V));
+  DFM_TRY(t.cls5.alloc((size_t)5 * Ho * Wo * cv));
+  DFM_TRY(t.cls3.alloc((size_t)3 * Ho * Wo * cv));
   DFM_TRY(t.g0.init(cv));
   DFM_TRY(t.g1.init(cv));
   DFM_TRY(t.gc1.init(2 * cv));
@@ -466,11 +491,12 @@ int tower_alloc(Tower& t, int D, int Ho, int Wo, int cv) {
 
 void tower_release(Tower& t) {
   for (DevBuf* b : {&t.raw0, &t.raw1, &t.b1, &t.b2, &t.b3, &t.b4, &t.b5, &t.b6, &t.cur, &t.p0b,
-                    &t.logit, &t.p1w})
+                    &t.logit, &t.p1w, &t.cls5, &t.cls3})
     b->release();
   for (Norm* n : {&t.g0, &t.g1, &t.gc1, &t.gc2, &t.gc3, &t.gc4, &t.gc5, &t.gc6, &t.gp0})
     n->release();
-  for (ConvW* c : {&t.dres0, &t.dres1, &t.c1, &t.c2, &t.c3, &t.c4, &t.c5, &t.c6, &t.p0, &t.p1tc}) {
+  for (ConvW* c : {&t.dres0, &t.dres1, &t.c1, &t.c2, &t.c3, &t.c4, &t.c5, &t.c6, &t.p0, &t.p1tc,
+                   &t.d0cur, &t.d0prev}) {
     c->simt.release();
     c->tc.release();
   }
@@ -515,8 +541,23 @@ int tower_set_param(Tower& t, bool mono, int cin0, int cv, const std::string& na
   const std::string hg = mono ? "hg_mono.0" : "hg_stereo.0";
   const std::string pr = mono ? "pred_mono.0" : "pred_stereo.0";
   *handled = true;
-  if (name == "dres0" + sfx + ".conv.weight")
+  if (name == "dres0" + sfx + ".conv.weight") {
+    if (!mono) {  // (cv, 2C, 27): channel halves as two C -> cv convs
+      const int C = cin0 / 2;
+      if (numel != (long long)27 * cin0 * cv)
+        return fail(DFM_ERR_INVALID, name + ": wrong element count");
+      std::vector<float> hc((size_t)cv * C * 27), hp((size_t)cv * C * 27);
+      for (int co = 0; co < cv; ++co)
+        for (int ci = 0; ci < C; ++ci)
+          for (int k = 0; k < 27; ++k) {
+            hc[((size_t)co * C + ci) * 27 + k] = h[((size_t)co * cin0 + ci) * 27 + k];
+            hp[((size_t)co * C + ci) * 27 + k] = h[((size_t)co * cin0 + C + ci) * 27 + k];
+          }
+      DFM_TRY(set_conv(t.d0cur, hc.data(), (long long)hc.size(), C, cv, 0, dfm::TC_S1));
+      DFM_TRY(set_conv(t.d0prev, hp.data(), (long long)hp.size(), C, cv, 0, dfm::TC_S1));
+    }
     return set_conv(t.dres0, h, numel, cin0, cv, 0, dfm::TC_S1);
+  }
   if (name == "dres1" + sfx + ".conv.weight")
     return set_conv(t.dres1, h, numel, cv, cv, 0, dfm::TC_S1);
   if (name == "dres0" + sfx + ".gn.weight" || name == "dres0" + sfx + ".gn.bias")
@@ -555,53 +596,125 @@ int tower_set_param(Tower& t, bool mono, int cin0, int cv, const std::string& na
 }
 
 // one tower of DfMBackbone.forward: dfm_backbone.py:175-183 / 189-197 + pred convs
+//
+// z-invariance ("optional algorithmic shortcut", validated against the
+// full computation by tests/test_gpu_parity.py): the cur-frame half of the volume is the
+// same on every depth plane, so everything the MONO tower computes is 4-periodic in z (two
+// stride-2 levels) on all planes whose receptive field does not reach the two z ends (zero
+// padding).  Through dres0/dres1, the hourglass and the pred convs that influence reaches
+// 14 planes (measured with the oracle).  The mono tower therefore runs on a shortened
+// volume: kZHead head planes, kZMid (two periods) interior planes, kZHead tail planes;
+// GroupNorm statistics weigh the interior planes so the sums equal those of the full
+// volume, and consumers expand z on read (same phase mod 4).
+constexpr int kZHead = 16, kZMid = 8;
+
 int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& wl,
-                  float* d_feat_out, cudaStream_t st) {
-  const int D = bb->D, Ho = bb->Ho, Wo = bb->Wo, cv = bb->d.cv_channels;
+                  float* d_feat_out, cudaStream_t st, dfm::ZExpand* zexp_out) {
+  const int Dfull = bb->D, Ho = bb->Ho, Wo = bb->Wo, cv = bb->d.cv_channels;
   const int impl = bb->d.conv_impl;
-  const long long V = (long long)D * Ho * Wo;
   const int cin0 = mono ? bb->d.in_channels : 2 * bb->d.in_channels;
 
-  // dres0 on the on-the-fly volume
-  dfm::ConvGeom g = geom_s(D, Ho, Wo, cin0, cv, 1, 1, 1, 1, 1, 1);
-  DFM_TRY(run_conv_warp(wl, t.dres0, t.raw0.p, g, impl, st, &t.g0));
+  dfm::ConvGeom g;
+  dfm::Term T0;
+  const ConvW& wcur = mono ? t.dres0 : t.d0cur;
+  const bool zinv = impl != DFM_CONV_SIMT && wcur.tc.ready() && (mono || t.d0prev.tc.ready());
+  const bool shorten = mono && zinv && Dfull >= 2 * kZHead + 2 * kZMid &&
+                       getenv("DFM_NO_ZSHORTEN") == nullptr;
+  const int D = shorten ? 2 * kZHead + kZMid : Dfull;  // planes actually computed
+  const long long V = (long long)D * Ho * Wo;           // computed voxels
+  dfm::ZExpand ze{Dfull, Dfull, 0, 0};                  // identity
+  if (shorten) ze = dfm::ZExpand{kZHead, Dfull - kZHead, Dfull - D, kZHead};
+  if (zexp_out) *zexp_out = ze;
+  // statistics weighting per resolution level (scale 1, 2, 4): interior planes
+  // [head/s, (head+mid)/s) each stand for (Dfull - 2 head) / mid planes
+  auto zw_at = [&](int scale) {
+    ZW z;
+    if (shorten) {
+      z.lo = kZHead / scale;
+      z.hi = (kZHead + kZMid) / scale;
+      z.w = (float)(Dfull - 2 * kZHead) / (float)kZMid;
+      z.count_planes = Dfull / scale;
+    }
+    return z;
+  };
+
+  // ---- first layer: dres0 on the on-the-fly plane-sweep volume --------------------------
+  if (zinv) {
+    // The cur-frame half of the volume is the same on every plane, so its conv response is
+    // too, except on the first and last plane (zero padding in z).  Five replicated planes
+    // give the three variants as output planes 0 / 2 / 4.
+    const int C = bb->d.in_channels;
+    dfm::WarpLoader wc = wl;
+    wc.first = 0;
+    g = geom_s(5, Ho, Wo, C, cv, 1, 1, 1, 1, 1, 1);
+    DFM_TRY(run_conv_warp(wc, wcur, t.cls5.p, g, impl, st));
+    const long long pe = (long long)Ho * Wo * cv;
+    dfm::pick_planes_kernel<<<(unsigned)((3 * pe + 255) / 256), 256, 0, st>>>(t.cls5.p, t.cls3.p, pe);
+    LAUNCH_CHECK();
+    if (mono) {
+      // dres0_mono's whole output is z-class compressed; its GroupNorm statistics weigh the
+      // three planes 1 : Dfull-2 : 1
+      CU_TRY(cudaMemsetAsync(t.g0.sums, 0, 2 * cv * sizeof(double), st));
+      dfm::channel_stats_zcls_kernel<32><<<148, 256, 0, st>>>(t.cls3.p, (long long)Ho * Wo, Dfull,
+                                                             t.g0.sums);
+      LAUNCH_CHECK();
+      DFM_TRY(gn_finalize(t.g0, (long long)Dfull * Ho * Wo, 32, st));
+      T0 = term(t.cls3, &t.g0, 1, D);  // first / interior / last plane of the computed volume
+    } else {
+      // stereo: prev-frame half on the tensor cores, cur-frame response added per z class
+      dfm::WarpLoader wp = wl;
+      wp.first = C;
+      g = geom_s(D, Ho, Wo, C, cv, 1, 1, 1, 1, 1, 1);
+      DFM_TRY(run_conv_warp(wp, t.d0prev, t.raw0.p, g, impl, st, &t.g0, t.cls3.p));
+      T0 = term(t.raw0, &t.g0, 1);
+    }
+  } else {
+    g = geom_s(D, Ho, Wo, cin0, cv, 1, 1, 1, 1, 1, 1);
+    DFM_TRY(run_conv_warp(wl, t.dres0, t.raw0.p, g, impl, st, &t.g0));
+    T0 = term(t.raw0, &t.g0, 1);
+  }
   // dres1 (GN, no act) on relu(gn(raw0))
   g = geom_s(D, Ho, Wo, cv, cv, 1, 1, 1, 1, 1, 1);
-  DFM_TRY(run_conv(src1(term(t.raw0, &t.g0, 1)), t.dres1, t.raw1.p, g, impl, st, &t.g1));
+  DFM_TRY(run_conv(src1(T0), t.dres1, t.raw1.p, g, impl, st, &t.g1, zw_at(1)));
   // cost0 = gn1(raw1) + relu(gn0(raw0)) is never stored: consumers re-evaluate it
-  const dfm::Term T1 = term(t.raw1, &t.g1, 0), T0 = term(t.raw0, &t.g0, 1);
+  const dfm::Term T1 = term(t.raw1, &t.g1, 0);
   // hourglass (conv_modules.py:129-149)
   g = geom_s(D, Ho, Wo, cv, 2 * cv, 2, 2, 2, 1, 1, 1);
-  DFM_TRY(run_conv(src2(T1, T0), t.c1, t.b1.p, g, impl, st, &t.gc1));
+  DFM_TRY(run_conv(src2(T1, T0), t.c1, t.b1.p, g, impl, st, &t.gc1, zw_at(2)));
   const int D2 = g.Do, H2 = g.Ho, W2 = g.Wo;
   g = geom_s(D2, H2, W2, 2 * cv, 2 * cv, 1, 1, 1, 1, 1, 1);
-  DFM_TRY(run_conv(src1(term(t.b1, &t.gc1, 1)), t.c2, t.b2.p, g, impl, st, &t.gc2));
+  DFM_TRY(run_conv(src1(term(t.b1, &t.gc1, 1)), t.c2, t.b2.p, g, impl, st, &t.gc2, zw_at(2)));
   g = geom_s(D2, H2, W2, 2 * cv, 2 * cv, 2, 2, 2, 1, 1, 1);
-  DFM_TRY(run_conv(src1(term(t.b2, &t.gc2, 1)), t.c3, t.b3.p, g, impl, st, &t.gc3));
+  DFM_TRY(run_conv(src1(term(t.b2, &t.gc2, 1)), t.c3, t.b3.p, g, impl, st, &t.gc3, zw_at(4)));
   const int D4 = g.Do, H4 = g.Ho, W4 = g.Wo;
   g = geom_s(D4, H4, W4, 2 * cv, 2 * cv, 1, 1, 1, 1, 1, 1);
-  DFM_TRY(run_conv(src1(term(t.b3, &t.gc3, 1)), t.c4, t.b4.p, g, impl, st, &t.gc4));
+  DFM_TRY(run_conv(src1(term(t.b3, &t.gc3, 1)), t.c4, t.b4.p, g, impl, st, &t.gc4, zw_at(4)));
   g = geom_t(D4, H4, W4, 2 * cv, 2 * cv);
-  DFM_TRY(run_conv(src1(term(t.b4, &t.gc4, 1)), t.c5, t.b5.p, g, impl, st, &t.gc5));
+  DFM_TRY(run_conv(src1(term(t.b4, &t.gc4, 1)), t.c5, t.b5.p, g, impl, st, &t.gc5, zw_at(2)));
   // post = relu(gn5(conv5) + pre),  pre = relu(gn2(conv2))
   g = geom_t(D2, H2, W2, 2 * cv, cv);
   DFM_TRY(run_conv(src2(term(t.b5, &t.gc5, 0), term(t.b2, &t.gc2, 1), 1), t.c6, t.b6.p, g, impl,
-                   st, &t.gc6));
-  // cur_cost = cost0 + gn6(conv6): channels-last copy for the pred conv + NCDHW output
-  {
-    dim3 grid((unsigned)((V + 31) / 32), (cv + 31) / 32), block(32, 8);
-    dfm::materialize_kernel<<<grid, block, 0, st>>>(src3(T1, T0, term(t.b6, &t.gc6, 0)), cv, V,
-                                                    t.cur.p, d_feat_out);
+                   st, &t.gc6, zw_at(1)));
+  // cur_cost = cost0 + gn6(conv6) is only materialised as the NCDHW output the caller asked
+  // for (z-expanded for the shortened mono tower); the pred conv re-evaluates the three terms
+  const dfm::Src cur_src = src3(T1, T0, term(t.b6, &t.gc6, 0));
+  if (d_feat_out) {
+    const long long Vfull = (long long)Dfull * Ho * Wo;
+    dim3 grid((unsigned)((Vfull + 31) / 32), (cv + 31) / 32), block(32, 8);
+    dfm::materialize_kernel<<<grid, block, 0, st>>>(cur_src, cv, Vfull, (long long)Ho * Wo, ze,
+                                                    nullptr, d_feat_out);
     LAUNCH_CHECK();
   }
   // depth prediction module (dfm_backbone.py:118-128)
   g = geom_s(D, Ho, Wo, cv, cv, 1, 1, 1, 1, 1, 1);
-  DFM_TRY(run_conv(src1(term(t.cur, nullptr, 0)), t.p0, t.p0b.p, g, impl, st, &t.gp0));
+  DFM_TRY(run_conv(cur_src, t.p0, t.p0b.p, g, impl, st, &t.gp0, zw_at(1)));
   if (impl != DFM_CONV_SIMT && t.p1tc.tc.ready()) {
     std::string err;
     ProfScope ps(conv_class("conv_tc_cout1", g, "src"), 2.0 * V * cv * 27, st);
+    dfm::TcOpts o1;
+    o1.store1 = 1;
     if (!dfm::tc_conv_src(src1(term(t.p0b, &t.gp0, 1)), t.p1tc.tc, t.logit.p, nullptr, g, st, &err,
-                          /*store1=*/1))
+                          o1))
       return fail(DFM_ERR_CUDA, err);
     g_launches.fetch_add(1);
     g_tc_launches.fetch_add(1);
@@ -740,7 +853,6 @@ int dfm_backbone_create(const dfm_backbone_desc_t* desc, dfm_backbone_t** out) {
     bb->dbg["c4" + s] = {&t.b4, 64};
     bb->dbg["c5" + s] = {&t.b5, 64};
     bb->dbg["c6" + s] = {&t.b6, 32};
-    bb->dbg["cur" + s] = {&t.cur, 32};
     bb->dbg["p0" + s] = {&t.p0b, 32};
     bb->dbg["logit" + s] = {&t.logit, 1};
   }
@@ -823,8 +935,9 @@ int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_
   wl.first = 0;
   DFM_TRY(make_warp_geom(geom, bb->d.feat_h, bb->d.feat_w, bb->d.cost_sample_factor,
                          bb->d.feat_sample_factor, &wl.g));
-  DFM_TRY(tower_forward(bb, bb->st, false, wl, d_stereo, st));
-  DFM_TRY(tower_forward(bb, bb->mo, true, wl, d_mono, st));
+  dfm::ZExpand ze_mono{bb->D, bb->D, 0, 0};
+  DFM_TRY(tower_forward(bb, bb->st, false, wl, d_stereo, st, nullptr));
+  DFM_TRY(tower_forward(bb, bb->mo, true, wl, d_mono, st, &ze_mono));
   // mono/stereo gate (dfm_backbone.py:130-141)
   const int HWo = bb->Ho * bb->Wo;
   const size_t smem = (size_t)2 * bb->D * 32 * sizeof(float);
@@ -832,7 +945,7 @@ int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_
     CU_TRY(cudaFuncSetAttribute(dfm::gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   dfm::gate_kernel<<<(HWo + 31) / 32, 128, smem, st>>>(bb->st.logit.p, bb->mo.logit.p, bb->wagg.p,
-                                                       bb->cost.p, bb->D, HWo);
+                                                       bb->cost.p, bb->D, HWo, ze_mono);
   LAUNCH_CHECK();
   if (d_cost)
     CU_TRY(cudaMemcpyAsync(d_cost, bb->cost.p, (size_t)bb->D * HWo * sizeof(float),

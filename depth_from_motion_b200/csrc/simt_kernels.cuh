@@ -60,7 +60,7 @@ struct SrcLoader {
   Src s;
   int C, Hi, Wi;
   __device__ __forceinline__ float load(int z, int y, int x, int c) const {
-    return load_src(s, ((long long)z * Hi + y) * Wi + x, C, c);
+    return load_src(s, z, (long long)y * Wi + x, (long long)Hi * Wi, C, c);
   }
 };
 
@@ -214,6 +214,44 @@ channel_stats_kernel(const float* __restrict__ x, long long V, double* __restric
   }
 }
 
+// Statistics of a z-class-compressed tensor [3][HW][C] that stands for D planes
+// (plane 0 once, plane 1 D-2 times, plane 2 once).
+template <int C>
+__global__ void __launch_bounds__(256)
+channel_stats_zcls_kernel(const float* __restrict__ x, long long HW, int D,
+                          double* __restrict__ sums) {
+  constexpr int ROWS = 256 / C;
+  __shared__ double sh[2][256];
+  const int c = threadIdx.x % C, r = threadIdx.x / C;
+  double s = 0.0, ss = 0.0;
+  for (long long v = (long long)blockIdx.x * ROWS + r; v < 3 * HW; v += (long long)gridDim.x * ROWS) {
+    const double wgt = (v / HW) == 1 ? (double)(D - 2) : 1.0;
+    const float a = x[v * C + c];
+    s += wgt * a;
+    ss += wgt * (double)a * a;
+  }
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = ss;
+  __syncthreads();
+  if (r == 0) {
+    for (int k = 1; k < ROWS; ++k) {
+      s += sh[0][k * C + c];
+      ss += sh[1][k * C + c];
+    }
+    atomicAdd(sums + 2 * c, s);
+    atomicAdd(sums + 2 * c + 1, ss);
+  }
+}
+
+// planes 0, 2, 4 of a 5-plane conv output -> the 3-plane class tensor
+__global__ void pick_planes_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                   long long plane_elems) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * plane_elems) return;
+  const long long pl = i / plane_elems, r = i % plane_elems;
+  out[i] = in[(2 * pl) * plane_elems + r];
+}
+
 // scale/shift of GroupNorm(groups, C) from per-channel sums over `count` voxels:
 // y = (x - mean_g) * rstd_g * gamma[c] + beta[c]  ==  x * scale[c] + shift[c]
 __global__ void gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
@@ -242,8 +280,22 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, const float*
 // Materialise a (<= 3 term) sum as a channels-last tensor and/or NCDHW output:
 // cur_cost = cost0 + hourglass(cost0)  (dfm_backbone.py:176-183).
 // ---------------------------------------------------------------------------------
+// z expansion of a tensor that was computed on a shortened volume.  Away from the two z
+// ends the mono tower is invariant under shifts by 4 planes (two stride-2 levels), so a full
+// plane z reads source plane z (head), z - shift (tail) or the interior plane of the same
+// phase, mid + (z - head) mod 4.
+struct ZExpand {
+  int head;   // planes [0, head) map to themselves
+  int tail0;  // planes [tail0, D) map to z - shift
+  int shift;
+  int mid;
+};
+__device__ __forceinline__ int zexpand(const ZExpand& e, int z) {
+  return z < e.head ? z : (z >= e.tail0 ? z - e.shift : e.mid + ((z - e.head) & 3));
+}
+
 __global__ void __launch_bounds__(256)
-materialize_kernel(Src s, int C, long long V, float* __restrict__ out_cl,
+materialize_kernel(Src s, int C, long long V, long long HW, ZExpand ze, float* __restrict__ out_cl,
                    float* __restrict__ out_ncdhw) {
   __shared__ float tile[32][33];
   const long long v0 = (long long)blockIdx.x * 32;
@@ -254,7 +306,7 @@ materialize_kernel(Src s, int C, long long V, float* __restrict__ out_cl,
     const int c = c0 + tx;
     float val = 0.f;
     if (v < V && c < C) {
-      val = load_src(s, v, C, c);
+      val = load_src(s, zexpand(ze, (int)(v / HW)), v % HW, HW, C, c);
       if (out_cl) out_cl[v * C + c] = val;
     }
     tile[j][tx] = val;
@@ -289,11 +341,11 @@ conv3d_c32_to_1_kernel(Src s, const float* __restrict__ w /*[27][32]*/, float* _
   for (int tap = 0; tap < 27; ++tap) {
     const int zi = z + tap / 9 - 1, yi = y + (tap / 3) % 3 - 1, xi = x + tap % 3 - 1;
     if (!live || zi < 0 || zi >= D || yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
-    const long long vi = ((long long)zi * H + yi) * W + xi;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int c = sub * 4 + k;
-      acc = fmaf(load_src(s, vi, 32, c), ws[tap * 32 + c], acc);
+      acc = fmaf(load_src(s, zi, (long long)yi * W + xi, (long long)H * W, 32, c),
+                 ws[tap * 32 + c], acc);
     }
   }
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -309,14 +361,15 @@ conv3d_c32_to_1_kernel(Src s, const float* __restrict__ w /*[27][32]*/, float* _
 __global__ void __launch_bounds__(128)
 gate_kernel(const float* __restrict__ ls, const float* __restrict__ lm,
             const float* __restrict__ wagg /*[D][2D]*/, float* __restrict__ cost, int D,
-            int HW) {
+            int HW, ZExpand zm /* z expansion of the mono logits */) {
   extern __shared__ float cat[];  // [2D][32]
   const int p0 = blockIdx.x * 32;
   const int px = threadIdx.x & 31, dg = threadIdx.x >> 5;
   for (int j = dg; j < 2 * D; j += 4) {
     const int p = p0 + px;
     float v = 0.f;
-    if (p < HW) v = j < D ? ls[(long long)j * HW + p] : lm[(long long)(j - D) * HW + p];
+    if (p < HW)
+      v = j < D ? ls[(long long)j * HW + p] : lm[(long long)zexpand(zm, j - D) * HW + p];
     cat[j * 32 + px] = v;
   }
   __syncthreads();

@@ -170,6 +170,37 @@ def test_simt_and_tensor_core_paths_agree():
         assert rel_err(a, b) < 2e-4
 
 
+def test_z_shortened_mono_tower_equals_full_computation():
+    # SURVEY.md section 7 shortcut: the mono tower is z-invariant away from the two z ends,
+    # so it is computed on 16 + 8 + 16 planes and expanded.  Must equal the full computation.
+    h, w, d = 64, 128, 64
+    cur, prev, metas, params = syn.make_kitti_pair(8, h, w, d)
+    cfg = syn.depth_cfg_for(d)
+    outs = {}
+    for key, env in (('short', None), ('full', '1')):
+        if env is None:
+            os.environ.pop('DFM_NO_ZSHORTEN', None)
+        else:
+            os.environ['DFM_NO_ZSHORTEN'] = env
+        try:
+            m = _backbone(params, cfg, 'auto')
+            with torch.no_grad():
+                outs[key] = m(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
+            capi.sync_check()
+        finally:
+            os.environ.pop('DFM_NO_ZSHORTEN', None)
+    for a, b, name in zip(outs['short'], outs['full'], ('cost', 'stereo', 'mono')):
+        e = rel_err(a, b)
+        print(name, e)
+        assert e < 2e-5, (name, e)
+    # and both agree with the fp32 SIMT path (no shortcut of any kind)
+    m = _backbone(params, cfg, 'simt')
+    with torch.no_grad():
+        ref = m(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
+    for a, b in zip(outs['short'], ref):
+        assert rel_err(a, b) < 2e-4
+
+
 def test_error_behaviour():
     cfg = syn.depth_cfg_for(8)
     m = modules.DfMBackbone(in_channels=32, depth_cfg=cfg).cuda().eval()
