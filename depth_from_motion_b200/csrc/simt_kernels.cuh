@@ -374,13 +374,27 @@ gate_kernel(const float* __restrict__ ls, const float* __restrict__ lm,
   }
   __syncthreads();
   const int p = p0 + px;
-  for (int d = dg; d < D; d += 4) {
-    const float* wr = wagg + (long long)d * 2 * D;
-    float a = 0.f;
-    for (int j = 0; j < 2 * D; ++j) a = fmaf(__ldg(wr + j), cat[j * 32 + px], a);
-    const float wgt = 1.f / (1.f + __expf(-a));
-    const float s = cat[d * 32 + px], m = cat[(D + d) * 32 + px];
-    if (p < HW) cost[(long long)d * HW + p] = wgt * s + (1.f - wgt) * m;
+  // each warp owns output planes d = dg, dg+4, ...; four of them at a time so the four
+  // dot products give independent FMA chains (the weight row reads are warp-uniform)
+  for (int d0 = dg; d0 < D; d0 += 16) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* wr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wr[k] = wagg + (long long)min(d0 + 4 * k, D - 1) * 2 * D;
+    for (int j = 0; j < 2 * D; ++j) {
+      const float c = cat[j * 32 + px];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] = fmaf(__ldg(wr[k] + j), c, a[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int d = d0 + 4 * k;
+      if (d < D && p < HW) {
+        const float wgt = 1.f / (1.f + __expf(-a[k]));
+        const float sv = cat[d * 32 + px], mv = cat[(D + d) * 32 + px];
+        cost[(long long)d * HW + p] = wgt * sv + (1.f - wgt) * mv;
+      }
+    }
   }
 }
 
@@ -555,6 +569,77 @@ lift_kernel(LiftParams p, const float* __restrict__ feats, const float* __restri
       const int c = lane + 32 * j;
       if (c < p.C) out[(long long)c * nvox + ovox] = tot_n > 0 ? tot[j] * inv : 0.f;
     }
+  }
+}
+
+// Thread-per-voxel variant for C <= 64: voxels are taken in OUTPUT order ([Nx][Ny][Nz]
+// linear), every thread keeps its C running sums in registers and the final stores are
+// coalesced across the warp for every channel (the warp-per-voxel kernel above writes one
+// 4-byte element per 4-byte-strided channel plane).
+template <int C>
+__global__ void __launch_bounds__(128)
+lift_voxel_kernel(LiftParams p, const float* __restrict__ feats, const float* __restrict__ xs,
+                  const float* __restrict__ ys, const float* __restrict__ zs,
+                  float* __restrict__ out) {
+  const long long nvox = (long long)p.nx * p.ny * p.nz;
+  const long long ovox = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ovox >= nvox) return;
+  const int iz = (int)(ovox % p.nz), iy = (int)((ovox / p.nz) % p.ny),
+            ix = (int)(ovox / ((long long)p.nz * p.ny));
+  const float px = __ldg(xs + ix), py = __ldg(ys + iy), pz = __ldg(zs + iz);
+  const long long fstride = (long long)C * p.Hf * p.Wf;
+  float tot[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) tot[c] = 0.f;
+  int tot_n = 0;
+  for (int f = 0; f < p.T; ++f) {
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    int nvalid = 0;
+    for (int v = 0; v < p.Nv; ++v) {
+      const int s = f * p.Nv + v;
+      const float* m = p.proj[s];
+      const float a = m[0] * px + m[1] * py + m[2] * pz + m[3];
+      const float b = m[4] * px + m[5] * py + m[6] * pz + m[7];
+      const float d = m[8] * px + m[9] * py + m[10] * pz + m[11];
+      float cx = a / d * p.scale_x - p.crop_x;
+      const float cy = b / d * p.scale_y - p.crop_y;
+      if (p.flip) cx = (float)p.img_w[s] - cx;
+      const bool valid = cx < (float)p.in_w && cx > 0.f && cy < (float)p.in_h && cy > 0.f &&
+                         d > 0.f;
+      if (!valid) continue;
+      ++nvalid;
+      const int sx = nearest_index(cx, p.Wf, (float)p.in_w);
+      const int sy = nearest_index(cy, p.Hf, (float)p.in_h);
+      if (sx < 0 || sx >= p.Wf || sy < 0 || sy >= p.Hf) continue;
+      const float4* fp = reinterpret_cast<const float4*>(
+          feats + s * fstride + ((long long)sy * p.Wf + sx) * C);
+#pragma unroll
+      for (int q = 0; q < C / 4; ++q) {
+        const float4 t4 = __ldg(fp + q);
+        acc[4 * q] += t4.x;
+        acc[4 * q + 1] += t4.y;
+        acc[4 * q + 2] += t4.z;
+        acc[4 * q + 3] += t4.w;
+      }
+    }
+    if (p.concat) {
+      const float inv = nvalid > 0 ? 1.f / (float)nvalid : 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) out[((long long)(f * C + c)) * nvox + ovox] = acc[c] * inv;
+    } else {
+      if (nvalid > 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) tot[c] += acc[c];
+      }
+      tot_n += nvalid;
+    }
+  }
+  if (!p.concat) {
+    const float inv = tot_n > 0 ? 1.f / (float)tot_n : 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[(long long)c * nvox + ovox] = tot[c] * inv;
   }
 }
 
