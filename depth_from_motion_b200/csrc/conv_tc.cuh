@@ -516,8 +516,8 @@ struct TcParams {
   int Di, Hi, Wi;       // input volume
   int Do, Ho, Wo, Cout; // output volume
   int Mx, My;           // extent of the M grid (output grid; input grid for transposed)
-  int tiles_x, tiles_y, nsplit, nseg, seg_len;
-  int n_items;
+  int tiles_x, tiles_y, nsplit;
+  int z_unit;  // granularity of a z cut in output planes (2 for the transposed conv)
   uint32_t w_bytes, w_hi_bytes;
   int* err;
   unsigned long long* role_cycles;  // optional [grid][8] role wait/busy cycle counters
@@ -536,19 +536,40 @@ struct TcParams {
 struct TcItem {
   int x0, y0, split, z_lo, z_hi;
 };
-__device__ __forceinline__ TcItem tc_decode(const TcParams& p, int item) {
-  TcItem it;
-  it.split = item % p.nsplit;
-  int r = item / p.nsplit;
-  const int tx = r % p.tiles_x;
-  r /= p.tiles_x;
-  const int ty = r % p.tiles_y;
-  const int seg = r / p.tiles_y;
-  it.x0 = tx * TC_BX;
-  it.y0 = ty * TC_BY;
-  it.z_lo = seg * p.seg_len;
-  it.z_hi = min(p.Do, it.z_lo + p.seg_len);
-  return it;
+// Work partition ("stream-K" over z): the (tile column, output plane) space of one
+// output-channel split is linearised column-major and cut into gridDim.x / nsplit equal
+// contiguous ranges, one per CTA; a CTA walks its range as pieces that end at column
+// boundaries.  Every CTA gets the same number of planes (+-1 unit), the only overhead is
+// the halo input planes at the 2-3 piece ends.  All roles of a CTA derive the same piece
+// list from blockIdx alone.
+struct TcWalk {
+  long long cur, end;  // in units of `unit` output planes
+  int split;
+};
+__device__ __forceinline__ TcWalk tc_walk_begin(const TcParams& p) {
+  TcWalk w;
+  const int per_split = gridDim.x / p.nsplit;
+  w.split = blockIdx.x % p.nsplit;
+  const int r = blockIdx.x / p.nsplit;
+  const long long units_col = p.Do / p.z_unit;
+  const long long total = (long long)p.tiles_x * p.tiles_y * units_col;
+  w.cur = total * r / per_split;
+  w.end = total * (r + 1) / per_split;
+  return w;
+}
+__device__ __forceinline__ bool tc_walk_next(const TcParams& p, TcWalk& w, TcItem& it) {
+  if (w.cur >= w.end) return false;
+  const long long units_col = p.Do / p.z_unit;
+  const int col = (int)(w.cur / units_col);
+  const long long u0 = w.cur % units_col;
+  const long long u1 = min(units_col, u0 + (w.end - w.cur));
+  it.split = w.split;
+  it.x0 = (col % p.tiles_x) * TC_BX;
+  it.y0 = (col / p.tiles_x) * TC_BY;
+  it.z_lo = (int)u0 * p.z_unit;
+  it.z_hi = (int)u1 * p.z_unit;
+  w.cur += u1 - u0;
+  return true;
 }
 
 // ----------------------------------------------------------------------------------
@@ -641,8 +662,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const bool timed = p.role_cycles != nullptr && tid == 128;
     unsigned long long t_wait_e = 0;
     const long long t_begin = clock64();
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const TcItem it = tc_decode(p, item);
+    TcWalk walk = tc_walk_begin(p);
+    TcItem it;
+    while (tc_walk_next(p, walk, it)) {
       int soff[NITEM], gx[NITEM], gy[NITEM];
       bool inb[NITEM], live[NITEM];
 #pragma unroll
@@ -731,8 +753,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t b_desc_hi = (B_SBO >> 4) | (1u << 14);
       const uint32_t w_hi16 = p.w_hi_bytes >> 4;
       uint32_t stage_ctr = 0, plane_ctr = 0;  // plane_ctr: running index of output planes
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const TcItem it = tc_decode(p, item);
+      TcWalk walk = tc_walk_begin(p);
+      TcItem it;
+      while (tc_walk_next(p, walk, it)) {
         const int zi0 = max(M::zi_first(it.z_lo), 0);
         const int zi1 = min(M::zi_last(it.z_hi - 1), p.Di - 1);
         const uint32_t plane_base = plane_ctr;  // slot of output plane zo: (base + zo - z_lo) % NSLOT
@@ -990,8 +1013,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         ssum[i] = ssq[i] = 0.f;
       }
     };
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const TcItem it = tc_decode(p, item);
+    TcWalk walk = tc_walk_begin(p);
+    TcItem it;
+    while (tc_walk_next(p, walk, it)) {
       cur_split = it.split;
       const int mx = it.x0 + (m & 7), my = it.y0 + (m >> 3);
       const bool ok = mx < p.Mx && my < p.My;
@@ -1158,36 +1182,15 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
   p.w_hi_bytes = w.hi_bytes;
   p.prog[0] = w.prog[0];
   p.prog[1] = w.prog[1];
-  const int base = p.tiles_x * p.tiles_y * p.nsplit;
-  const int grid_cap = std::max(p.nsplit, sms / p.nsplit * p.nsplit);
-  // z segments (in output planes; even lengths for the transposed conv): balance the
-  // persistent grid against the halo planes a cut costs
-  const int unit = MODE == TC_T ? 2 : 1;
-  const int halo = MODE == TC_S1 ? 2 : 1;
-  int best_seg = 1;
-  double best_cost = 1e30;
-  p.seg_len = g.Do;
-  for (int ns = 1; ns <= std::min(g.Do / unit, 16); ++ns) {
-    int len = (g.Do + ns - 1) / ns;
-    len = (len + unit - 1) / unit * unit;
-    const int nseg = (g.Do + len - 1) / len;
-    const long long items = (long long)base * nseg;
-    const long long grid = std::min<long long>(items, grid_cap);
-    const long long rounds = (items + grid - 1) / grid;
-    const double planes_in = MODE == TC_S2 ? 2.0 * len + 1 : MODE == TC_T ? len / 2.0 + 1 : len + 2;
-    const double cost = (double)rounds * planes_in;
-    (void)halo;
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best_seg = nseg;
-      p.seg_len = len;
-    }
-  }
-  p.nseg = best_seg;
-  p.n_items = base * p.nseg;
+  p.z_unit = MODE == TC_T ? 2 : 1;
+  const long long cols = (long long)p.tiles_x * p.tiles_y;
+  const long long units = cols * (g.Do / p.z_unit);
+  // persistent grid: one CTA per SM, a multiple of the output-channel splits; never more
+  // CTAs per split than there are z units
+  int per_split = std::max(1, sms / p.nsplit);
+  per_split = (int)std::min<long long>(per_split, units);
+  const int grid = per_split * p.nsplit;
   p.err = tc_err_flag().get();
-  int grid = std::min(p.n_items, grid_cap);
-  grid = std::max(p.nsplit, grid / p.nsplit * p.nsplit);
   static const bool role_dbg = getenv("DFM_TC_ROLE_CYCLES") != nullptr;
   static const int dbg_flags = getenv("DFM_TC_DEBUG") ? atoi(getenv("DFM_TC_DEBUG")) : 0;
   p.dbg = dbg_flags;
@@ -1206,10 +1209,10 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
     for (int b = 0; b < grid; ++b)
       for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)b * 8 + k] / grid;
     fprintf(stderr,
-            "[tc mode=%d cin=%d ncta=%d grid=%d items=%d seg=%d] mma: total %.0f wait_full_a %.0f "
+            "[tc mode=%d cin=%d ncta=%d grid=%d cols=%lld Do=%d] mma: total %.0f wait_full_a %.0f "
             "wait_empty_acc %.0f | load: total %.0f wait_empty_a %.0f | epi: total %.0f "
             "wait_full_acc %.0f\n",
-            MODE, CIN, NCTA, grid, p.n_items, p.seg_len, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+            MODE, CIN, NCTA, grid, cols, g.Do, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
   }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
