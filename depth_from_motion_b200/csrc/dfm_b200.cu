@@ -473,6 +473,7 @@ int tower_alloc(Tower& t, int D, int Ho, int Wo, int cv) {
   DFM_TRY(t.b4.alloc(V4 * 2 * cv));
   DFM_TRY(t.b5.alloc(V2 * 2 * cv));
   DFM_TRY(t.b6.alloc(V * cv));
+  DFM_TRY(t.cur.alloc(V * cv));
   DFM_TRY(t.p0b.alloc(V * cv));
   DFM_TRY(t.logit.alloc(V));
   DFM_TRY(t.cls5.alloc((size_t)5 * Ho * Wo * cv));
@@ -695,19 +696,29 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
   g = geom_t(D2, H2, W2, 2 * cv, cv);
   DFM_TRY(run_conv(src2(term(t.b5, &t.gc5, 0), term(t.b2, &t.gc2, 1), 1), t.c6, t.b6.p, g, impl,
                    st, &t.gc6, zw_at(1)));
-  // cur_cost = cost0 + gn6(conv6) is only materialised as the NCDHW output the caller asked
-  // for (z-expanded for the shortened mono tower); the pred conv re-evaluates the three terms
+  // cur_cost = cost0 + gn6(conv6): a channels-last copy feeds the pred conv (a one-term load
+  // keeps that conv MMA-bound; the three-term load made it loader-bound), the NCDHW copy
+  // (z-expanded for the shortened mono tower) is the output the caller asked for
   const dfm::Src cur_src = src3(T1, T0, term(t.b6, &t.gc6, 0));
-  if (d_feat_out) {
-    const long long Vfull = (long long)Dfull * Ho * Wo;
-    dim3 grid((unsigned)((Vfull + 31) / 32), (cv + 31) / 32), block(32, 8);
-    dfm::materialize_kernel<<<grid, block, 0, st>>>(cur_src, cv, Vfull, (long long)Ho * Wo, ze,
-                                                    nullptr, d_feat_out);
+  {
+    const dfm::ZExpand ident{D, D, 0, 0};
+    const bool one_pass = !shorten;  // same iteration space for both copies
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((V + 31) / 32), (cv + 31) / 32);
+    dfm::materialize_kernel<<<grid, block, 0, st>>>(cur_src, cv, V, (long long)Ho * Wo, ident,
+                                                    t.cur.p, one_pass ? d_feat_out : nullptr);
     LAUNCH_CHECK();
+    if (!one_pass && d_feat_out) {
+      const long long Vfull = (long long)Dfull * Ho * Wo;
+      dim3 gridf((unsigned)((Vfull + 31) / 32), (cv + 31) / 32);
+      dfm::materialize_kernel<<<gridf, block, 0, st>>>(cur_src, cv, Vfull, (long long)Ho * Wo, ze,
+                                                       nullptr, d_feat_out);
+      LAUNCH_CHECK();
+    }
   }
   // depth prediction module (dfm_backbone.py:118-128)
   g = geom_s(D, Ho, Wo, cv, cv, 1, 1, 1, 1, 1, 1);
-  DFM_TRY(run_conv(cur_src, t.p0, t.p0b.p, g, impl, st, &t.gp0, zw_at(1)));
+  DFM_TRY(run_conv(src1(term(t.cur, nullptr, 0)), t.p0, t.p0b.p, g, impl, st, &t.gp0, zw_at(1)));
   if (impl != DFM_CONV_SIMT && t.p1tc.tc.ready()) {
     std::string err;
     ProfScope ps(conv_class("conv_tc_cout1", g, "src"), 2.0 * V * cv * 27, st);
