@@ -40,6 +40,7 @@ V = D * HO * WO
 FLOPS_PER_FRAME = 521856.0 * V
 IO_BYTES_PER_FRAME = 2 * 32 * H * W * 4 + 5.25e6 + 33 * V * 4
 WORKLOAD = 'dfm_r34_1x8_kitti-3d-3class D=112 384x1248 batch=1'
+NCU_DOMINANT_TRAFFIC_BYTES = 828.6e6   # see profiles/r01_ncu_conv_tc.csv
 
 
 def peaks():
@@ -267,7 +268,13 @@ def run_ours(args):
         per_launch_s = r['ms'] * 1e-3 / r['launches']
         ach = per_launch_flops / per_launch_s / 1e12
         roof = dict(bound='tensor', kernel=dom_key, achieved=round(ach, 2), peak=pk['bf16'],
-                    unit='TFLOP/s', frac=round(ach / pk['bf16'], 4), traffic=None,
+                    unit='TFLOP/s', frac=round(ach / pk['bf16'], 4),
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch,
+                    # from the committed ncu --set full capture (profiles/r01_ncu_conv_tc.csv);
+                    # algorithmic bytes: 429.4 MB in + 429.4 MB out
+                    traffic=NCU_DOMINANT_TRAFFIC_BYTES,
+                    executed_bf16_tflops=round(3 * ach, 1),
+                    executed_frac_of_peak=round(3 * ach / pk['bf16'], 4),
                     peak_source=pk['src'] + ' bf16 dense (sustained)',
                     launches_per_step=r['launches'] / args.steps,
                     ms_per_launch=round(per_launch_s * 1e3, 4),
