@@ -261,7 +261,7 @@ def run_ours(args):
     dom_key = f'conv_tc<32->32,s1,src>@{D}x{HO}x{WO}'
     roof = None
     tc_ms = sum(v['ms'] for k, v in prof.items() if k.startswith('conv_tc'))
-    conv_ms = sum(v['ms'] for v in prof.values())
+    conv_ms = sum(v['ms'] for k, v in prof.items() if k.startswith('conv_'))
     if dom_key in prof:
         r = prof[dom_key]
         per_launch_flops = r['flops'] / r['launches']

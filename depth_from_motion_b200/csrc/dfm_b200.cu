@@ -463,6 +463,22 @@ struct dfm_backbone {
 
 namespace {
 
+// cur_cost materialisation: vectorised kernel for the 32-channel case
+int launch_materialize(const dfm::Src& src, int C, long long V, long long HW, dfm::ZExpand ze,
+                       float* out_cl, float* out_ncdhw, const char* tag, cudaStream_t st) {
+  ProfScope ps(tag, 0.0, st);
+  if (C == 32 && V % 4 == 0 && V < (1LL << 31)) {
+    const int ntiles = (int)((V + 31) / 32);
+    dfm::materialize32_kernel<<<std::min(ntiles, 148 * 16), 256, 0, st>>>(src, (int)V, (int)HW, ze,
+                                                                         out_cl, out_ncdhw);
+  } else {
+    dim3 block(32, 8), grid((unsigned)((V + 31) / 32), (C + 31) / 32);
+    dfm::materialize_kernel<<<grid, block, 0, st>>>(src, C, V, HW, ze, out_cl, out_ncdhw);
+  }
+  LAUNCH_CHECK();
+  return DFM_OK;
+}
+
 int tower_alloc(Tower& t, int D, int Ho, int Wo, int cv) {
   const size_t V = (size_t)D * Ho * Wo, V2 = V / 8, V4 = V / 64;
   DFM_TRY(t.raw0.alloc(V * cv));
@@ -703,18 +719,11 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
   {
     const dfm::ZExpand ident{D, D, 0, 0};
     const bool one_pass = !shorten;  // same iteration space for both copies
-    dim3 block(32, 8);
-    dim3 grid((unsigned)((V + 31) / 32), (cv + 31) / 32);
-    dfm::materialize_kernel<<<grid, block, 0, st>>>(cur_src, cv, V, (long long)Ho * Wo, ident,
-                                                    t.cur.p, one_pass ? d_feat_out : nullptr);
-    LAUNCH_CHECK();
-    if (!one_pass && d_feat_out) {
-      const long long Vfull = (long long)Dfull * Ho * Wo;
-      dim3 gridf((unsigned)((Vfull + 31) / 32), (cv + 31) / 32);
-      dfm::materialize_kernel<<<gridf, block, 0, st>>>(cur_src, cv, Vfull, (long long)Ho * Wo, ze,
-                                                       nullptr, d_feat_out);
-      LAUNCH_CHECK();
-    }
+    DFM_TRY(launch_materialize(cur_src, cv, V, (long long)Ho * Wo, ident, t.cur.p,
+                               one_pass ? d_feat_out : nullptr, "materialize", st));
+    if (!one_pass && d_feat_out)
+      DFM_TRY(launch_materialize(cur_src, cv, (long long)Dfull * Ho * Wo, (long long)Ho * Wo, ze,
+                                 nullptr, d_feat_out, "materialize_expand", st));
   }
   // depth prediction module (dfm_backbone.py:118-128)
   g = geom_s(D, Ho, Wo, cv, cv, 1, 1, 1, 1, 1, 1);
@@ -934,10 +943,14 @@ int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_
                                    std::to_string(bb->missing.size() - 1) + " more)");
   if (!bb->depths_set) return fail(DFM_ERR_STATE, "downsampled_depth not set");
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps_all("backbone_forward_total", 0.0, st);
   const int C = bb->d.in_channels;
   const long long HW = (long long)bb->d.feat_h * bb->d.feat_w;
-  DFM_TRY(to_nhwc(d_cur, bb->cur_nhwc.p, C, HW, st));
-  DFM_TRY(to_nhwc(d_prev, bb->prev_nhwc.p, C, HW, st));
+  {
+    ProfScope ps("nchw_to_nhwc_x2", 0.0, st);
+    DFM_TRY(to_nhwc(d_cur, bb->cur_nhwc.p, C, HW, st));
+    DFM_TRY(to_nhwc(d_prev, bb->prev_nhwc.p, C, HW, st));
+  }
   dfm::WarpLoader wl{};
   wl.cur = bb->cur_nhwc.p;
   wl.prev = bb->prev_nhwc.p;
@@ -955,8 +968,11 @@ int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_
   if (smem > 48 * 1024)
     CU_TRY(cudaFuncSetAttribute(dfm::gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
-  dfm::gate_kernel<<<(HWo + 31) / 32, 128, smem, st>>>(bb->st.logit.p, bb->mo.logit.p, bb->wagg.p,
-                                                       bb->cost.p, bb->D, HWo, ze_mono);
+  {
+    ProfScope ps("gate", 0.0, st);
+    dfm::gate_kernel<<<(HWo + 31) / 32, 128, smem, st>>>(bb->st.logit.p, bb->mo.logit.p,
+                                                         bb->wagg.p, bb->cost.p, bb->D, HWo, ze_mono);
+  }
   LAUNCH_CHECK();
   if (d_cost)
     CU_TRY(cudaMemcpyAsync(d_cost, bb->cost.p, (size_t)bb->D * HWo * sizeof(float),
@@ -1092,8 +1108,11 @@ int dfm_depth_head_forward(const float* d_cost, const float* d_depth_samples, in
   if (!d_cost || !d_depth_samples) return fail(DFM_ERR_INVALID, "null argument");
   if (D < 1 || Ho < 1 || Wo < 1 || factor < 1) return fail(DFM_ERR_INVALID, "bad shape");
   dim3 grid((Wo * factor + 127) / 128, Ho * factor);
-  dfm::depth_head_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
-      d_cost, d_depth_samples, D, Ho, Wo, factor, d_volume, d_softmax, d_preds);
+  {
+    ProfScope ps("depth_head", 0.0, (cudaStream_t)stream);
+    dfm::depth_head_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+        d_cost, d_depth_samples, D, Ho, Wo, factor, d_volume, d_softmax, d_preds);
+  }
   LAUNCH_CHECK();
   return DFM_OK;
 }

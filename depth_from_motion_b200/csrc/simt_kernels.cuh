@@ -320,6 +320,75 @@ materialize_kernel(Src s, int C, long long V, long long HW, ZExpand ze, float* _
   }
 }
 
+// Vectorised variant for C == 32: 256 threads = 32 voxels x 8 channel quads; the per-channel
+// affine parameters of a thread's quad live in registers, loads / channels-last stores are
+// float4, the NCDHW copy goes through a 32x32 shared-memory transpose and is written as
+// float4 runs of 4 consecutive voxels.  Requires V % 4 == 0 for the NCDHW float4 path.
+__global__ void __launch_bounds__(256)
+materialize32_kernel(Src s, int V, int HW, ZExpand ze, float* __restrict__ out_cl,
+                     float* __restrict__ out_ncdhw) {
+  constexpr int C = 32;
+  __shared__ float tile[C][36];
+  const int q = threadIdx.x & 7, vl = threadIdx.x >> 3;
+  float4 sc[3], sh[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    sc[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    sh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < s.n && s.t[i].scale) {
+      sc[i] = __ldg(reinterpret_cast<const float4*>(s.t[i].scale) + q);
+      sh[i] = __ldg(reinterpret_cast<const float4*>(s.t[i].shift) + q);
+    }
+  }
+  const int ntiles = (V + 31) / 32;
+  for (int tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+    const int v = tile_i * 32 + vl;
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (v < V) {
+      const int z = zexpand(ze, v / HW), pos = v % HW;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i < s.n) {
+          const long long off = ((long long)term_plane(s.t[i], z) * HW + pos) * C + 4 * q;
+          float4 a = __ldg(reinterpret_cast<const float4*>(s.t[i].x + off));
+          a.x = fmaf(a.x, sc[i].x, sh[i].x);
+          a.y = fmaf(a.y, sc[i].y, sh[i].y);
+          a.z = fmaf(a.z, sc[i].z, sh[i].z);
+          a.w = fmaf(a.w, sc[i].w, sh[i].w);
+          if (s.t[i].relu) {
+            a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f);
+            a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+          }
+          val.x += a.x; val.y += a.y; val.z += a.z; val.w += a.w;
+        }
+      }
+      if (s.outer_relu) {
+        val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f);
+        val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f);
+      }
+      if (out_cl) *reinterpret_cast<float4*>(out_cl + (long long)v * C + 4 * q) = val;
+    }
+    if (out_ncdhw) {
+      tile[4 * q][vl] = val.x;
+      tile[4 * q + 1][vl] = val.y;
+      tile[4 * q + 2][vl] = val.z;
+      tile[4 * q + 3][vl] = val.w;
+      __syncthreads();
+      const int c = threadIdx.x >> 3, vq = threadIdx.x & 7;
+      const int v0 = tile_i * 32 + 4 * vq;
+      if (v0 + 3 < V) {
+        *reinterpret_cast<float4*>(out_ncdhw + (long long)c * V + v0) =
+            make_float4(tile[c][4 * vq], tile[c][4 * vq + 1], tile[c][4 * vq + 2],
+                        tile[c][4 * vq + 3]);
+      } else {
+        for (int k = 0; k < 4; ++k)
+          if (v0 + k < V) out_ncdhw[(long long)c * V + v0 + k] = tile[c][4 * vq + k];
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // 3x3x3 conv C -> 1 (nn.Conv3d(cv, 1, 3, 1, 1, bias=False), dfm_backbone.py:128).
 // 8 lanes per output voxel, each lane owns 4 of the 32 input channels.
@@ -432,8 +501,12 @@ depth_head_kernel(const float* __restrict__ cost, const float* __restrict__ samp
   const long long plane = (long long)Ho * Wo;
   const long long opix = (long long)Y * OW + X, oplane = (long long)OH * OW;
 
-  // pass 1: running max / sum (online softmax) and, if requested, the raw volume
-  float m = -INFINITY, ssum = 0.f, esum = 0.f;
+  // The upsampled column is piecewise linear in k between the low-res planes, so its maximum
+  // is the maximum of the D (y,x)-interpolated low-res values: no online-softmax rescaling.
+  float m = -INFINITY;
+  for (int z = 0; z < D; ++z) m = fmaxf(m, dh_plane(cost, z * plane, o, w));
+  // pass 1: sum of exponentials and the expectation
+  float ssum = 0.f, esum = 0.f;
   int zc = -1;
   float b0 = 0.f, b1 = 0.f;
   for (int k = 0; k < OD; ++k) {
@@ -447,16 +520,13 @@ depth_head_kernel(const float* __restrict__ cost, const float* __restrict__ samp
       zc = z0;
     }
     const float v = (1.f - lz1) * b0 + lz1 * b1;
-    if (vol) vol[k * oplane + opix] = v;
-    const float mn = fmaxf(m, v);
-    const float corr = __expf(m - mn), e = __expf(v - mn);
-    ssum = ssum * corr + e;
-    esum = esum * corr + e * __ldg(samples + k);
-    m = mn;
+    const float e = __expf(v - m);
+    ssum += e;
+    esum = fmaf(e, __ldg(samples + k), esum);
   }
   if (preds) preds[opix] = esum / ssum;
-  if (!sm) return;
-  // pass 2: normalised probabilities
+  if (!sm && !vol) return;
+  // pass 2: the two 4-D outputs
   const float inv = 1.f / ssum;
   zc = -1;
   for (int k = 0; k < OD; ++k) {
@@ -470,7 +540,8 @@ depth_head_kernel(const float* __restrict__ cost, const float* __restrict__ samp
       zc = z0;
     }
     const float v = (1.f - lz1) * b0 + lz1 * b1;
-    sm[k * oplane + opix] = __expf(v - m) * inv;
+    if (vol) vol[k * oplane + opix] = v;
+    if (sm) sm[k * oplane + opix] = __expf(v - m) * inv;
   }
 }
 
