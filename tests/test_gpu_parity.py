@@ -157,6 +157,28 @@ def test_backbone_midsize_vs_oracle(impl):
         assert e < TOL, (key, e)
 
 
+def test_shipped_kitti_config_shape_vs_oracle():
+    # configs/dfm/dfm_r34_1x8_kitti-3d-3class.py as shipped: 320x1280 crops, num_bins 288 ->
+    # D = 72 planes.  One whole frame through the CPU oracle (~10-20 s on the box's cores)
+    # against the tensor-core path with all shortcuts (z-class first layer, shortened mono
+    # tower) active.
+    h, w, d = 320, 1280, 72
+    cur, prev, metas, params = syn.make_kitti_pair(21, h, w, d, ori_shape=(375, 1242, 3),
+                                                   crop_offset=(0, 55))
+    cfg = syn.depth_cfg_for(d)
+    torch.set_num_threads(max(1, (os.cpu_count() or 8)))
+    with torch.no_grad():
+        ref = O.dfm_backbone_forward(params, cur, prev, metas, cfg)
+    m = _backbone(params, cfg, 'auto')
+    with torch.no_grad():
+        out = m(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
+    capi.sync_check()
+    for got, r, key in zip(out, ref, ('cost', 'stereo', 'mono')):
+        e = rel_err(got, r)
+        print('shipped-shape', key, e)
+        assert e < TOL, (key, e)
+
+
 def test_simt_and_tensor_core_paths_agree():
     h, w, d = 64, 128, 16
     cur, prev, metas, params = syn.make_kitti_pair(6, h, w, d)
