@@ -456,6 +456,7 @@ struct dfm_backbone {
   int D, Ho, Wo;
   Tower st, mo;
   DevBuf cur_nhwc, prev_nhwc, depths, wagg, cost, volume_dbg;
+  DevBuf stage_cur, stage_prev;  // NCHW staging of the host-buffer entry point
   bool depths_set = false;
   std::set<std::string> missing;
   std::map<std::string, std::pair<const DevBuf*, int>> dbg;  // name -> (buffer, channels)
@@ -885,7 +886,7 @@ int dfm_backbone_destroy(dfm_backbone_t* bb) {
   tower_release(bb->st);
   tower_release(bb->mo);
   for (DevBuf* b : {&bb->cur_nhwc, &bb->prev_nhwc, &bb->depths, &bb->wagg, &bb->cost,
-                    &bb->volume_dbg})
+                    &bb->volume_dbg, &bb->stage_cur, &bb->stage_prev})
     b->release();
   delete bb;
   return DFM_OK;
@@ -934,9 +935,15 @@ long long dfm_backbone_workspace_bytes(const dfm_backbone_t* bb) {
   return n;
 }
 
-int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_prev,
-                         const dfm_geometry_t* geom, float* d_cost, float* d_stereo,
-                         float* d_mono, void* stream) {
+}  // extern "C"
+
+namespace {
+// prev_ready: optional event after which d_prev may be read (host-buffer entry point: the
+// prev-frame H2D copy runs on a second stream underneath the mono tower, which needs only
+// the cur-frame features)
+int backbone_forward_impl(dfm_backbone_t* bb, const float* d_cur, const float* d_prev,
+                          const dfm_geometry_t* geom, float* d_cost, float* d_stereo,
+                          float* d_mono, void* stream, cudaEvent_t prev_ready) {
   if (!bb || !d_cur || !d_prev || !geom) return fail(DFM_ERR_INVALID, "null argument");
   if (!bb->missing.empty())
     return fail(DFM_ERR_STATE, "missing parameter: " + *bb->missing.begin() + " (+" +
@@ -947,9 +954,8 @@ int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_
   const int C = bb->d.in_channels;
   const long long HW = (long long)bb->d.feat_h * bb->d.feat_w;
   {
-    ProfScope ps("nchw_to_nhwc_x2", 0.0, st);
+    ProfScope ps("nchw_to_nhwc_cur", 0.0, st);
     DFM_TRY(to_nhwc(d_cur, bb->cur_nhwc.p, C, HW, st));
-    DFM_TRY(to_nhwc(d_prev, bb->prev_nhwc.p, C, HW, st));
   }
   dfm::WarpLoader wl{};
   wl.cur = bb->cur_nhwc.p;
@@ -960,8 +966,13 @@ int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_
   DFM_TRY(make_warp_geom(geom, bb->d.feat_h, bb->d.feat_w, bb->d.cost_sample_factor,
                          bb->d.feat_sample_factor, &wl.g));
   dfm::ZExpand ze_mono{bb->D, bb->D, 0, 0};
-  DFM_TRY(tower_forward(bb, bb->st, false, wl, d_stereo, st, nullptr));
   DFM_TRY(tower_forward(bb, bb->mo, true, wl, d_mono, st, &ze_mono));
+  if (prev_ready) CU_TRY(cudaStreamWaitEvent(st, prev_ready, 0));
+  {
+    ProfScope ps("nchw_to_nhwc_prev", 0.0, st);
+    DFM_TRY(to_nhwc(d_prev, bb->prev_nhwc.p, C, HW, st));
+  }
+  DFM_TRY(tower_forward(bb, bb->st, false, wl, d_stereo, st, nullptr));
   // mono/stereo gate (dfm_backbone.py:130-141)
   const int HWo = bb->Ho * bb->Wo;
   const size_t smem = (size_t)2 * bb->D * 32 * sizeof(float);
@@ -979,6 +990,15 @@ int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_
                            cudaMemcpyDeviceToDevice, st));
   return DFM_OK;
 }
+}  // namespace
+
+extern "C" {
+
+int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_prev,
+                         const dfm_geometry_t* geom, float* d_cost, float* d_stereo,
+                         float* d_mono, void* stream) {
+  return backbone_forward_impl(bb, d_cur, d_prev, geom, d_cost, d_stereo, d_mono, stream, nullptr);
+}
 
 const float* dfm_backbone_cost_device(const dfm_backbone_t* bb) { return bb ? bb->cost.p : nullptr; }
 
@@ -989,12 +1009,23 @@ int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const floa
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nfeat = (size_t)bb->d.in_channels * bb->d.feat_h * bb->d.feat_w;
   const size_t V = (size_t)bb->D * bb->Ho * bb->Wo;
-  // staging: NCHW inputs land in the (otherwise later-written) p0 buffers of the towers
-  float* d_cur = bb->st.p0b.p;
-  float* d_prev = bb->mo.p0b.p;
-  if (nfeat > bb->st.p0b.n) return fail(DFM_ERR_INVALID, "feature map larger than staging buffer");
+  DFM_TRY(bb->stage_cur.alloc(nfeat));
+  DFM_TRY(bb->stage_prev.alloc(nfeat));
+  float* d_cur = bb->stage_cur.p;
+  float* d_prev = bb->stage_prev.p;
+  // the prev-frame copy rides a second stream underneath the mono tower
+  static cudaStream_t copy_stream = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_prev = nullptr;
+  if (!copy_stream) {
+    CU_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ev_prev, cudaEventDisableTiming));
+  }
+  CU_TRY(cudaEventRecord(ev_fork, st));  // staging buffers are free once prior work is done
+  CU_TRY(cudaStreamWaitEvent(copy_stream, ev_fork, 0));
   CU_TRY(cudaMemcpyAsync(d_cur, h_cur, nfeat * 4, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(d_prev, h_prev, nfeat * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(d_prev, h_prev, nfeat * 4, cudaMemcpyHostToDevice, copy_stream));
+  CU_TRY(cudaEventRecord(ev_prev, copy_stream));
   float* d_st = nullptr;
   float* d_mo = nullptr;
   DevBuf tmp_s, tmp_m;
@@ -1006,7 +1037,7 @@ int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const floa
     DFM_TRY(tmp_m.alloc(V * 32));
     d_mo = tmp_m.p;
   }
-  int rc = dfm_backbone_forward(bb, d_cur, d_prev, geom, nullptr, d_st, d_mo, stream);
+  int rc = backbone_forward_impl(bb, d_cur, d_prev, geom, nullptr, d_st, d_mo, stream, ev_prev);
   if (rc == DFM_OK && (out_flags & DFM_OUT_COST) && h_cost)
     if (cudaMemcpyAsync(h_cost, bb->cost.p, V * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
       rc = fail(DFM_ERR_CUDA, "D2H copy of cost failed");
