@@ -1,0 +1,435 @@
+// tcgen05 3x3x3 conv for the BEV necks (DfMNeck / OutdoorImVoxelNeck):
+// 64..256 channels on a [Nx=220][Ny=300][Nz<=12] voxel grid, strides (1,1,1) / (1,1,2),
+// pads (1,1,1) / (1,1,0).
+//
+// Same operand formulation as conv_tc.cuh (bf16 hi/lo split, K-major no-swizzle bricks, one
+// brick serves the 9 in-plane taps, kz folded into N), but the loop nest is K-outer because
+// the weights (27*Cin*Cout*4 B, up to 7 MB) cannot stay resident:
+//   * a CTA owns a 16 (x) x 8 (y) tile and ALL (<= 12) output planes of the short z axis;
+//     their accumulators (32 output channels each) live in TMEM for the whole item;
+//   * for each 32-channel input group: copy that group's 110.6 KB weight image to shared
+//     memory, then march the input planes through the usual loader -> MMA pipeline;
+//   * after the last group the epilogue drains the planes (raw conv output; BatchNorm/ReLU
+//     are applied by the consumer's load, like everywhere else).
+#pragma once
+#include "conv_tc.cuh"
+
+namespace dfm {
+
+constexpr int NK_BX = 8, NK_BY = 16;           // tile: 8 along y (brick x), 16 along x (brick y)
+constexpr int NK_PX = NK_BX + 2, NK_PY = NK_BY + 2;
+constexpr int NK_ROWS = 186;                    // 180 brick rows padded (== 2 mod 8)
+constexpr int NK_NSTAGE = 4;
+constexpr int NK_NCTA = 32;                     // output channels per CTA
+constexpr uint32_t NK_STAGE_BYTES = 2 * 4 * NK_ROWS * 16;
+constexpr uint32_t NK_TAP16 = 4 * 96;           // one in-plane tap of a group image, 16 B units
+constexpr uint32_t NK_WHI_BYTES = 9 * NK_TAP16 * 16;
+constexpr uint32_t NK_W_BYTES = 2 * NK_WHI_BYTES;
+constexpr int NK_LOAD_THREADS = 256;
+constexpr int NK_THREADS = 128 + NK_LOAD_THREADS + 32;
+
+enum { NKZ_S1P1 = 0, NKZ_S2P1 = 1, NKZ_S1P0 = 2 };
+
+inline int nk_zmode(const ConvGeom& g) {
+  if (g.transposed || g.sd != 1 || g.sh != 1 || g.pd != 1 || g.ph != 1) return -1;
+  if (g.Cin % 32 || g.Cout % 32 || g.Cin < 64 || g.Wo > 16) return -1;
+  if (g.sw == 1 && g.pw == 1) return NKZ_S1P1;
+  if (g.sw == 2 && g.pw == 1 && g.Wi % 2 == 0) return NKZ_S2P1;
+  if (g.sw == 1 && g.pw == 0 && g.Wo == 1 && g.Wi == 3) return NKZ_S1P0;
+  return -1;
+}
+
+struct NeckTcWeights {
+  uint8_t* dev = nullptr;  // [nsplit][ncg][NK_W_BYTES]
+  int Cin = 0, Cout = 0, zmode = -1;
+  bool ready() const { return dev != nullptr; }
+  void release() {
+    if (dev) cudaFree(dev);
+    dev = nullptr;
+  }
+  // packed: [27][Cin][Cout] fp32, tap = kz*9 + ky*3 + kx with (kz,ky,kx) over (Nz, Ny, Nx)...
+  // NOTE the conv dims are (D,H,W) = (Nx, Ny, Nz): the packed tap index is kd*9 + kh*3 + kw,
+  // i.e. kd over Nx, kh over Ny, kw over Nz (the short, marched axis).
+  bool build(const float* packed, int cin, int cout, int zm, std::string* err) {
+    release();
+    Cin = cin;
+    Cout = cout;
+    zmode = zm;
+    const int nsplit = cout / 32, ncg = cin / 32;
+    // order of the three marched-axis taps inside an image (see kernel): consecutive row
+    // blocks must land in consecutive output planes
+    const int order[3][3] = {{2, 1, 0}, {2, 0, 1}, {0, 1, 2}};
+    std::vector<uint16_t> img((size_t)nsplit * ncg * NK_W_BYTES / 2);
+    for (int s = 0; s < nsplit; ++s)
+      for (int cg = 0; cg < ncg; ++cg)
+        for (int t = 0; t < 9; ++t) {      // in-plane tap: kd (Nx) * 3 + kh (Ny)
+          const int kd = t / 3, kh = t % 3;
+          for (int kc = 0; kc < 4; ++kc)
+            for (int r = 0; r < 96; ++r)
+              for (int e = 0; e < 8; ++e) {
+                const int kw = order[zm][r / 32];
+                const int co = s * 32 + r % 32, ci = cg * 32 + kc * 8 + e;
+                const int tap = kd * 9 + kh * 3 + kw;
+                const float w = packed[((size_t)tap * cin + ci) * cout + co];
+                const uint16_t hi = bf16_rn_bits(w);
+                const uint16_t lo = bf16_rn_bits(w - bf16_bits_to_float(hi));
+                const size_t base = ((size_t)s * ncg + cg) * (NK_W_BYTES / 2);
+                const size_t off = base + (((size_t)t * 4 + kc) * 96 + r) * 8 + e;
+                img[off] = hi;
+                img[off + NK_WHI_BYTES / 2] = lo;
+              }
+        }
+    if (cudaMalloc(&dev, img.size() * 2) != cudaSuccess ||
+        cudaMemcpy(dev, img.data(), img.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+      if (err) *err = "NeckTcWeights: device upload failed";
+      release();
+      return false;
+    }
+    return true;
+  }
+};
+
+struct NeckParams {
+  const uint8_t* wimg;
+  float* out;
+  Src src;
+  int Nx, Ny, Zi, Zo, Cin, Cout;
+  int zmode;
+  int tiles_x, tiles_y, nsplit, ncg, n_items;
+  int* err;
+};
+
+// 8 consecutive channels of input voxel (ix, iy, iz), with the fused input transform
+template <int NT>
+struct NeckLoader {
+  struct Raw {
+    float4 a[NT][2];
+  };
+  static __device__ __forceinline__ void issue(const NeckParams& p, long long vox, int c0, Raw& r) {
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const float* px = p.src.t[t].x + vox * p.Cin + c0;
+      r.a[t][0] = __ldg(reinterpret_cast<const float4*>(px));
+      r.a[t][1] = __ldg(reinterpret_cast<const float4*>(px) + 1);
+    }
+  }
+  static __device__ __forceinline__ void finish(const NeckParams& p, const Raw& r, int c0,
+                                                float v[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      float u[8] = {r.a[t][0].x, r.a[t][0].y, r.a[t][0].z, r.a[t][0].w,
+                    r.a[t][1].x, r.a[t][1].y, r.a[t][1].z, r.a[t][1].w};
+      const Term& tm = p.src.t[t];
+      if (tm.scale) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(tm.scale + c0));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(tm.scale + c0) + 1);
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(tm.shift + c0));
+        const float4 h1 = __ldg(reinterpret_cast<const float4*>(tm.shift + c0) + 1);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = fmaf(u[i], sc[i], sh[i]);
+      }
+      if (tm.relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = fmaxf(u[i], 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += u[i];
+    }
+    if (p.src.outer_relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+  }
+};
+
+// which weight rows / output planes input plane iz feeds: rows [n0, n0+n) -> planes zo0...
+__device__ __forceinline__ void nk_plane_map(int zmode, int iz, int Zo, int& n0, int& nblk,
+                                             int& zo0) {
+  if (zmode == NKZ_S1P1) {        // rows [kw=2|1|0] -> planes iz-1, iz, iz+1
+    const int lo = iz - 1 < 0 ? 1 : 0, hi = iz + 1 >= Zo ? 1 : 2;
+    n0 = lo * 32;
+    nblk = hi - lo + 1;
+    zo0 = iz - 1 + lo;
+  } else if (zmode == NKZ_S2P1) { // rows [kw=2|0|1]; iz = 2q+1 -> planes q, q+1; iz = 2q -> q
+    const int q = iz >> 1;
+    if (iz & 1) {
+      n0 = 0;
+      nblk = q + 1 < Zo ? 2 : 1;
+      zo0 = q;
+    } else {
+      n0 = 64;
+      nblk = 1;
+      zo0 = q;
+    }
+  } else {                        // pad 0, single output plane: kw = iz
+    n0 = iz * 32;
+    nblk = 1;
+    zo0 = 0;
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NK_THREADS, 1)
+neck_conv_kernel(const __grid_constant__ NeckParams p) {
+  constexpr uint32_t A_LBO = NK_ROWS * 16, A_SBO = NK_PX * 16, A_HL = 4 * NK_ROWS * 16;
+  constexpr uint32_t A_LBO16 = A_LBO >> 4, A_HL16 = A_HL >> 4, B_LBO16 = 96;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr int NPOS = NK_PX * NK_PY, LG_THREADS = NK_LOAD_THREADS / 2;
+  constexpr int NITEM = (NPOS * 4 + LG_THREADS - 1) / LG_THREADS;
+  constexpr int LB = 6 / NT;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* w_s = smem;
+  uint8_t* a_s = smem + NK_W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + NK_NSTAGE * NK_STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NK_NSTAGE + 4);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_a = [&](int s) { return bar0 + 8u * s; };
+  auto empty_a = [&](int s) { return bar0 + 8u * (NK_NSTAGE + s); };
+  const uint32_t w_full = bar0 + 8u * (2 * NK_NSTAGE), w_empty = w_full + 8;
+  const uint32_t acc_full = w_full + 16, acc_empty = w_full + 24;
+  constexpr int MMA_WARP = NK_THREADS / 32 - 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < NK_NSTAGE; ++s) {
+      mbar_init(full_a(s), LG_THREADS / 32);
+      mbar_init(empty_a(s), 1);
+    }
+    mbar_init(w_full, NK_LOAD_THREADS / 32);
+    mbar_init(w_empty, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp < 4) {  // accumulators start at zero and are re-zeroed by the epilogue
+    for (uint32_t c = 0; c < TMEM_COLS; c += 64)
+      tmem_zero<64>(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  const int split = blockIdx.x % p.nsplit;
+
+  if (warp >= 4 && warp < MMA_WARP) {
+    // ============================ loaders ============================
+    const int lw = warp - 4, lgrp = lw & 1;
+    const int lt = (lw >> 1) * 32 + lane, lall = lw * 32 + lane;
+    const int chunk = lt & 3;
+    uint32_t stage_ctr = 0, w_ctr = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int tile = item / p.nsplit;
+      const int y0 = (tile % p.tiles_x) * NK_BX, x0 = (tile / p.tiles_x) * NK_BY;
+      for (int cg = 0; cg < p.ncg; ++cg, ++w_ctr) {
+        // this group's weight image (all loader threads), once the previous group's MMAs retired
+        mbar_wait(w_empty, (w_ctr & 1) ^ 1, p.err);
+        {
+          const uint4* src = reinterpret_cast<const uint4*>(
+              p.wimg + ((size_t)split * p.ncg + cg) * NK_W_BYTES);
+          uint4* dst = reinterpret_cast<uint4*>(w_s);
+          for (uint32_t i = lall; i < NK_W_BYTES / 16; i += NK_LOAD_THREADS) dst[i] = __ldg(src + i);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(w_full);
+        }
+        for (int iz = 0; iz < p.Zi; ++iz, ++stage_ctr) {
+          if ((int)(stage_ctr & 1) != lgrp) continue;
+          const int s = stage_ctr % NK_NSTAGE;
+          mbar_wait(empty_a(s), ((stage_ctr / NK_NSTAGE) & 1) ^ 1, p.err);
+          uint8_t* st = a_s + s * NK_STAGE_BYTES;
+          const int c0 = cg * 32 + chunk * 8;
+#pragma unroll
+          for (int k0 = 0; k0 < NITEM; k0 += LB) {
+            typename NeckLoader<NT>::Raw raw[LB];
+            bool inb[LB], live[LB];
+            int soff[LB];
+#pragma unroll
+            for (int b = 0; b < LB; ++b) {
+              const int i = lt + (k0 + b) * LG_THREADS;
+              live[b] = (k0 + b) < NITEM && i < NPOS * 4;
+              const int pos = i >> 2;
+              const int bx = pos % NK_PX, by = pos / NK_PX;
+              const int gy = y0 - 1 + bx, gx = x0 - 1 + by;
+              inb[b] = live[b] && gx >= 0 && gx < p.Nx && gy >= 0 && gy < p.Ny;
+              soff[b] = (chunk * NK_ROWS + pos) * 16;
+              if (inb[b])
+                NeckLoader<NT>::issue(p, ((long long)gx * p.Ny + gy) * p.Zi + iz, c0, raw[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < LB; ++b) {
+              if (live[b]) {
+                float v[8];
+                if (inb[b]) {
+                  NeckLoader<NT>::finish(p, raw[b], c0, v);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                }
+                split_store(v, st + soff[b], st + A_HL + soff[b]);
+              }
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_a(s));
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ============================ MMA issuer (warp-uniform) ============================
+    const uint32_t w_base = smem_u32(w_s), a_base = smem_u32(a_s);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a_desc_hi = (A_SBO >> 4) | (1u << 14), b_desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t w_hi16 = NK_WHI_BYTES >> 4;
+    uint32_t stage_ctr = 0, w_ctr = 0, item_ctr = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_ctr) {
+      // the previous item's accumulators must have been drained (and re-zeroed)
+      mbar_wait(acc_empty, (item_ctr & 1) ^ 1, p.err);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int cg = 0; cg < p.ncg; ++cg, ++w_ctr) {
+        mbar_wait(w_full, w_ctr & 1, p.err);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int iz = 0; iz < p.Zi; ++iz, ++stage_ctr) {
+          const int s = stage_ctr % NK_NSTAGE;
+          mbar_wait(full_a(s), (stage_ctr / NK_NSTAGE) & 1, p.err);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          int n0, nblk, zo0;
+          nk_plane_map(p.zmode, iz, p.Zo, n0, nblk, zo0);
+          const uint32_t d0 = tmem_u + (uint32_t)zo0 * NK_NCTA;
+          const uint32_t idesc = idesc_bf16(nblk * NK_NCTA);
+          const uint32_t a_lo_stage = (((a_base + s * NK_STAGE_BYTES) >> 4) & 0x3FFF) | (A_LBO16 << 16);
+          const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFF) + (uint32_t)n0 + (B_LBO16 << 16);
+          uint64_t da[2][2], db[2][2];
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            da[ks][0] = pack64(a_lo_stage + 2 * ks * A_LBO16, a_desc_hi);
+            da[ks][1] = pack64(a_lo_stage + 2 * ks * A_LBO16 + A_HL16, a_desc_hi);
+            db[ks][0] = pack64(b_lo0 + 2 * ks * B_LBO16, b_desc_hi);
+            db[ks][1] = pack64(b_lo0 + 2 * ks * B_LBO16 + w_hi16, b_desc_hi);
+          }
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                umma_bf16(d0, da[ks][0], db[ks][0], idesc, 1u);
+                umma_bf16(d0, da[ks][1], db[ks][0], idesc, 1u);
+                umma_bf16(d0, da[ks][0], db[ks][1], idesc, 1u);
+              }
+            }
+            const uint32_t ainc = (tap == 2 || tap == 5) ? (uint32_t)(NK_PX - 2) : 1u;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              desc_add(da[ks][0], ainc);
+              desc_add(da[ks][1], ainc);
+              desc_add(db[ks][0], NK_TAP16);
+              desc_add(db[ks][1], NK_TAP16);
+            }
+          }
+          if (elect_one()) umma_commit(empty_a(s));
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(w_empty);  // weights may be replaced once these retire
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(acc_full);
+      __syncwarp();
+    }
+  } else {
+    // ============================ epilogue (warps 0-3) ============================
+    const int m = warp * 32 + lane;
+    uint32_t item_ctr = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_ctr) {
+      const int tile = item / p.nsplit;
+      const int y = (tile % p.tiles_x) * NK_BX + (m & 7), x = (tile / p.tiles_x) * NK_BY + (m >> 3);
+      const bool ok = x < p.Nx && y < p.Ny;
+      mbar_wait(acc_full, item_ctr & 1, p.err);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int zo = 0; zo < p.Zo; ++zo) {
+        uint32_t r[NK_NCTA];
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)zo * NK_NCTA;
+        tmem_ld<NK_NCTA>(ta, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_zero<NK_NCTA>(ta);
+        if (ok) {
+          float4* dst = reinterpret_cast<float4*>(
+              p.out + (((long long)x * p.Ny + y) * p.Zo + zo) * p.Cout + split * NK_NCTA);
+#pragma unroll
+          for (int q = 0; q < NK_NCTA / 4; ++q)
+            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                 __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == MMA_WARP)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(TMEM_COLS));
+}
+
+inline bool neck_tc_conv(const Src& s, const NeckTcWeights& w, float* out, const ConvGeom& g,
+                         cudaStream_t st, std::string* err) {
+  const size_t smem = NK_W_BYTES + (size_t)NK_NSTAGE * NK_STAGE_BYTES + (2 * NK_NSTAGE + 4) * 8 + 16;
+  NeckParams p{};
+  p.wimg = w.dev;
+  p.out = out;
+  p.src = s;
+  p.Nx = g.Di; p.Ny = g.Hi; p.Zi = g.Wi; p.Zo = g.Wo;
+  p.Cin = g.Cin; p.Cout = g.Cout;
+  p.zmode = w.zmode;
+  p.tiles_x = (g.Hi + NK_BX - 1) / NK_BX;   // along Ny
+  p.tiles_y = (g.Di + NK_BY - 1) / NK_BY;   // along Nx
+  p.nsplit = g.Cout / 32;
+  p.ncg = g.Cin / 32;
+  p.n_items = p.tiles_x * p.tiles_y * p.nsplit;
+  p.err = tc_err_flag().get();
+  const int sms = tc_sm_count();
+  int grid = std::max(p.nsplit, sms / p.nsplit * p.nsplit);
+  grid = std::min(grid, p.n_items);
+  grid = std::max(p.nsplit, grid / p.nsplit * p.nsplit);
+  auto launch = [&](auto kern) -> bool {
+    // (both instantiations share one function-pointer type, so no static "done" flag here)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess) {
+      if (err) *err = "neck_tc_conv: cannot reserve shared memory";
+      return false;
+    }
+    kern<<<grid, NK_THREADS, smem, st>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("neck_tc_conv launch: ") + cudaGetErrorString(e);
+      return false;
+    }
+    return true;
+  };
+  if (s.n == 1) return launch(neck_conv_kernel<1>);
+  if (s.n == 2) return launch(neck_conv_kernel<2>);
+  if (err) *err = "neck_tc_conv: at most two input terms";
+  return false;
+}
+
+}  // namespace dfm

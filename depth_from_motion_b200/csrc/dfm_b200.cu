@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc_neck.cuh"
 #include "simt_kernels.cuh"
 
 namespace {
@@ -142,6 +143,7 @@ struct ConvW {
   int Cin = 0, Cout = 0, transposed = 0;
   DevBuf simt;          // [27][Cin][Cout] fp32
   dfm::TcWeights tc;    // bf16 hi/lo images for the tensor-core kernel
+  dfm::NeckTcWeights ntc;  // K-outer tensor-core kernel of the BEV necks
 };
 
 // (Cout,Cin,3,3,3) or transposed (Cin,Cout,3,3,3)  ->  [tap][ci][co]

@@ -59,7 +59,7 @@ def main():
         x = torch.from_numpy(rng.standard_normal((1, cin, 220, 300, 12)).astype(np.float32)).cuda()
         ms = timeit(lambda: mod(x), n=1)
         flops = 3.212e12 if cin == 64 else 7.649e12
-        out[name] = dict(ms=round(ms, 1), tflops=round(flops / ms / 1e9, 2), impl='fp32 SIMT')
+        out[name] = dict(ms=round(ms, 1), tflops=round(flops / ms / 1e9, 2), impl='tcgen05 K-outer conv (conv_tc_neck.cuh)')
     print(json.dumps(out))
 
 
