@@ -309,8 +309,9 @@ def run_ours(args):
         clocks=clocks,
         e2e=dict(value=e2e_fps, unit='frames/s', h2d_bytes_per_step=h2d,
                  d2h_bytes_per_step=d2h,
-                 what='dfm_backbone_forward_host (pinned host features in, logits out) + '
-                      'dfm_depth_head_forward (depth_preds out); stereo_feat stays on device'),
+                 what='dfm_backbone_forward_host (pinned host features in, logits out; the '
+                      'prev-frame copy overlaps the mono tower) + dfm_depth_head_forward '
+                      '(depth_preds out); stereo_feat stays on device for the next stage'),
         gpu_launches=l1 - l0, tc_launches=tc1 - tc0,
         roofline=roof,
         tensor=dict(achieved_tflops=round(FLOPS_PER_FRAME * fps / world / 1e12, 2),

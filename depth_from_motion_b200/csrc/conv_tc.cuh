@@ -23,9 +23,16 @@
 //   * weights (hi+lo images of all 27 taps, <= 110.6 KB) stay resident in shared
 //     memory for the life of the CTA; layers with Cin*Cout > 1024 are split over
 //     output-channel groups of NCTA = 1024/Cin handled by different CTAs.
-//   * warp roles: warps 0-3 epilogue (TMEM -> registers -> global), warps 4-7 loaders,
-//     warp 8 lane 0 issues every tcgen05.mma / tcgen05.commit; smem stages and TMEM
-//     slots are handed over with mbarriers.
+//   * warp roles: warps 0-3 epilogue (TMEM -> registers -> global, GroupNorm sums), warps 4-11
+//     loaders (two groups filling alternate stages), warp 12 issues every tcgen05.mma /
+//     tcgen05.commit from warp-uniform code; smem stages and TMEM slots are handed over with
+//     mbarriers.  Accumulators are only ever accumulated into: the epilogue re-zeroes a slot
+//     after draining it.
+//   * modes: stride 1 (TC_S1), stride 2 (TC_S2, x/y parity sub-bricks) and the stride-2
+//     transposed conv (TC_T, 4 (px,py) parity classes per output plane); the work of a launch
+//     is cut "stream-K" style into equal contiguous (tile column, plane) ranges per CTA.
+//   * diagnosis: DFM_TC_ROLE_CYCLES=1 prints per-role busy / wait cycles of every launch,
+//     DFM_TC_DEBUG=<bits> disables roles (1 loaders, 2 epilogue, 8 proxy fence).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -60,7 +67,6 @@ inline float bf16_bits_to_float(uint16_t b) {
 // ----------------------------------------------------------------------------------
 enum { TC_S1 = 0, TC_S2 = 1, TC_T = 2 };
 constexpr int TC_BX = 8, TC_BY = 16;  // M tile: 8 (x) * 16 (y) = 128 accumulator rows
-constexpr int TC_NSLOT_MAX = 16;
 constexpr int TC_LOAD_THREADS = 256;
 constexpr int TC_THREADS = 128 + TC_LOAD_THREADS + 32;  // epilogue | loaders | MMA issuer
 constexpr int TC_MAXOPS = 9, TC_MAXBLK = 32;

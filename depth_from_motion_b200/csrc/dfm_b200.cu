@@ -114,8 +114,6 @@ struct DevBuf {
   }
 };
 
-size_t g_dummy = 0;
-
 struct Norm {  // GroupNorm (statistics computed per frame) or folded BatchNorm (static)
   int C = 0;
   DevBuf gamma, beta, scale, shift;

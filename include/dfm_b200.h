@@ -106,8 +106,8 @@ int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const floa
  * (lets a host-buffer caller chain dfm_depth_head_forward without a round trip). */
 const float* dfm_backbone_cost_device(const dfm_backbone_t* bb);
 /* Test hook: copies a named intermediate (channels-last [D][H][W][C]) to d_out.
- * Names: "volume" (only kept when conv_impl == DFM_CONV_SIMT), "raw0", "raw1", "c1".."c6",
- * "cur", "p0", "logit" with suffix "_mono" for the mono tower. */
+ * Names: "raw0", "raw1", "c1".."c6", "p0", "logit", with suffix "_mono" for the mono tower
+ * (which may hold the z-shortened volume). */
 int dfm_backbone_debug_tensor(dfm_backbone_t* bb, const char* name, float* d_out,
                               long long numel, void* stream);
 /* Synchronises `stream` and reports asynchronous failures of this library's kernels
