@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, 'libdfm_b200.so')
 DFM_OK = 0
 DFM_CONV_AUTO, DFM_CONV_SIMT, DFM_CONV_TC = 0, 1, 2
 DFM_OUT_COST, DFM_OUT_STEREO, DFM_OUT_MONO = 1, 2, 4
+DFM_LAYOUT_NCDHW, DFM_LAYOUT_DHWC = 0, 1
 
 # every symbol include/dfm_b200.h declares (tests/test_capi_symbols.py checks the
 # header against this list and against the built library)
@@ -26,10 +27,12 @@ SYMBOLS = (
     'dfm_backbone_set_depths', 'dfm_backbone_missing_params',
     'dfm_backbone_workspace_bytes', 'dfm_backbone_forward',
     'dfm_backbone_forward_host', 'dfm_backbone_cost_device',
+    'dfm_backbone_stereo_feat_device',
     'dfm_backbone_debug_tensor', 'dfm_op_build_cost_volume', 'dfm_op_conv3d',
     'dfm_depth_head_forward', 'dfm_multiview_lift', 'dfm_neck_create',
     'dfm_neck_destroy', 'dfm_neck_set_param', 'dfm_neck_missing_params',
-    'dfm_neck_forward',
+    'dfm_neck_forward', 'dfm_frustum_create', 'dfm_frustum_destroy',
+    'dfm_frustum_set_param', 'dfm_frustum_missing_params', 'dfm_frustum_forward',
 )
 
 
@@ -64,6 +67,17 @@ class NeckDesc(ctypes.Structure):
     _fields_ = [('in_channels', c_int), ('out_channels', c_int),
                 ('num_frames', c_int), ('nx', c_int), ('ny', c_int),
                 ('nz', c_int), ('conv_impl', c_int)]
+
+
+class FrustumDesc(ctypes.Structure):
+    """``dfm_frustum_desc_t``."""
+    _fields_ = [(n, c_int) for n in
+                ('num_3dconvs', 'cv_channels', 'out_channels', 'in_sem_channels',
+                 'sem_atten_feat', 'stereo_atten_feat', 'cat_img_feature',
+                 'num_planes', 'feat_h', 'feat_w', 'sem_h', 'sem_w',
+                 'depth_factor', 'nx', 'ny', 'nz')] + \
+               [('depth_min', c_float), ('depth_max', c_float),
+                ('conv_impl', c_int)]
 
 
 _lib = None
@@ -104,6 +118,8 @@ def lib():
                                             c_int, vp, vp, vp, vp]
     L.dfm_backbone_cost_device.argtypes = [vp]
     L.dfm_backbone_cost_device.restype = vp
+    L.dfm_backbone_stereo_feat_device.argtypes = [vp]
+    L.dfm_backbone_stereo_feat_device.restype = vp
     L.dfm_backbone_debug_tensor.argtypes = [vp, c_char_p, vp, c_longlong, vp]
     L.dfm_op_build_cost_volume.argtypes = [vp, vp, c_int, c_int, c_int, vp,
                                            c_int, c_int, c_int,
@@ -120,6 +136,13 @@ def lib():
     L.dfm_neck_set_param.argtypes = [vp, c_char_p, vp, c_longlong]
     L.dfm_neck_missing_params.argtypes = [vp]
     L.dfm_neck_forward.argtypes = [vp, vp, vp, vp]
+    L.dfm_frustum_create.argtypes = [POINTER(FrustumDesc), vp, vp, vp,
+                                     POINTER(vp)]
+    L.dfm_frustum_destroy.argtypes = [vp]
+    L.dfm_frustum_set_param.argtypes = [vp, c_char_p, vp, c_longlong]
+    L.dfm_frustum_missing_params.argtypes = [vp]
+    L.dfm_frustum_forward.argtypes = [vp, vp, c_int, vp, vp, vp, vp, vp,
+                                      POINTER(c_double), c_int, c_int, vp, vp]
     _lib = L
     return L
 

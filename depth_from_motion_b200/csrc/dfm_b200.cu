@@ -16,6 +16,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc_neck.cuh"
 #include "simt_kernels.cuh"
+#include "frustum_kernels.cuh"
 
 namespace {
 
@@ -1001,6 +1002,9 @@ int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_
 }
 
 const float* dfm_backbone_cost_device(const dfm_backbone_t* bb) { return bb ? bb->cost.p : nullptr; }
+const float* dfm_backbone_stereo_feat_device(const dfm_backbone_t* bb) {
+  return bb ? bb->st.cur.p : nullptr;
+}
 
 int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const float* h_prev,
                               const dfm_geometry_t* geom, int out_flags, float* h_cost,
@@ -1138,10 +1142,10 @@ int dfm_depth_head_forward(const float* d_cost, const float* d_depth_samples, in
                            float* d_preds, void* stream) {
   if (!d_cost || !d_depth_samples) return fail(DFM_ERR_INVALID, "null argument");
   if (D < 1 || Ho < 1 || Wo < 1 || factor < 1) return fail(DFM_ERR_INVALID, "bad shape");
-  dim3 grid((Wo * factor + 127) / 128, Ho * factor);
+  dim3 grid((Wo * factor + 31) / 32, Ho * factor), block(32, dfm::DH_ZS);
   {
     ProfScope ps("depth_head", 0.0, (cudaStream_t)stream);
-    dfm::depth_head_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+    dfm::depth_head_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
         d_cost, d_depth_samples, D, Ho, Wo, factor, d_volume, d_softmax, d_preds);
   }
   LAUNCH_CHECK();
@@ -1151,3 +1155,4 @@ int dfm_depth_head_forward(const float* d_cost, const float* d_depth_samples, in
 }  // extern "C"
 
 #include "neck_api.inc"
+#include "frustum_api.inc"

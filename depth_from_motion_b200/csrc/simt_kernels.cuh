@@ -481,14 +481,21 @@ __device__ __forceinline__ float dh_plane(const float* __restrict__ c, long long
          w[3] * (w[0] * __ldg(c + zoff + o[2]) + w[1] * __ldg(c + zoff + o[3]));
 }
 
-__global__ void __launch_bounds__(128)
+// DH_ZS threads share one pixel: each owns a contiguous range of the depth axis (its share of
+// the low-res planes for the maximum, of the upsampled bins for the sums and the writes), so
+// the serial per-pixel loops are DH_ZS times shorter and the grid DH_ZS times larger.
+constexpr int DH_ZS = 4;
+__global__ void __launch_bounds__(32 * DH_ZS)
 depth_head_kernel(const float* __restrict__ cost, const float* __restrict__ samples, int D,
                   int Ho, int Wo, int f, float* __restrict__ vol, float* __restrict__ sm,
-                  float* __restrict__ preds) {
+                  float* __restrict__ preds, float2* __restrict__ norm = nullptr) {
+  __shared__ float red[3][DH_ZS][32];
   const int OW = Wo * f, OH = Ho * f, OD = D * f;
-  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tx = threadIdx.x, seg = threadIdx.y;
+  const int Xr = blockIdx.x * 32 + tx;
+  const bool live = Xr < OW;
+  const int X = live ? Xr : OW - 1;
   const int Y = blockIdx.y;
-  if (X >= OW) return;
   const float sx = OW > 1 ? (float)(Wo - 1) / (OW - 1) : 0.f;
   const float sy = OH > 1 ? (float)(Ho - 1) / (OH - 1) : 0.f;
   const float sz = OD > 1 ? (float)(D - 1) / (OD - 1) : 0.f;
@@ -504,12 +511,18 @@ depth_head_kernel(const float* __restrict__ cost, const float* __restrict__ samp
   // The upsampled column is piecewise linear in k between the low-res planes, so its maximum
   // is the maximum of the D (y,x)-interpolated low-res values: no online-softmax rescaling.
   float m = -INFINITY;
-  for (int z = 0; z < D; ++z) m = fmaxf(m, dh_plane(cost, z * plane, o, w));
-  // pass 1: sum of exponentials and the expectation
+  for (int z = seg * D / DH_ZS; z < (seg + 1) * D / DH_ZS; ++z)
+    m = fmaxf(m, dh_plane(cost, z * plane, o, w));
+  red[0][seg][tx] = m;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < DH_ZS; ++i) m = fmaxf(m, red[0][i][tx]);
+  // pass 1: sum of exponentials and the expectation over this thread's bins
+  const int k_lo = seg * OD / DH_ZS, k_hi = (seg + 1) * OD / DH_ZS;
   float ssum = 0.f, esum = 0.f;
   int zc = -1;
   float b0 = 0.f, b1 = 0.f;
-  for (int k = 0; k < OD; ++k) {
+  for (int k = k_lo; k < k_hi; ++k) {
     const float fz = sz * k;
     const int z0 = (int)fz;
     const int z1 = z0 + (z0 < D - 1 ? 1 : 0);
@@ -522,14 +535,29 @@ depth_head_kernel(const float* __restrict__ cost, const float* __restrict__ samp
     const float v = (1.f - lz1) * b0 + lz1 * b1;
     const float e = __expf(v - m);
     ssum += e;
-    esum = fmaf(e, __ldg(samples + k), esum);
+    if (preds) esum = fmaf(e, __ldg(samples + k), esum);
   }
-  if (preds) preds[opix] = esum / ssum;
+  red[1][seg][tx] = ssum;
+  red[2][seg][tx] = esum;
+  __syncthreads();
+  ssum = esum = 0.f;
+#pragma unroll
+  for (int i = 0; i < DH_ZS; ++i) {
+    ssum += red[1][i][tx];
+    esum += red[2][i][tx];
+  }
+  if (!live) return;
+  if (seg == 0) {
+    if (preds) preds[opix] = esum / ssum;
+    // (max, 1 / sum of exponentials) per pixel: lets a consumer evaluate any softmax value
+    // from the low-res logits without the full-resolution volume (frustum_kernels.cuh)
+    if (norm) norm[opix] = make_float2(m, 1.f / ssum);
+  }
   if (!sm && !vol) return;
   // pass 2: the two 4-D outputs
   const float inv = 1.f / ssum;
   zc = -1;
-  for (int k = 0; k < OD; ++k) {
+  for (int k = k_lo; k < k_hi; ++k) {
     const float fz = sz * k;
     const int z0 = (int)fz;
     const int z1 = z0 + (z0 < D - 1 ? 1 : 0);

@@ -10,6 +10,7 @@ of PyTorch ops:
     DfMNeck              mmdet3d/models/necks/dfm_neck.py:10-122
     OutdoorImVoxelNeck   mmdet3d/models/necks/imvoxel_neck.py:8-68
     multiview_lift       mmdet3d/models/detectors/multiview_dfm.py:119-209
+    FrustumToVoxel       mmdet3d/models/necks/feature_transformation.py:12-173
 
 The ``nn.Conv3d`` / ``nn.GroupNorm`` / ``nn.BatchNorm3d`` children below are
 parameter containers only (they give the exact reference ``state_dict`` layout so
@@ -254,6 +255,10 @@ class DfMBackbone(nn.Module):
         capi.check(L.dfm_backbone_forward(
             self._handle, _ptr(cur), _ptr(prev), ctypes.byref(geom), _ptr(cost),
             _ptr(stereo), _ptr(mono), _stream()), 'dfm_backbone_forward')
+        # the handle keeps a channels-last copy of stereo_feat until the next forward;
+        # FrustumToVoxel reads it instead of transposing `stereo` again
+        self._generation = getattr(self, '_generation', 0) + 1
+        stereo._dfm_channels_last = (self, self._generation)
         return cost, stereo, mono
 
     def debug_tensor(self, name, shape):
@@ -485,6 +490,172 @@ class DfMNeck(_NeckBase):
     def forward(self, x):
         assert x.shape[1] == self.in_channels[0] * self.num_frames
         return self._run(x, self.num_frames, self.conv_impl)
+
+
+class CostLogits:
+    """Marks a ``[B, 1, D, H, W]`` tensor of low-res cost logits (DfMBackbone's
+    first output) handed to ``FrustumToVoxel.forward`` in place of
+    ``stereo_feat_softmax``: the depth distribution is then evaluated from the
+    logits inside the sampling kernel and the x4-upsampled ``[B, 1, 4D, 4H, 4W]``
+    softmax volume (depth_head.py:196-204) is never materialised.  With
+    ``depth_samples`` (the tensor the detector injects into DepthHead,
+    detectors/dfm.py:90) the same pass also produces DepthHead's ``depth_preds``,
+    left in ``self.depth_preds`` after the call."""
+
+    def __init__(self, cost, depth_samples=None):
+        self.cost = cost
+        self.depth_samples = depth_samples
+        self.depth_preds = None
+
+
+@NECKS.register_module()
+class FrustumToVoxel(nn.Module):
+    """Drop-in for the reference ``FrustumToVoxel``
+    (necks/feature_transformation.py:12-173): same constructor arguments and
+    ``state_dict`` keys (``voxel_convs.<i>.0.conv.weight`` /
+    ``voxel_convs.<i>.0.gn.{weight,bias}``); ``depth_cfg`` and ``coordinates_3d``
+    are injected by the detector exactly like the reference
+    (detectors/dfm.py:85-100)."""
+
+    def __init__(self, num_3dconvs=1, cv_channels=32, out_channels=32,
+                 in_sem_channels=32, sem_atten_feat=True,
+                 stereo_atten_feat=False, cat_img_feature=True,
+                 norm_cfg=dict(type='GN', num_groups=32, requires_grad=True),
+                 conv_impl='auto'):
+        super().__init__()
+        self.GN = True
+        self.num_3dconvs = num_3dconvs
+        self.cv_channels = cv_channels
+        self.out_channels = out_channels
+        self.in_sem_channels = in_sem_channels
+        self.sem_atten_feat = sem_atten_feat
+        self.stereo_atten_feat = stereo_atten_feat
+        self.cat_img_feature = bool(cat_img_feature)
+        self.conv_impl = conv_impl
+        assert norm_cfg['type'] == 'GN' and norm_cfg['num_groups'] == 32
+        cin = cv_channels + (in_sem_channels if self.cat_img_feature else 0)
+        self.voxel_convs = nn.Sequential(*[
+            nn.Sequential(_ConvGN(cin if i == 0 else out_channels,
+                                  out_channels, 32))
+            for i in range(num_3dconvs)])
+        self._handle = None
+        self._key = None
+
+    def init_weights(self):
+        pass
+
+    def release(self):
+        if getattr(self, '_handle', None) is not None:
+            capi.lib().dfm_frustum_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _separable_centres(c3d):
+        """coordinates_3d is a meshgrid of three linspaces (detectors/dfm.py:
+        193-211); the kernel takes the three axes."""
+        c3d = c3d.detach().to('cpu', torch.float32)
+        xs = c3d[0, 0, :, 0].contiguous()
+        ys = c3d[0, :, 0, 1].contiguous()
+        zs = c3d[:, 0, 0, 2].contiguous()
+        ok = (torch.equal(c3d[..., 0], xs[None, None, :].expand(c3d.shape[:3]))
+              and torch.equal(c3d[..., 1], ys[None, :, None].expand(c3d.shape[:3]))
+              and torch.equal(c3d[..., 2], zs[:, None, None].expand(c3d.shape[:3])))
+        if not ok:
+            raise RuntimeError('coordinates_3d is not a separable (meshgrid) voxel grid')
+        return xs, ys, zs
+
+    def _ensure_handle(self, d, h, w, sh, sw, f):
+        c3d = self.coordinates_3d
+        key = (d, h, w, sh, sw, f, tuple(c3d.shape), c3d.data_ptr(),
+               c3d._version, float(self.depth_cfg['depth_min']),
+               float(self.depth_cfg['depth_max']))
+        if self._handle is not None and key == self._key:
+            return
+        self.release()
+        xs, ys, zs = self._separable_centres(c3d)
+        nz, ny, nx = c3d.shape[:3]
+        desc = capi.FrustumDesc(
+            self.num_3dconvs, self.cv_channels, self.out_channels,
+            self.in_sem_channels, int(self.sem_atten_feat),
+            int(self.stereo_atten_feat), int(self.cat_img_feature), d, h, w, sh,
+            sw, f, nx, ny, nz, float(self.depth_cfg['depth_min']),
+            float(self.depth_cfg['depth_max']), _IMPL[self.conv_impl])
+        hd = ctypes.c_void_p()
+        capi.check(capi.lib().dfm_frustum_create(
+            ctypes.byref(desc), _ptr(xs), _ptr(ys), _ptr(zs), ctypes.byref(hd)),
+            'dfm_frustum_create')
+        self._handle, self._key = hd, key
+        self._sync = _ParamSync()
+
+    def forward(self, stereo_feat, stereo_feat_softmax, img_metas,
+                cur_sem_feats=None):
+        """feature_transformation.py:68-173.  ``stereo_feat_softmax`` is the
+        DepthHead's ``[B, 1, fD, fH, fW]`` tensor like in the reference, or a
+        ``CostLogits`` wrapper (fused path)."""
+        _check_cuda(stereo_feat, 'stereo_feat')
+        b, c, d, h, w = stereo_feat.shape
+        assert b == len(img_metas)
+        logits = sm = samples = preds = None
+        if isinstance(stereo_feat_softmax, CostLogits):
+            logits = stereo_feat_softmax.cost.contiguous()
+            _check_cuda(logits, 'cost logits')
+            assert tuple(logits.shape) == (b, 1, d, h, w)
+            f = int(self.depth_cfg.get('downsample_factor', 4))
+            if stereo_feat_softmax.depth_samples is not None:
+                samples = stereo_feat_softmax.depth_samples.detach().to(
+                    logits.device, torch.float32).contiguous()
+                assert samples.numel() == f * d
+                preds = torch.empty((b, 1, f * h, f * w), device=logits.device)
+                stereo_feat_softmax.depth_preds = preds
+        elif stereo_feat_softmax is not None:
+            sm = stereo_feat_softmax.contiguous()
+            _check_cuda(sm, 'stereo_feat_softmax')
+            f = sm.shape[2] // d
+            assert tuple(sm.shape) == (b, 1, f * d, f * h, f * w)
+        else:
+            f = 1
+        sem = None
+        sh = sw = 1
+        if self.cat_img_feature:
+            _check_cuda(cur_sem_feats, 'cur_sem_feats')
+            sem = cur_sem_feats.contiguous()
+            sh, sw = sem.shape[-2:]
+        self._ensure_handle(d, h, w, sh, sw, f)
+        L = capi.lib()
+        self._sync.sync(self, lambda k, p, m: capi.check(
+            L.dfm_frustum_set_param(self._handle, k, p, m),
+            f'dfm_frustum_set_param({k.decode()})'))
+        nz, ny, nx = self.coordinates_3d.shape[:3]
+        pad = img_metas[0]['pad_shape']
+        x = stereo_feat.contiguous()
+        out = torch.empty((b, self.out_channels, nz // 4, ny, nx),
+                          device=x.device)
+        # a stereo_feat that came straight out of our DfMBackbone has a live
+        # channels-last twin inside the backbone handle: no transpose needed
+        tag = getattr(stereo_feat, '_dfm_channels_last', None)
+        twin = None
+        if (tag is not None and b == 1 and tag[0]._handle is not None
+                and tag[0]._generation == tag[1]):
+            twin = L.dfm_backbone_stereo_feat_device(tag[0]._handle)
+        for i in range(b):
+            P = (ctypes.c_double * 16)(*np.asarray(
+                img_metas[i]['cam2img'], np.float64).reshape(-1)[:16].tolist())
+            capi.check(L.dfm_frustum_forward(
+                self._handle,
+                ctypes.c_void_p(twin) if twin else _ptr(x[i]),
+                capi.DFM_LAYOUT_DHWC if twin else capi.DFM_LAYOUT_NCDHW,
+                _ptr(sm[i]) if sm is not None else None,
+                _ptr(logits[i]) if logits is not None else None,
+                _ptr(samples), _ptr(preds[i]) if preds is not None else None,
+                _ptr(sem[i]) if sem is not None else None, P, int(pad[0]),
+                int(pad[1]), _ptr(out[i]), _stream()), 'dfm_frustum_forward')
+        return out
 
 
 def aligned_voxel_centers(n_voxels, voxel_range):

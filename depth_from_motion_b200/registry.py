@@ -144,4 +144,10 @@ def register_into_mmdet():
                                    module=modules.OutdoorImVoxelNeck)
     except Exception:
         pass
+    try:  # FrustumToVoxel registers into mmdet's NECKS (feature_transformation.py:9-12)
+        from mmdet.models.builder import NECKS as MM_NECKS
+        MM_NECKS.register_module(name='FrustumToVoxel', force=True,
+                                 module=modules.FrustumToVoxel)
+    except Exception:
+        pass
     return True

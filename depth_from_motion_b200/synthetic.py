@@ -159,3 +159,62 @@ def make_neck_params(rng, template_state_dict):
         else:
             raise KeyError(k)
     return out
+
+
+# KITTI model-level voxel grid (configs/dfm/dfm_r34_1x8_kitti-3d-3class.py:1,10-11)
+KITTI_POINT_CLOUD_RANGE = [2, -30.4, -3, 59.6, 30.4, 1]
+KITTI_VOXEL_SIZE = [0.2, 0.2, 0.2]
+
+
+def frustum_voxel_centres(point_cloud_range, n_voxels):
+    """The three axes of ``DfM.prepare_coordinates_3d`` (detectors/dfm.py:193-211):
+    linspace of voxel centres, (nx, ny, nz) cells."""
+    pcr = point_cloud_range
+    axes = []
+    for a, n in enumerate(n_voxels):
+        vs = (pcr[3 + a] - pcr[a]) / n
+        axes.append(torch.linspace(pcr[a] + vs / 2., pcr[3 + a] - vs / 2., n,
+                                   dtype=torch.float32))
+    return axes
+
+
+def frustum_coordinates(point_cloud_range, n_voxels):
+    """coordinates_3d [nz, ny, nx, 3] holding (x, y, z), detectors/dfm.py:208-211."""
+    xs, ys, zs = frustum_voxel_centres(point_cloud_range, n_voxels)
+    zz, yy, xx = torch.meshgrid(zs, ys, xs, indexing='ij')
+    return torch.stack([xx, yy, zz], dim=-1).float()
+
+
+def make_frustum_case(seed, h, w, num_planes, n_voxels, num_3dconvs=1,
+                      cat_img_feature=True):
+    """Synthetic FrustumToVoxel inputs: ``h x w`` is the padded network input,
+    the plane-sweep volume is [32, num_planes, h/4, w/4].  cam2img is KITTI P2
+    rescaled to the h x w image so that part of the grid projects outside."""
+    rng = np.random.RandomState(seed)
+    ho, wo = h // 4, w // 4
+    stereo = torch.cat([smooth_field(rng, 32, ho, wo, cell=4)
+                        for _ in range(num_planes)], 0)
+    stereo = stereo.permute(1, 0, 2, 3)[None].contiguous()  # [1,32,D,ho,wo]
+    cost = torch.cat([smooth_field(rng, 1, ho, wo, cell=4)
+                      for _ in range(num_planes)], 1)[:, None] * 2.0
+    sem = smooth_field(rng, 32, ho, wo, cell=4)
+    s = w / 1248.0
+    P = KITTI_P2.copy()
+    P[:2] *= s
+    P[1, 2] = 0.45 * h
+    params = {}
+    cin = 64 if cat_img_feature else 32
+    for i in range(num_3dconvs):
+        ci = cin if i == 0 else 32
+        params[f'voxel_convs.{i}.0.conv.weight'] = torch.from_numpy(
+            _kaiming(rng, (32, ci, 3, 3, 3), ci * 27))
+        params[f'voxel_convs.{i}.0.gn.weight'] = torch.from_numpy(
+            (0.5 + rng.random_sample(32)).astype(np.float32))
+        params[f'voxel_convs.{i}.0.gn.bias'] = torch.from_numpy(
+            (0.2 * rng.standard_normal(32)).astype(np.float32))
+    metas = [dict(cam2img=P.astype(np.float32).tolist(), pad_shape=(h, w, 3))]
+    return dict(stereo=stereo, cost=cost.contiguous(), sem=sem, metas=metas,
+                params=params,
+                coordinates_3d=frustum_coordinates(KITTI_POINT_CLOUD_RANGE,
+                                                   n_voxels),
+                depth_cfg=depth_cfg_for(num_planes))

@@ -105,6 +105,9 @@ int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const floa
 /* Device pointer of the gated logits kept inside the handle after a forward
  * (lets a host-buffer caller chain dfm_depth_head_forward without a round trip). */
 const float* dfm_backbone_cost_device(const dfm_backbone_t* bb);
+/* Channels-last [D][Ho][Wo][cv] device copy of stereo_feat kept by the last forward (valid until
+ * the next one): hand it to dfm_frustum_forward with DFM_LAYOUT_DHWC to skip a transpose. */
+const float* dfm_backbone_stereo_feat_device(const dfm_backbone_t* bb);
 /* Test hook: copies a named intermediate (channels-last [D][H][W][C]) to d_out.
  * Names: "raw0", "raw1", "c1".."c6", "p0", "logit", with suffix "_mono" for the mono tower
  * (which may hold the z-shortened volume). */
@@ -202,6 +205,55 @@ int dfm_neck_set_param(dfm_neck_t* neck, const char* name, const float* h_data,
 int dfm_neck_missing_params(const dfm_neck_t* neck);
 /* d_x [1, Cin_total, Nx, Ny, Nz] -> d_bev [1, out_channels, Ny, Nx]. */
 int dfm_neck_forward(dfm_neck_t* neck, const float* d_x, float* d_bev, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * FrustumToVoxel (mmdet3d/models/necks/feature_transformation.py:12-173), the stage that
+ * consumes the hot path's outputs: the pseudo-lidar voxel grid
+ * (detectors/dfm.py:174-211) is projected with cam2img[:3] (:175-187), stereo_feat / the depth
+ * distribution / cur_sem_feats are grid-sampled there (:127-158), then voxel_convs
+ * (Conv3d k3 + GroupNorm(32) + ReLU, :49-62) and AvgPool3d((4,1,1)) (:63,166).
+ * ---------------------------------------------------------------------------------- */
+#define DFM_LAYOUT_NCDHW 0 /* [C][D][H][W], the reference tensor layout   */
+#define DFM_LAYOUT_DHWC 1  /* channels-last [D][H][W][C]                   */
+typedef struct dfm_frustum dfm_frustum_t;
+typedef struct dfm_frustum_desc {
+  int num_3dconvs;       /* feature_transformation.py:17 (1..4)            */
+  int cv_channels;       /* 32                                              */
+  int out_channels;      /* 32                                              */
+  int in_sem_channels;   /* 32                                              */
+  int sem_atten_feat, stereo_atten_feat, cat_img_feature; /* :20-22        */
+  int num_planes;        /* D of stereo_feat [1, cv, D, feat_h, feat_w]     */
+  int feat_h, feat_w;
+  int sem_h, sem_w;      /* cur_sem_feats [1, sem, sem_h, sem_w]            */
+  int depth_factor;      /* softmax volume is [f*D][f*feat_h][f*feat_w]     */
+  int nx, ny, nz;        /* voxel grid; coordinates_3d is [nz][ny][nx][3]   */
+  float depth_min, depth_max; /* depth_cfg                                  */
+  int conv_impl;         /* DFM_CONV_*                                      */
+} dfm_frustum_desc_t;
+/* h_xs [nx], h_ys [ny], h_zs [nz]: the separable pseudo-lidar voxel centres of
+ * coordinates_3d (x = [0,0,:,0], y = [0,:,0,1], z = [:,0,0,2]). */
+int dfm_frustum_create(const dfm_frustum_desc_t* desc, const float* h_xs, const float* h_ys,
+                       const float* h_zs, dfm_frustum_t** out);
+int dfm_frustum_destroy(dfm_frustum_t* f);
+/* Reference state_dict keys: "voxel_convs.<i>.0.conv.weight", "voxel_convs.<i>.0.gn.weight",
+ * "voxel_convs.<i>.0.gn.bias". */
+int dfm_frustum_set_param(dfm_frustum_t* f, const char* name, const float* h_data,
+                          long long numel);
+int dfm_frustum_missing_params(const dfm_frustum_t* f);
+/* One sample.  d_stereo_feat: device, layout as flagged.  The depth distribution is either the
+ * materialised DepthHead output d_softmax [f*D][f*H][f*W] (the reference's argument) or, with
+ * d_softmax == NULL, rebuilt on the fly from the low-res logits d_cost_logits [D][H][W]
+ * (DfMBackbone's first output) so the 0.5-0.9 GB volume never exists; that pass is
+ * DepthHead.forward's reduction, so with d_depth_samples [f*D] and d_depth_preds [f*H][f*W]
+ * (both optional) it also returns the DepthHead's depth_preds and no separate
+ * dfm_depth_head_forward call is needed.  d_sem: [sem][sem_h][sem_w] (NULL when
+ * !cat_img_feature).  cam2img: 16 doubles, row-major img_meta['cam2img'].
+ * pad_h/pad_w: img_metas[0]['pad_shape'].  d_out: [out_channels][nz/4][ny][nx]. */
+int dfm_frustum_forward(dfm_frustum_t* f, const float* d_stereo_feat, int stereo_layout,
+                        const float* d_softmax, const float* d_cost_logits,
+                        const float* d_depth_samples, float* d_depth_preds, const float* d_sem,
+                        const double* cam2img, int pad_h, int pad_w, float* d_out,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,9 @@ follows (paths relative to the reference checkout, commit e2321189):
                             mmdet3d/models/necks/imvoxel_neck.py:8-117
     a9  points_cam2img / points_img2cam
                             mmdet3d/core/bbox/structures/utils.py:176-248
+    f1  FrustumToVoxel.forward
+                            mmdet3d/models/necks/feature_transformation.py:68-187
+                            mmdet3d/models/detectors/dfm.py:174-211 (voxel grid)
 
 Third-party arithmetic: every number on this path is produced by PyTorch ATen
 ops in the reference (README pins torch 1.9 + mmcv-full 1.6.0, the latter used
@@ -39,7 +42,7 @@ The reference's own tests hold golden vectors only for the geometry helpers
 (tests/test_utils/test_utils.py:186-193, tests/test_utils/test_box3d.py:1653-1680)
 and ``point_sample`` (tests/test_models/test_fusion/test_point_fusion.py:13-58);
 those are reproduced in tests/test_oracle_golden.py.  For build_dfm_cost /
-DfMBackbone / DepthHead / DfMNeck the reference has NO tests, so this
+DfMBackbone / DepthHead / DfMNeck / FrustumToVoxel the reference has NO tests, so this
 restatement is pinned against outputs of the reference's own source files
 executed verbatim in the build container (oracle/ref_loader.py), committed as
 fixtures under tests/golden/ by tests/golden/make_golden.py.
@@ -412,6 +415,89 @@ def dfm_neck_forward(p, x, mono_channels):
 # helpers shared by tests / bench (deterministic synthetic inputs, NumPy legacy
 # MT19937 so both sides of a fixture regenerate identical tensors)
 # ----------------------------------------------------------------------------
+# ----------------------------------------------------------------------------
+# f1  FrustumToVoxel
+# ----------------------------------------------------------------------------
+def frustum_coordinates_3d(voxel_cfg):
+    """DfM.prepare_coordinates_3d (detectors/dfm.py:174-211, sample_rate (1,1,1)):
+    pseudo-lidar voxel centres [Nz, Ny, Nx, 3] holding (x, y, z)."""
+    pcr = voxel_cfg['point_cloud_range']
+    vs = voxel_cfg['voxel_size']
+    grid = (np.array(pcr[3:6], dtype=np.float32) -
+            np.array(pcr[0:3], dtype=np.float32)) / np.array(vs)
+    gx, gy, gz = np.round(grid).astype(np.int64).tolist()
+    zs = torch.linspace(pcr[2] + vs[2] / 2., pcr[5] - vs[2] / 2., gz,
+                        dtype=torch.float32)
+    ys = torch.linspace(pcr[1] + vs[1] / 2., pcr[4] - vs[1] / 2., gy,
+                        dtype=torch.float32)
+    xs = torch.linspace(pcr[0] + vs[0] / 2., pcr[3] - vs[0] / 2., gx,
+                        dtype=torch.float32)
+    zs, ys, xs = torch.meshgrid(zs, ys, xs, indexing='ij')
+    return torch.stack([xs, ys, zs], dim=-1).float()
+
+
+def frustum_grid(coordinates_3d, cam2img, pad_shape, depth_cfg):
+    """feature_transformation.py:84-124 for one sample: pseudo-lidar -> rect
+    camera (x,y,z) -> (-y,-z,x) (:175-177), pixel = P[:3] [X,Y,Z,1] / w
+    (:180-187), third coordinate = rect depth; normalisation by the padded image
+    size and the depth range; the two validity masks."""
+    c3d = coordinates_3d.reshape(-1, 3)
+    rect = torch.stack([-c3d[:, 1], -c3d[:, 2], c3d[:, 0]], dim=-1)
+    P = torch.as_tensor(cam2img, dtype=torch.float32)[:3].float()
+    hom = torch.cat([rect, torch.ones((rect.shape[0], 1))], dim=1)
+    pts = torch.mm(hom, P.t())
+    pts[:, 0] /= pts[:, 2]
+    pts[:, 1] /= pts[:, 2]
+    coord = torch.cat([pts[:, 0:2], rect[:, 2:]], dim=-1)
+    coord = coord.view(*coordinates_3d.shape[:3], 3)
+    valid2d = ((coord[..., 0] >= 0) & (coord[..., 0] <= pad_shape[1]) &
+               (coord[..., 1] >= 0) & (coord[..., 1] <= pad_shape[0]))
+    lo = torch.as_tensor([0, 0, depth_cfg['depth_min']])
+    span = torch.as_tensor([pad_shape[1] - 1, pad_shape[0] - 1,
+                            depth_cfg['depth_max'] - depth_cfg['depth_min']])
+    norm = (coord - lo) / span
+    norm = norm * 2. - 1.
+    valid = valid2d & (norm[..., 2] >= -1.) & (norm[..., 2] <= 1.)
+    return norm, valid2d, valid.float()
+
+
+def frustum_to_voxel_forward(p, stereo_feat, stereo_feat_softmax, img_metas,
+                             cur_sem_feats, coordinates_3d, depth_cfg,
+                             sem_atten_feat=True, stereo_atten_feat=False,
+                             cat_img_feature=True, num_3dconvs=1):
+    """FrustumToVoxel.forward, feature_transformation.py:68-173 (batch loop
+    included; like the reference, pad_shape is read from img_metas[0])."""
+    norms, v2ds, vs = [], [], []
+    for m in img_metas:
+        n, v2, v = frustum_grid(coordinates_3d, m['cam2img'],
+                                img_metas[0]['pad_shape'], depth_cfg)
+        norms.append(n)
+        v2ds.append(v2)
+        vs.append(v)
+    norm = torch.stack(norms)
+    valid2d = torch.stack(v2ds)
+    valid = torch.stack(vs)
+    voxel = F.grid_sample(stereo_feat, norm, align_corners=True)
+    voxel = voxel * valid[:, None]
+    pred_disp = None
+    if stereo_atten_feat or (sem_atten_feat and cat_img_feature):
+        pred_disp = F.grid_sample(stereo_feat_softmax, norm, align_corners=True)
+        pred_disp = pred_disp * valid[:, None]
+        if stereo_atten_feat:
+            voxel = voxel * pred_disp
+    if cat_img_feature:
+        norm2d = norm.clone()
+        norm2d[..., 2] = 0
+        v2 = F.grid_sample(cur_sem_feats.unsqueeze(2), norm2d, align_corners=True)
+        v2 = v2 * valid2d.float()[:, None]
+        if sem_atten_feat:
+            v2 = v2 * pred_disp
+        voxel = torch.cat([voxel, v2], dim=1)
+    for i in range(num_3dconvs):
+        voxel = _conv_module(voxel, p, f'voxel_convs.{i}.0')
+    return F.avg_pool3d(voxel, (4, 1, 1), stride=(4, 1, 1))
+
+
 def tf32_round(x):
     """Round-to-nearest-even to 10 mantissa bits (precision study only)."""
     xi = x.contiguous().view(torch.int32)

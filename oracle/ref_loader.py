@@ -19,6 +19,7 @@ straight from the read-only reference tree:
     mmdet3d/models/dense_heads/depth_head.py   (DepthHead)
     mmdet3d/models/necks/imvoxel_neck.py       (OutdoorImVoxelNeck, ResModule)
     mmdet3d/models/necks/dfm_neck.py           (DfMNeck)
+    mmdet3d/models/necks/feature_transformation.py (FrustumToVoxel)
 
 No reference source is copied into this repository.
 """
@@ -211,6 +212,8 @@ def load_reference():
         sys.modules['mmdet3d.models.necks'].imvoxel_neck = iv
         dn = _exec('mmdet3d.models.necks.dfm_neck',
                    'mmdet3d/models/necks/dfm_neck.py')
+        ft = _exec('mmdet3d.models.necks.feature_transformation',
+                   'mmdet3d/models/necks/feature_transformation.py')
 
         ns = types.SimpleNamespace(
             points_cam2img=su.points_cam2img,
@@ -223,6 +226,7 @@ def load_reference():
             OutdoorImVoxelNeck=iv.OutdoorImVoxelNeck,
             ResModule=iv.ResModule,
             DfMNeck=dn.DfMNeck,
+            FrustumToVoxel=ft.FrustumToVoxel,
             ConvModule=_ConvModule,
         )
         _LOADED = ns

@@ -7,7 +7,7 @@ container, where /root/reference is mounted:
 Inputs are regenerated from fixed NumPy seeds by depth_from_motion_b200.synthetic
 (and stored too, so a fixture is self-contained); outputs are what the
 reference's own DfMBackbone / DepthHead / DfMNeck / OutdoorImVoxelNeck /
-point_sample code returns on CPU in fp32.
+FrustumToVoxel / point_sample code returns on CPU in fp32.
 """
 import copy
 import os
@@ -83,12 +83,51 @@ def neck_case(ns):
         print(name, tuple(y.shape), float(y.abs().max()))
 
 
+FRUSTUM_CASE = dict(seed=31, h=32, w=64, num_planes=8, n_voxels=(24, 20, 8))
+
+
+def frustum_case(ns):
+    """Reference DepthHead + FrustumToVoxel run verbatim on the synthetic case
+    (the reference calls .cuda() on its voxel grid: made a no-op on this CPU box)."""
+    c = syn.make_frustum_case(**FRUSTUM_CASE)
+    cfg = c['depth_cfg']
+    head = ns.DepthHead(
+        depth_cfg=dict(mode='UD', num_bins=cfg['num_bins'], min_depth=2,
+                       max_depth=59.6), with_convs=False, num_views=1,
+        depth_loss=dict(type='balanced_focal', loss_weight=1.0, fg_weight=5,
+                        bg_weight=1, alpha=1, gamma=2)).eval()
+    head.depth_samples = O.depth_samples(cfg)
+    head.downsample_factor = 4
+    m = ns.FrustumToVoxel().eval()
+    m.load_state_dict(c['params'], strict=True)
+    m.coordinates_3d = c['coordinates_3d']
+    m.depth_cfg = cfg
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        with torch.no_grad():
+            _, sm, _ = head(c['cost'])
+            out = m(c['stereo'], sm, copy.deepcopy(c['metas']), c['sem'])
+    finally:
+        torch.Tensor.cuda = saved
+    np.savez_compressed(
+        os.path.join(HERE, 'frustum.npz'), stereo=c['stereo'].numpy(),
+        cost=c['cost'].numpy(), sem=c['sem'].numpy(), softmax=sm.numpy(),
+        out=out.numpy())
+    print('frustum', tuple(out.shape), float(out.abs().max()),
+          float((out != 0).float().mean()))
+
+
 def main():
     ns = load_reference()
     torch.manual_seed(0)
+    if 'frustum' in sys.argv[1:]:
+        frustum_case(ns)
+        return
     for name, spec in KITTI_CASES.items():
         kitti_case(ns, name, spec)
     neck_case(ns)
+    frustum_case(ns)
 
 
 if __name__ == '__main__':

@@ -390,3 +390,121 @@ def test_multiview_lift_vs_oracle(concat, flip):
     print('mismatching voxels', bad)
     assert bad <= 0.005
     assert float(ref.abs().sum()) > 0
+
+
+# ---------------------------------------------------------------------------
+# FrustumToVoxel
+# ---------------------------------------------------------------------------
+def _frustum_module(c, impl='auto', **kw):
+    m = modules.FrustumToVoxel(conv_impl=impl, **kw)
+    m.load_state_dict(c['params'], strict=True)
+    m = m.cuda().eval()
+    m.coordinates_3d = c['coordinates_3d']
+    m.depth_cfg = c['depth_cfg']
+    return m
+
+
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+@pytest.mark.parametrize('fused', [False, True])
+def test_frustum_matches_reference_fixture(impl, fused):
+    """CUDA FrustumToVoxel vs the verbatim reference run (tests/golden/frustum.npz): with the
+    reference's materialised softmax volume, and with the volume rebuilt from the logits."""
+    from tests.util import load_frustum_case
+    c, gold = load_frustum_case()
+    m = _frustum_module(c, impl)
+    dist = (modules.CostLogits(c['cost'].cuda()) if fused
+            else torch.from_numpy(gold['softmax']).cuda())
+    out = m(c['stereo'].cuda(), dist, c['metas'], c['sem'].cuda())
+    ref = torch.from_numpy(gold['out'])
+    assert out.shape == ref.shape
+    e = rel_err(out, ref)
+    print('frustum fixture', impl, fused, e)
+    assert e < TOL
+
+
+@pytest.mark.parametrize('variant', ['default', 'stereo_atten', 'no_img', 'two_convs'])
+def test_frustum_variants_vs_oracle(variant):
+    """Constructor switches (feature_transformation.py:17-22) and a voxel grid that leaves
+    the depth range and the image on all sides, against the oracle."""
+    kw = dict(default={}, stereo_atten=dict(stereo_atten_feat=True, sem_atten_feat=False),
+              no_img=dict(cat_img_feature=False, stereo_atten_feat=True),
+              two_convs=dict(num_3dconvs=2))[variant]
+    c = syn.make_frustum_case(41, 64, 160, 12, (40, 36, 12),
+                              num_3dconvs=kw.get('num_3dconvs', 1),
+                              cat_img_feature=kw.get('cat_img_feature', True))
+    # grid from 0.5 m (closer than depth_min) to 70 m (beyond depth_max)
+    c['coordinates_3d'] = syn.frustum_coordinates([0.5, -30.4, -3, 70.0, 30.4, 1],
+                                                  (40, 36, 12))
+    cfg = c['depth_cfg']
+    _, sm, _ = O.depth_head_forward(c['cost'], O.depth_samples(cfg), 4)
+    ref = O.frustum_to_voxel_forward(
+        c['params'], c['stereo'], sm, c['metas'], c['sem'], c['coordinates_3d'], cfg,
+        sem_atten_feat=kw.get('sem_atten_feat', True),
+        stereo_atten_feat=kw.get('stereo_atten_feat', False),
+        cat_img_feature=kw.get('cat_img_feature', True),
+        num_3dconvs=kw.get('num_3dconvs', 1))
+    m = _frustum_module(c, **kw)
+    sem = c['sem'].cuda() if kw.get('cat_img_feature', True) else None
+    a = m(c['stereo'].cuda(), sm.cuda(), c['metas'], sem)
+    b = m(c['stereo'].cuda(), modules.CostLogits(c['cost'].cuda()), c['metas'], sem)
+    ea, eb = rel_err(a, ref), rel_err(b, ref)
+    print('frustum', variant, ea, eb, float((ref != 0).float().mean()))
+    assert ea < TOL and eb < TOL
+
+
+def test_frustum_full_size_properties():
+    """KITTI shape (D=112 planes, 96x312 lattice, 20x304x288 voxels): the fused path
+    agrees with the materialised-softmax path, voxels that project outside the image carry
+    only the conv's response to zeros, and the output is finite."""
+    c = syn.make_frustum_case(51, 384, 1248, 112, (288, 304, 20))
+    m = _frustum_module(c)
+    stereo, cost, sem = c['stereo'].cuda(), c['cost'].cuda(), c['sem'].cuda()
+    head = modules.DepthHead(depth_cfg=dict(mode='UD', num_bins=448, min_depth=2,
+                                            max_depth=59.6), with_convs=False)
+    head.depth_samples = O.depth_samples(c['depth_cfg'])
+    _, sm, _ = head(cost)
+    a = m(stereo, sm, c['metas'], sem)
+    del sm
+    b = m(stereo, modules.CostLogits(cost), c['metas'], sem)
+    assert a.shape == (1, 32, 5, 304, 288)
+    assert torch.isfinite(a).all()
+    e = rel_err(b, a)
+    print('frustum full size fused vs materialised', e)
+    assert e < 1e-4
+    # zero input region: y = +-30 m at x = 2.1 m projects far outside the image on every
+    # height, and so do its 3x3x3 neighbours -> out = relu(gn(0)) there
+    sc = m.voxel_convs[0][0].gn
+    corner = a[0, :, :, 0, 0].cpu()
+    # raw conv output 0 -> (0 - mean) * rstd * gamma + beta: identical on all pooled planes
+    assert float((corner - corner[:, :1]).abs().max()) < 1e-5
+    assert sc.weight.numel() == 32
+
+
+def test_frustum_fused_depth_preds_and_backbone_twin():
+    """backbone -> (DepthHead + FrustumToVoxel in one call): depth_preds of the fused pass
+    equal the DepthHead's, and reading the backbone's channels-last twin of stereo_feat gives
+    the same voxels as transposing the NCDHW tensor."""
+    from tests.util import load_frustum_case
+    cur, prev, metas, params, cfg, _ = load_kitti_case('kitti_plain')
+    bb = _backbone(params, cfg, 'auto')
+    cost, stereo, _ = bb(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
+    assert getattr(stereo, '_dfm_channels_last', None) is not None
+    c, _ = load_frustum_case()
+    m = _frustum_module(c)
+    sem = c['sem'].cuda()
+    samples = O.depth_samples(cfg)
+    lg = modules.CostLogits(cost, depth_samples=samples)
+    a = m(stereo, lg, c['metas'], sem)                      # twin path
+    b = m(stereo.clone(), modules.CostLogits(cost), c['metas'], sem)  # transpose path
+    assert torch.equal(a, b)
+    _, sm, preds = O.depth_head_forward(cost.cpu(), samples, 4)
+    assert rel_err(lg.depth_preds, preds) < 1e-5
+    ref = O.frustum_to_voxel_forward(c['params'], stereo.cpu(), sm, c['metas'], c['sem'],
+                                     c['coordinates_3d'], cfg)
+    e = rel_err(a, ref)
+    print('backbone -> frustum', e)
+    assert e < TOL
+    # a second backbone forward invalidates the twin: the module must fall back to the tensor
+    bb(prev.cuda(), cur.cuda(), copy.deepcopy(metas))
+    a2 = m(stereo, modules.CostLogits(cost), c['metas'], sem)
+    assert torch.equal(a2, b)

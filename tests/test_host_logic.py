@@ -65,6 +65,10 @@ def test_state_dict_contract():
     assert 'mono_layers.0.conv0.conv.weight' in n.state_dict()
     assert 'stereo_layers.5.bn.running_var' in n.state_dict()
     assert 'model.1.conv.weight' in modules.OutdoorImVoxelNeck(64, 256).state_dict()
+    f = modules.FrustumToVoxel().state_dict()
+    assert {k: tuple(v.shape) for k, v in f.items()} == {
+        'voxel_convs.0.0.conv.weight': (32, 64, 3, 3, 3),
+        'voxel_convs.0.0.gn.weight': (32,), 'voxel_convs.0.0.gn.bias': (32,)}
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not mounted')
@@ -77,7 +81,10 @@ def test_state_dict_matches_reference_modules():
     assert list(a) == list(b)
     assert all(a[k].shape == b[k].shape for k in a)
     for ours, ref in ((modules.DfMNeck(64, 256, num_frames=2), ns.DfMNeck(64, 256, num_frames=2)),
-                      (modules.OutdoorImVoxelNeck(64, 256), ns.OutdoorImVoxelNeck(64, 256))):
+                      (modules.OutdoorImVoxelNeck(64, 256), ns.OutdoorImVoxelNeck(64, 256)),
+                      (modules.FrustumToVoxel(), ns.FrustumToVoxel()),
+                      (modules.FrustumToVoxel(num_3dconvs=2, cat_img_feature=False),
+                       ns.FrustumToVoxel(num_3dconvs=2, cat_img_feature=False))):
         a, b = ours.state_dict(), ref.state_dict()
         assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a)
 
@@ -98,6 +105,12 @@ def test_reference_configs_parse_and_build_hot_path(cfg_name):
         assert m.num_planes == 72
         h = pkg.build_head(dict(model['depth_head']))
         assert isinstance(h, modules.DepthHead) and not h.with_convs
+        ft = pkg.build_neck(dict(model['feature_transformation']))
+        assert isinstance(ft, modules.FrustumToVoxel) and ft.sem_atten_feat
+        vc = model['voxel_cfg']
+        nvox = [round((vc['point_cloud_range'][3 + a] - vc['point_cloud_range'][a]) /
+                      vc['voxel_size'][a]) for a in range(3)]
+        assert nvox == [288, 304, 20]
     else:
         n = pkg.build_neck(dict(model['neck_3d']))
         assert isinstance(n, (modules.DfMNeck, modules.OutdoorImVoxelNeck))

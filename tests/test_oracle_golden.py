@@ -120,3 +120,24 @@ def test_depth_tables():
     assert d.shape == (72,) and abs(float(d[0]) - (2 + 0.5 * 4 * 0.2)) < 1e-5
     s = O.depth_samples(cfg)
     assert s.shape == (288,) and abs(float(s[-1]) - (59.6 - 0.1)) < 1e-4
+
+
+def test_frustum_to_voxel_matches_reference_fixture():
+    """oracle restatement (DepthHead -> FrustumToVoxel)
+    against the verbatim reference run stored in tests/golden/frustum.npz."""
+    from tests.util import load_frustum_case
+    c, gold = load_frustum_case()
+    cfg = c['depth_cfg']
+    _, sm, _ = O.depth_head_forward(c['cost'], O.depth_samples(cfg), 4)
+    assert torch.equal(sm, torch.from_numpy(gold['softmax']))
+    out = O.frustum_to_voxel_forward(c['params'], c['stereo'], sm, c['metas'], c['sem'],
+                                     c['coordinates_3d'], cfg)
+    ref = torch.from_numpy(gold['out'])
+    assert out.shape == ref.shape == (1, 32, 2, 20, 24)
+    assert float((out - ref).abs().max()) <= 1e-6
+    # the grid of the shipped config (detectors/dfm.py:174-211)
+    full = O.frustum_coordinates_3d(dict(point_cloud_range=syn.KITTI_POINT_CLOUD_RANGE,
+                                         voxel_size=syn.KITTI_VOXEL_SIZE))
+    assert tuple(full.shape) == (20, 304, 288, 3)
+    assert torch.equal(full, syn.frustum_coordinates(syn.KITTI_POINT_CLOUD_RANGE,
+                                                     (288, 304, 20)))

@@ -31,3 +31,15 @@ def rel_err(a, b):
     a = torch.as_tensor(a, dtype=torch.float64).cpu()
     b = torch.as_tensor(b, dtype=torch.float64).cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# must match tests/golden/make_golden.py
+FRUSTUM_CASE = dict(seed=31, h=32, w=64, num_planes=8, n_voxels=(24, 20, 8))
+
+
+def load_frustum_case():
+    c = syn.make_frustum_case(**FRUSTUM_CASE)
+    gold = dict(np.load(os.path.join(GOLDEN, 'frustum.npz')))
+    for k in ('stereo', 'cost', 'sem'):
+        c[k] = torch.from_numpy(gold[k])
+    return c, gold
