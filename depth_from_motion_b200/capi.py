@@ -11,7 +11,7 @@ from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_longlong,
                     c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdfm_b200.so')
+LIB_PATH = os.environ.get('DFM_B200_LIB') or os.path.join(_HERE, 'libdfm_b200.so')
 
 DFM_OK = 0
 DFM_CONV_AUTO, DFM_CONV_SIMT, DFM_CONV_TC = 0, 1, 2

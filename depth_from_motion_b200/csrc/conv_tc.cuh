@@ -69,7 +69,8 @@ enum { TC_S1 = 0, TC_S2 = 1, TC_T = 2 };
 constexpr int TC_BX = 8, TC_BY = 16;  // M tile: 8 (x) * 16 (y) = 128 accumulator rows
 constexpr int TC_LOAD_THREADS = 256;
 constexpr int TC_THREADS = 128 + TC_LOAD_THREADS + 32;  // epilogue | loaders | MMA issuer
-constexpr int TC_MAXOPS = 9, TC_MAXBLK = 32;
+constexpr int TC_MAXOPS = 9, TC_MAXBLK = 48;
+constexpr int TC_ZERO_TAP = 255;  // TcBlk::tap of an all-zero padding block
 
 template <int MODE>
 struct TcMode;
@@ -123,9 +124,10 @@ struct TcOp {
   uint32_t b_off;   // byte offset of this op's weight image (hi half) in smem
   uint32_t b_lbo;   // bytes between 8-channel chunks of the weight image
   uint16_t blk0, blk1;
-  // static decomposition into MMAs when every output plane is live and nothing is fresh:
-  // run = nblk | first block << 4 | (dz+1) of first plane << 8 | colblk << 10 |
-  //       blocks per plane << 12 | planes << 16
+  // static decomposition into MMAs when every output plane is live:
+  // run = nblk | first block << 4 | lin0 << 10, lin = (dz+1) * SLOT_BLOCKS + colblk of the
+  // first block; a run is a range of consecutive lin values (split at issue time only where
+  // the accumulator slot ring wraps between two planes)
   uint32_t nruns;
   uint32_t runs[3];
 };
@@ -158,8 +160,7 @@ inline void tc_build_program(int ptype, int Cin, int ncta, uint32_t* w_cursor, T
     for (TcBlk b : blks) pr->blks[nb++] = b;
     op.blk1 = (uint16_t)nb;
     *w_cursor += (uint32_t)(Cin / 8) * op.b_lbo;
-    // static runs: maximal groups of blocks that are consecutive in (plane, colblk)
-    // order with SLOT_BLOCKS column blocks per plane
+    // static runs: maximal groups of blocks that are consecutive in (plane, colblk) order
     op.nruns = 0;
     size_t i = 0;
     while (i < blks.size()) {
@@ -167,15 +168,8 @@ inline void tc_build_program(int ptype, int Cin, int ncta, uint32_t* w_cursor, T
       auto lin = [&](const TcBlk& b) { return (b.dz + 1) * M::SLOT_BLOCKS + b.colblk; };
       while (e < blks.size() && lin(blks[e]) == lin(blks[i]) + (int)(e - i)) ++e;
       const int nblk = (int)(e - i);
-      int planes = 1, bpp = nblk;
-      if (blks[e - 1].dz != blks[i].dz) {  // spans planes: must cover whole slots
-        planes = blks[e - 1].dz - blks[i].dz + 1;
-        bpp = nblk / planes;
-      }
-      op.runs[op.nruns++] = (uint32_t)nblk | ((uint32_t)i << 4) |
-                            ((uint32_t)(blks[i].dz + 1) << 8) | ((uint32_t)blks[i].colblk << 10) |
-                            ((uint32_t)bpp << 12) | ((uint32_t)planes << 16);
-      pr->need |= ((1u << planes) - 1u) << (blks[i].dz + 1);
+      op.runs[op.nruns++] = (uint32_t)nblk | ((uint32_t)i << 4) | ((uint32_t)lin(blks[i]) << 10);
+      for (size_t k = i; k < e; ++k) pr->need |= 1u << (blks[k].dz + 1);
       i = e;
     }
   };
@@ -208,11 +202,27 @@ inline void tc_build_program(int ptype, int Cin, int ncta, uint32_t* w_cursor, T
         for (int c = 0; c < 4; ++c) {
           const int px = cls_px[c], py = cls_py[c];
           // o = 2i - 1 + k: p=0 -> k=1,s=0 ; p=1 -> (k=2,s=0) or (k=0,s=1)
-          int kx, ky;
-          if (px == 0) { if (sx) continue; kx = 1; } else kx = sx ? 0 : 2;
-          if (py == 0) { if (sy) continue; ky = 1; } else ky = sy ? 0 : 2;
-          blks.push_back(TcBlk{(int8_t)dz, (uint8_t)c, (uint8_t)(kz * 9 + ky * 3 + kx), 0});
+          int kx = -1, ky = -1;
+          if (px == 0) { if (!sx) kx = 1; } else kx = sx ? 0 : 2;
+          if (py == 0) { if (!sy) ky = 1; } else ky = sy ? 0 : 2;
+          const bool real = kx >= 0 && ky >= 0;
+          blks.push_back(TcBlk{(int8_t)dz, (uint8_t)c,
+                               (uint8_t)(real ? kz * 9 + ky * 3 + kx : TC_ZERO_TAP), 0});
         }
+      }
+      // The x-only and y-only shifts touch two classes per plane: instead of three N = 2*NCTA
+      // MMAs (each costs the ~47-cycle issue floor) keep the all-zero blocks between the first
+      // and the last real one, so that one N = 10*NCTA MMA spans the three planes.  The
+      // diagonal shift touches one class per plane; padding it would not fit in shared memory
+      // next to four stages, so it stays three small MMAs.
+      if (sh == 3) {
+        std::vector<TcBlk> real;
+        for (const TcBlk& b : blks)
+          if (b.tap != TC_ZERO_TAP) real.push_back(b);
+        blks = real;
+      } else {
+        while (!blks.empty() && blks.front().tap == TC_ZERO_TAP) blks.erase(blks.begin());
+        while (!blks.empty() && blks.back().tap == TC_ZERO_TAP) blks.pop_back();
       }
       add_op(sy * M::PITCH + sx, blks);
     }
@@ -257,6 +267,7 @@ struct TcWeights {
               for (int j = 0; j < ncta; ++j)
                 for (int e = 0; e < 8; ++e) {
                   const int tap = prog[t].blks[op.blk0 + b].tap;
+                  if (tap == TC_ZERO_TAP) continue;  // img is zero-initialised
                   const int ci = kc * 8 + e, co = s * ncta + j;
                   const float w = packed[((size_t)tap * cin + ci) * cout + co];
                   const uint16_t hi = bf16_rn_bits(w);
@@ -418,6 +429,30 @@ __device__ __forceinline__ void split_store(const float v[8], uint8_t* hi_dst, u
 // issue() only starts the global loads (so several items are in flight per thread),
 // finish() applies the fused transform.
 // ----------------------------------------------------------------------------------
+// 16-byte activation load of the loader warps (experiment hook: DFM_LD_VARIANT)
+#ifndef DFM_LD_VARIANT
+#define DFM_LD_VARIANT 0
+#endif
+__device__ __forceinline__ float4 ld_act(const float4* p) {
+#if DFM_LD_VARIANT == 1
+  return __ldcg(p);
+#elif DFM_LD_VARIANT == 2
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#elif DFM_LD_VARIANT == 3
+  return __ldcs(p);
+#elif DFM_LD_VARIANT == 4
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+
 template <int NT>  // number of input terms (compile-time: sizes the in-flight registers)
 struct SrcLoader8 {
   Src s;
@@ -432,8 +467,8 @@ struct SrcLoader8 {
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const float* px = s.t[t].x + term_plane(s.t[t], z) * plane + inpl;
-      r.a[t][0] = __ldg(reinterpret_cast<const float4*>(px));
-      r.a[t][1] = __ldg(reinterpret_cast<const float4*>(px) + 1);
+      r.a[t][0] = ld_act(reinterpret_cast<const float4*>(px));
+      r.a[t][1] = ld_act(reinterpret_cast<const float4*>(px) + 1);
     }
   }
   __device__ __forceinline__ void finish(const Raw& r, int c0, float v[8]) const {
@@ -606,8 +641,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint8_t* w_s = smem;
   uint8_t* a_s = smem + p.w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_s + M::NSTAGE * STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * M::NSTAGE + 2 * M::NSLOT);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * M::NSTAGE + 2 * M::NSLOT + 1);
 
+  const long long t_kernel0 = clock64();
   const int tid = threadIdx.x, lane = tid & 31;
   // shfl broadcast: tells the compiler the warp index is warp-uniform, so the role
   // branches below are convergent and the MMA warp can use the uniform datapath
@@ -619,13 +655,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   auto empty_acc = [&](int s) { return bar0 + 8u * (2 * M::NSTAGE + TC_NSLOT + s); };
   constexpr int MMA_WARP = TC_THREADS / 32 - 1;
 
-  {  // resident weights of this CTA's output-channel group
-    const int split = blockIdx.x % p.nsplit;
-    const uint4* src = reinterpret_cast<const uint4*>(p.wimg + (size_t)split * p.w_bytes);
-    uint4* dst = reinterpret_cast<uint4*>(w_s);
-    for (uint32_t i = tid; i < p.w_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
+  const uint32_t w_bar = bar0 + 8u * (2 * M::NSTAGE + 2 * TC_NSLOT);
   if (tid == 0) {
     for (int s = 0; s < M::NSTAGE; ++s) {
       mbar_init(full_a(s), LG_THREADS / 32);  // one arrival per loader warp of the group
@@ -635,7 +665,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_init(full_acc(s), 1);
       mbar_init(empty_acc(s), 4);
     }
+    mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // Resident weights of this CTA's output-channel group: bulk async copies (TMA engine)
+    // that land while TMEM is being allocated / zeroed and the loaders fill the first
+    // stages; only the MMA issuer waits for them.  (A thread-copy loop here cost every
+    // launch ~10 us of serialised load latency.)
+    const int split = blockIdx.x % p.nsplit;
+    const uint8_t* src = p.wimg + (size_t)split * p.w_bytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(w_bar),
+                 "r"(p.w_bytes)
+                 : "memory");
+    constexpr uint32_t CHUNK = 32768;
+    for (uint32_t off = 0; off < p.w_bytes; off += CHUNK) {
+      const uint32_t n = min(CHUNK, p.w_bytes - off);
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(smem_u32(w_s + off)), "l"(src + off), "r"(n), "r"(w_bar)
+          : "memory");
+    }
   }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -752,6 +800,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const bool issuer = lane == 0;
       unsigned long long t_wait_a = 0, t_wait_acc = 0;
       const long long t_begin = clock64();
+      mbar_wait(w_bar, 0u, p.err);  // weight image has landed
       const uint32_t w_base = smem_u32(w_s), a_base = smem_u32(a_s);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably uniform
       constexpr uint32_t A_LBO16 = A_LBO >> 4, A_HL16 = A_HL >> 4;
@@ -892,6 +941,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               }
               done = true;
             }
+            if constexpr (MODE == TC_T) {
+              // Transposed-conv issue sequence for a plane whose three output planes are all
+              // live: the op list of tc_build_program<TC_T> is static -- shift (0,0): one run
+              // of 12 blocks from lin 0; x-only / y-only shifts: one (zero-padded) run of 10
+              // blocks from lin 1 / lin 2; diagonal shift: single blocks at lin 2, 6, 10 --
+              // so everything but the slot-ring wrap position is a compile-time constant.
+              // (The table-driven path below costs ~35 scalar instructions per MMA and shares
+              // its issue slots with three other warps; it only serves the boundary planes.)
+              if (regular) {
+                constexpr uint32_t SB = M::SLOT_BLOCKS;
+                constexpr uint32_t KCH16 = CIN / 8;
+                constexpr uint32_t NB[4] = {12u, 10u, 10u, 3u};      // blocks per weight image
+                constexpr uint32_t LIN0[4] = {0u, 1u, 2u, 2u};
+                // lin index at which the accumulator slot ring wraps (16: not inside the window)
+                const uint32_t cut = (wrapmask & 1u) ? SB : (wrapmask & 2u) ? 2u * SB : 16u;
+                auto col_of = [&](uint32_t lin) {
+                  const uint32_t pl = lin / SB;
+                  const uint32_t cb = pl == 0u ? colbase[0] : pl == 1u ? colbase[1] : colbase[2];
+                  return cb + (lin % SB) * NCTA;
+                };
+                auto mma3 = [&](uint32_t lin, uint64_t dah, uint64_t dal, uint32_t blo,
+                                uint32_t nblk) {
+                  const uint32_t idesc = idesc_bf16((int)(nblk * NCTA));
+                  const uint32_t d0 = tmem_u + col_of(lin);
+                  const uint64_t dbh = pack64(blo, b_desc_hi);
+                  const uint64_t dbl = pack64(blo + w_hi16, b_desc_hi);
+                  if (elect_one()) {
+                    umma_bf16(d0, dah, dbh, idesc, 1u);
+                    umma_bf16(d0, dal, dbh, idesc, 1u);
+                    umma_bf16(d0, dah, dbl, idesc, 1u);
+                  }
+                };
+                uint32_t b_img16 = (w_base >> 4) & 0x3FFF;  // start of this shift's weight image
+#pragma unroll
+                for (int sh = 0; sh < 4; ++sh) {
+                  const uint32_t b_lbo16 = NB[sh] * NCTA;
+                  const uint32_t a16 = (uint32_t)((sh >> 1) * M::PITCH + (sh & 1));
+#pragma unroll
+                  for (int ks = 0; ks < M::CG / 16; ++ks) {
+                    const uint32_t alo = a_lo_stage + a16 + 2 * ks * A_LBO16;
+                    const uint64_t dah = pack64(alo, a_desc_hi);
+                    const uint64_t dal = pack64(alo + A_HL16, a_desc_hi);
+                    const uint32_t blo = b_img16 + (uint32_t)(cg * NCH + 2 * ks) * b_lbo16 +
+                                         (b_lbo16 << 16);
+                    if (sh == 3) {
+#pragma unroll
+                      for (uint32_t k = 0; k < 3; ++k)
+                        mma3(LIN0[3] + k * SB, dah, dal, blo + k * NCTA, 1u);
+                    } else {
+                      const uint32_t lin0 = LIN0[sh], end = LIN0[sh] + NB[sh];
+                      const uint32_t c = min(max(cut, lin0), end);
+                      if (c > lin0) mma3(lin0, dah, dal, blo, c - lin0);
+                      if (end > c) mma3(c, dah, dal, blo + (c - lin0) * NCTA, end - c);
+                    }
+                  }
+                  b_img16 += KCH16 * b_lbo16;
+                }
+                done = true;
+              }
+            }
             if (!done) {
 #pragma unroll 1
             for (int o = 0; o < pr.nops; ++o) {
@@ -920,24 +1029,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               };
               if (regular && fm == 0) {
                 // fast path: the host-precomputed runs, split only where the slot ring wraps
+                constexpr uint32_t SB = M::SLOT_BLOCKS;
                 for (uint32_t r = 0; r < op.nruns; ++r) {
                   const uint32_t rc = op.runs[r];
-                  const uint32_t nblk = rc & 15u, bs = (rc >> 4) & 15u, dzc = (rc >> 8) & 3u;
-                  const uint32_t cb = (rc >> 10) & 3u, bpp = (rc >> 12) & 15u, npl = (rc >> 16) & 3u;
-                  uint32_t p0 = npl;
-                  if (npl == 3u) {
-                    if (wrapmask & 1u) p0 = 1u; else if (wrapmask & 2u) p0 = 2u;
-                  } else if (npl == 2u) {
-                    if (wrapmask & (1u << dzc)) p0 = 1u;
-                  }
-                  const uint32_t cbase = dzc == 0u ? colbase[0] : dzc == 1u ? colbase[1] : colbase[2];
-                  if (p0 == npl) {
-                    issue(cbase + cb * NCTA, bs, nblk, 0u);
-                  } else {
-                    issue(cbase + cb * NCTA, bs, p0 * bpp, 0u);
-                    const uint32_t d2 = dzc + p0;
-                    const uint32_t cbase2 = d2 == 1u ? colbase[1] : colbase[2];
-                    issue(cbase2 + cb * NCTA, bs + p0 * bpp, (npl - p0) * bpp, 0u);
+                  const uint32_t nblk = rc & 15u, bs = (rc >> 4) & 63u, lin0 = (rc >> 10) & 15u;
+                  uint32_t a = lin0;
+                  const uint32_t end = lin0 + nblk;
+                  while (a < end) {
+                    const uint32_t pl = a / SB;
+                    uint32_t b = end;
+                    if (pl == 0u) {
+                      if (wrapmask & 1u) b = min(b, SB);
+                      else if (wrapmask & 2u) b = min(b, 2u * SB);
+                    } else if (pl == 1u) {
+                      if (wrapmask & 2u) b = min(b, 2u * SB);
+                    }
+                    const uint32_t cbase = pl == 0u ? colbase[0] : pl == 1u ? colbase[1] : colbase[2];
+                    issue(cbase + (a % SB) * NCTA, bs + (a - lin0), b - a, 0u);
+                    a = b;
                   }
                 }
               } else {
@@ -986,6 +1095,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (timed && issuer) {
         unsigned long long* rc = p.role_cycles + (size_t)blockIdx.x * 8;
         rc[0] = (unsigned long long)(clock64() - t_begin);
+        rc[7] = (unsigned long long)(t_begin - t_kernel0);
         rc[1] = t_wait_a;
         rc[2] = t_wait_acc;
       }
@@ -1217,8 +1327,8 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
     fprintf(stderr,
             "[tc mode=%d cin=%d ncta=%d grid=%d cols=%lld Do=%d] mma: total %.0f wait_full_a %.0f "
             "wait_empty_acc %.0f | load: total %.0f wait_empty_a %.0f | epi: total %.0f "
-            "wait_full_acc %.0f\n",
-            MODE, CIN, NCTA, grid, cols, g.Do, a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+            "wait_full_acc %.0f | prologue %.0f\n",
+            MODE, CIN, NCTA, grid, cols, g.Do, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
   }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
