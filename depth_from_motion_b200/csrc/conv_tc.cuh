@@ -32,7 +32,8 @@
 //     transposed conv (TC_T, 4 (px,py) parity classes per output plane); the work of a launch
 //     is cut "stream-K" style into equal contiguous (tile column, plane) ranges per CTA.
 //   * diagnosis: DFM_TC_ROLE_CYCLES=1 prints per-role busy / wait cycles of every launch,
-//     DFM_TC_DEBUG=<bits> disables roles (1 loaders, 2 epilogue, 8 proxy fence).
+//     DFM_TC_DEBUG=<bits> disables roles (1 loaders, 2 epilogue, 8 proxy fence, 16 the
+//     loaders' global loads, 32 the loaders' shared-memory stores).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -761,7 +762,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             typename Loader::Raw raw[LB];
 #pragma unroll
             for (int b = 0; b < LB; ++b)
-              if (k0 + b < NITEM && inb[k0 + b]) ld.issue(zi, gy[k0 + b], gx[k0 + b], c0, raw[b]);
+              if (k0 + b < NITEM && inb[k0 + b] && !(p.dbg & 16))
+                ld.issue(zi, gy[k0 + b], gx[k0 + b], c0, raw[b]);
 #pragma unroll
             for (int b = 0; b < LB; ++b) {
               if (k0 + b < NITEM && live[k0 + b]) {
@@ -772,7 +774,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v[i] = 0.f;
                 }
-                split_store(v, st + soff[k0 + b], st + A_HL + soff[k0 + b]);
+                if (!(p.dbg & 32)) split_store(v, st + soff[k0 + b], st + A_HL + soff[k0 + b]);
+                else if (v[0] + v[1] + v[2] + v[3] + v[4] + v[5] + v[6] + v[7] == 1.2345f) st[0] = 1;
               }
             }
           }
