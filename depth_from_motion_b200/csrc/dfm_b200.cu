@@ -723,9 +723,12 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
     const bool one_pass = !shorten;  // same iteration space for both copies
     DFM_TRY(launch_materialize(cur_src, cv, V, (long long)Ho * Wo, ident, t.cur.p,
                                one_pass ? d_feat_out : nullptr, "materialize", st));
+    // the z-expanded NCDHW copy re-reads every stored plane up to 20 times: read the one-term
+    // channels-last copy just written instead of summing the three terms again
     if (!one_pass && d_feat_out)
-      DFM_TRY(launch_materialize(cur_src, cv, (long long)Dfull * Ho * Wo, (long long)Ho * Wo, ze,
-                                 nullptr, d_feat_out, "materialize_expand", st));
+      DFM_TRY(launch_materialize(src1(term(t.cur, nullptr, 0)), cv, (long long)Dfull * Ho * Wo,
+                                 (long long)Ho * Wo, ze, nullptr, d_feat_out,
+                                 "materialize_expand", st));
   }
   // depth prediction module (dfm_backbone.py:118-128)
   g = geom_s(D, Ho, Wo, cv, cv, 1, 1, 1, 1, 1, 1);
@@ -1142,6 +1145,8 @@ int dfm_depth_head_forward(const float* d_cost, const float* d_depth_samples, in
                            float* d_preds, void* stream) {
   if (!d_cost || !d_depth_samples) return fail(DFM_ERR_INVALID, "null argument");
   if (D < 1 || Ho < 1 || Wo < 1 || factor < 1) return fail(DFM_ERR_INVALID, "bad shape");
+  if ((long long)D * factor > dfm::DH_MAXBINS)
+    return fail(DFM_ERR_INVALID, "DepthHead: more than 1024 depth bins");
   dim3 grid((Wo * factor + 31) / 32, Ho * factor), block(32, dfm::DH_ZS);
   {
     ProfScope ps("depth_head", 0.0, (cudaStream_t)stream);
