@@ -1147,10 +1147,12 @@ int dfm_depth_head_forward(const float* d_cost, const float* d_depth_samples, in
   if (D < 1 || Ho < 1 || Wo < 1 || factor < 1) return fail(DFM_ERR_INVALID, "bad shape");
   if ((long long)D * factor > dfm::DH_MAXBINS)
     return fail(DFM_ERR_INVALID, "DepthHead: more than 1024 depth bins");
+  if (dfm::dh_smem_bytes(D, factor) > 32768)
+    return fail(DFM_ERR_INVALID, "DepthHead: too many depth planes for the staged columns");
   dim3 grid((Wo * factor + 31) / 32, Ho * factor), block(32, dfm::DH_ZS);
   {
     ProfScope ps("depth_head", 0.0, (cudaStream_t)stream);
-    dfm::depth_head_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+    dfm::depth_head_kernel<<<grid, block, dfm::dh_smem_bytes(D, factor), (cudaStream_t)stream>>>(
         d_cost, d_depth_samples, D, Ho, Wo, factor, d_volume, d_softmax, d_preds);
   }
   LAUNCH_CHECK();

@@ -486,10 +486,16 @@ __device__ __forceinline__ float dh_plane(const float* __restrict__ c, long long
 // the serial per-pixel loops are DH_ZS times shorter and the grid DH_ZS times larger.
 constexpr int DH_ZS = 4;
 constexpr int DH_MAXBINS = 1024;  // bins (f * D) whose interpolation table fits in shared memory
+__host__ __device__ inline int dh_ncols(int f) { return 32 / f + 3; }
+inline size_t dh_smem_bytes(int D, int f) { return (size_t)D * 2 * dh_ncols(f) * sizeof(float); }
 __global__ void __launch_bounds__(32 * DH_ZS)
 depth_head_kernel(const float* __restrict__ cost, const float* __restrict__ samples, int D,
                   int Ho, int Wo, int f, float* __restrict__ vol, float* __restrict__ sm,
                   float* __restrict__ preds, float2* __restrict__ norm = nullptr) {
+  // the two low-res rows (y0, y1) x the <= 32/f + 3 low-res columns this block of 32 pixels
+  // interpolates between, all D planes: [D][2][nc].  Staged once per block -- every thread
+  // fetching its four corners per plane from global memory made the kernel L1-wavefront bound.
+  extern __shared__ float dh_cols[];
   __shared__ float red[3][DH_ZS][32];
   // per upsampled bin k: low-res plane z0 = floor(sz * k), weight of plane z0 + 1, and the bin's
   // depth.  Tabulated once per block: the int<->float conversions of computing them per
@@ -516,16 +522,29 @@ depth_head_kernel(const float* __restrict__ cost, const float* __restrict__ samp
   const int x0 = (int)fx, y0 = (int)fy;
   const int x1 = x0 + (x0 < Wo - 1 ? 1 : 0), y1 = y0 + (y0 < Ho - 1 ? 1 : 0);
   const float lx1 = fx - x0, ly1 = fy - y0;
-  const int o[4] = {y0 * Wo + x0, y0 * Wo + x1, y1 * Wo + x0, y1 * Wo + x1};
   const float w[4] = {1.f - lx1, lx1, 1.f - ly1, ly1};
   const long long plane = (long long)Ho * Wo;
   const long long opix = (long long)Y * OW + X, oplane = (long long)OH * OW;
+  const int nc = dh_ncols(f);
+  const int xb = (int)(sx * (blockIdx.x * 32));  // first low-res column of the block
+  for (int i = seg * 32 + tx; i < D * 2 * nc; i += 32 * DH_ZS) {
+    const int z = i / (2 * nc), rc = i - z * 2 * nc;
+    const int r = rc >= nc ? 1 : 0, c = rc - r * nc;
+    dh_cols[i] = __ldg(cost + z * plane + (r ? y1 : y0) * Wo + min(xb + c, Wo - 1));
+  }
+  __syncthreads();
+  const int c0 = x0 - xb, c1 = x1 - xb;
+  // same association as ATen upsample_trilinear3d:
+  // h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)
+  auto col = [&](int z) {
+    const float* pz = dh_cols + z * 2 * nc;
+    return w[2] * (w[0] * pz[c0] + w[1] * pz[c1]) + w[3] * (w[0] * pz[nc + c0] + w[1] * pz[nc + c1]);
+  };
 
   // The upsampled column is piecewise linear in k between the low-res planes, so its maximum
   // is the maximum of the D (y,x)-interpolated low-res values: no online-softmax rescaling.
   float m = -INFINITY;
-  for (int z = seg * D / DH_ZS; z < (seg + 1) * D / DH_ZS; ++z)
-    m = fmaxf(m, dh_plane(cost, z * plane, o, w));
+  for (int z = seg * D / DH_ZS; z < (seg + 1) * D / DH_ZS; ++z) m = fmaxf(m, col(z));
   red[0][seg][tx] = m;
   __syncthreads();
 #pragma unroll
@@ -539,8 +558,8 @@ depth_head_kernel(const float* __restrict__ cost, const float* __restrict__ samp
     const int z0 = tab_z0[k];
     const float lz1 = tab_l1[k];
     if (z0 != zc) {
-      b0 = (z0 == zc + 1 && zc >= 0) ? b1 : dh_plane(cost, z0 * plane, o, w);
-      b1 = z0 < D - 1 ? dh_plane(cost, (z0 + 1) * plane, o, w) : b0;
+      b0 = (z0 == zc + 1 && zc >= 0) ? b1 : col(z0);
+      b1 = z0 < D - 1 ? col(z0 + 1) : b0;
       zc = z0;
     }
     const float v = (1.f - lz1) * b0 + lz1 * b1;
@@ -572,8 +591,8 @@ depth_head_kernel(const float* __restrict__ cost, const float* __restrict__ samp
     const int z0 = tab_z0[k];
     const float lz1 = tab_l1[k];
     if (z0 != zc) {
-      b0 = (z0 == zc + 1 && zc >= 0) ? b1 : dh_plane(cost, z0 * plane, o, w);
-      b1 = z0 < D - 1 ? dh_plane(cost, (z0 + 1) * plane, o, w) : b0;
+      b0 = (z0 == zc + 1 && zc >= 0) ? b1 : col(z0);
+      b1 = z0 < D - 1 ? col(z0 + 1) : b0;
       zc = z0;
     }
     const float v = (1.f - lz1) * b0 + lz1 * b1;
