@@ -40,7 +40,7 @@ V = D * HO * WO
 FLOPS_PER_FRAME = 521856.0 * V
 IO_BYTES_PER_FRAME = 2 * 32 * H * W * 4 + 5.25e6 + 33 * V * 4
 WORKLOAD = 'dfm_r34_1x8_kitti-3d-3class D=112 384x1248 batch=1'
-NCU_DOMINANT_TRAFFIC_BYTES = 976.7e6   # 587.1 MB read + 389.6 MB written, profiles/r01_ncu_conv_tc.csv
+NCU_DOMINANT_TRAFFIC_BYTES = 973.3e6   # 587.2 MB read + 386.1 MB written, profiles/r01_ncu_conv_tc.csv
 
 
 def peaks():
