@@ -156,3 +156,50 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(['cuobjdump', '-lelf', capi.LIB_PATH], capture_output=True,
                          text=True).stdout if shutil.which('cuobjdump') else 'sm_100a'
     assert 'sm_100a' in out
+
+
+@pytest.mark.skipif(shutil.which('gcc') is None, reason='no C compiler')
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The header is plain C: compile it with gcc and compare sizeof / offsetof of every
+    descriptor struct with the ctypes mirror in capi.py (an ABI drift would corrupt
+    arguments silently)."""
+    structs = {'dfm_geometry_t': capi.Geometry, 'dfm_backbone_desc_t': capi.BackboneDesc,
+               'dfm_lift_desc_t': capi.LiftDesc, 'dfm_neck_desc_t': capi.NeckDesc,
+               'dfm_frustum_desc_t': capi.FrustumDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>',
+             f'#include "{os.path.join(ROOT, "include", "dfm_b200.h")}"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0;', '}']
+    src = tmp_path / 'abi.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'abi'
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-o', str(exe), str(src)],
+                   check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                 check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f'{cname}.{fname}']) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_frustum_host_side_contract():
+    """FrustumToVoxel mirror: voxel-grid axes are recovered from the injected coordinates_3d
+    (detectors/dfm.py:193-211), a non-meshgrid tensor is refused, CPU tensors are refused."""
+    c3d = syn.frustum_coordinates(syn.KITTI_POINT_CLOUD_RANGE, (288, 304, 20))
+    xs, ys, zs = modules.FrustumToVoxel._separable_centres(c3d)
+    assert (len(xs), len(ys), len(zs)) == (288, 304, 20)
+    assert abs(float(xs[0]) - 2.1) < 1e-6 and abs(float(ys[-1]) - 30.3) < 1e-5
+    assert abs(float(zs[0]) + 2.9) < 1e-6
+    bad = c3d.clone()
+    bad[3, 5, 7, 0] += 0.01
+    with pytest.raises(RuntimeError):
+        modules.FrustumToVoxel._separable_centres(bad)
+    m = modules.FrustumToVoxel()
+    m.coordinates_3d, m.depth_cfg = c3d, syn.depth_cfg_for(8)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 32, 8, 8, 16), modules.CostLogits(torch.zeros(1, 1, 8, 8, 16)),
+          [dict(cam2img=np.eye(4).tolist(), pad_shape=(32, 64, 3))], torch.zeros(1, 32, 8, 16))
