@@ -232,7 +232,7 @@ inline void tc_build_program(int ptype, int Cin, int ncta, uint32_t* w_cursor, T
 
 struct TcWeights {
   uint8_t* dev = nullptr;  // [nsplit][image bytes]
-  int Cin = 0, Cout = 0, ncta = 0, nsplit = 0, mode = -1;
+  int Cin = 0, Cout = 0, ncta = 0, nsplit = 0, mode = -1, kslice = 0;
   uint32_t image_bytes = 0, hi_bytes = 0;
   TcProgram prog[2];
 
@@ -243,21 +243,25 @@ struct TcWeights {
   }
   // packed: [27][Cin][Cout] fp32 (tap = kz*9 + ky*3 + kx; transposed weights are
   // already in "o = 2i - 1 + k" orientation)
+  // kslice: the CTA groups split the *input* channels (16 per group) and each covers all
+  // output channels; partial sums meet in global memory (see conv_tc_kernel, KSLICE).
   template <int MODE>
-  bool build_mode(const float* packed, int cin, int cout, std::string* err) {
+  bool build_mode(const float* packed, int cin, int cout, std::string* err, bool ks = false) {
     release();
     mode = MODE;
     Cin = cin;
     Cout = cout;
-    ncta = 1024 / cin;
-    nsplit = cout / ncta;
+    kslice = ks ? 1 : 0;
+    const int cin_img = ks ? 16 : cin;  // input channels of one weight image
+    ncta = ks ? cout : 1024 / cin;
+    nsplit = ks ? cin / 16 : cout / ncta;
     uint32_t cursor = 0;
     const int ntypes = MODE == TC_S2 ? 2 : 1;
-    for (int t = 0; t < ntypes; ++t) tc_build_program<MODE>(t, cin, ncta, &cursor, &prog[t]);
+    for (int t = 0; t < ntypes; ++t) tc_build_program<MODE>(t, cin_img, ncta, &cursor, &prog[t]);
     hi_bytes = cursor;
     image_bytes = 2 * hi_bytes;
     std::vector<uint16_t> img((size_t)nsplit * image_bytes / 2);
-    const int kch = cin / 8;
+    const int kch = cin_img / 8;
     for (int s = 0; s < nsplit; ++s)
       for (int t = 0; t < ntypes; ++t)
         for (int o = 0; o < prog[t].nops; ++o) {
@@ -269,7 +273,7 @@ struct TcWeights {
                 for (int e = 0; e < 8; ++e) {
                   const int tap = prog[t].blks[op.blk0 + b].tap;
                   if (tap == TC_ZERO_TAP) continue;  // img is zero-initialised
-                  const int ci = kc * 8 + e, co = s * ncta + j;
+                  const int ci = kc * 8 + e + (ks ? s * 16 : 0), co = ks ? j : s * ncta + j;
                   const float w = packed[((size_t)tap * cin + ci) * cout + co];
                   const uint16_t hi = bf16_rn_bits(w);
                   const uint16_t lo = bf16_rn_bits(w - bf16_bits_to_float(hi));
@@ -289,7 +293,13 @@ struct TcWeights {
   }
   bool build(const float* packed, int cin, int cout, int m, std::string* err) {
     if (m == TC_S1) return build_mode<TC_S1>(packed, cin, cout, err);
-    if (m == TC_S2) return build_mode<TC_S2>(packed, cin, cout, err);
+    if (m == TC_S2) {
+      // stride-2 layers are loader-bound: with output-channel groups every group re-loads and
+      // re-transforms the whole input (2x for 32->64, 4x for 64->64); input-channel slices load
+      // it exactly once (DFM_NO_KSLICE=1 keeps the output-channel split for A/B runs)
+      static const bool no_ks = getenv("DFM_NO_KSLICE") != nullptr;
+      return build_mode<TC_S2>(packed, cin, cout, err, cout == 64 && !no_ks);
+    }
     return build_mode<TC_T>(packed, cin, cout, err);
   }
 };
@@ -569,6 +579,7 @@ struct TcParams {
   // (longer) z-invariant interior of a shortened volume
   int zw_lo, zw_hi;
   float zw;
+  long long slice_stride;  // K-slice variant: elements between the slices' partial outputs
   int store1;  // epilogue stores only output channel 0, densely ([V] floats): the Cout=1 conv
   int dbg;  // diagnosis only (DFM_TC_DEBUG): 1 loaders skip work, 2 epilogue skips, 4 no MMA,
             // 8 loaders skip the proxy fence
@@ -629,7 +640,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   constexpr uint32_t STAGE_BYTES = 2 * A_HL;
   constexpr uint32_t B_SBO = 128;
   constexpr int SLOT_COLS = M::SLOT_BLOCKS * NCTA;
-  constexpr int TC_NSLOT = M::NSLOT;
+  // K-slice variant (stride 2, instantiated with CIN = 16 = the channels this CTA group loads,
+  // NCTA = all output channels): every slice stores its partial sums; kslice_reduce_kernel adds
+  // them in slice order (deterministic) and takes the GroupNorm statistics on the way
+  constexpr bool KSLICE = MODE == TC_S2 && CIN == 16;
+  constexpr int TC_NSLOT = M::NSLOT * SLOT_COLS > 512 ? 512 / SLOT_COLS : M::NSLOT;
   constexpr uint32_t TMEM_COLS = TC_NSLOT * SLOT_COLS;  // 256 / 512
   constexpr int NPOS = M::PXB * M::PYB;
   // two loader groups (even / odd loader warps) fill alternate stages: while one group
@@ -754,7 +769,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int s = stage_ctr % M::NSTAGE;
           mbar_wait_timed(empty_a(s), ((stage_ctr / M::NSTAGE) & 1) ^ 1, p.err, t_wait_e, timed);
           uint8_t* st = a_s + s * STAGE_BYTES;
-          const int c0 = cg * M::CG + chunk * 8;
+          const int c0 = cg * M::CG + chunk * 8 + (KSLICE ? it.split * CIN : 0);
           constexpr int LB = Loader::BATCH < NITEM ? Loader::BATCH : NITEM;
           if (!(p.dbg & 1))
 #pragma unroll
@@ -1111,14 +1126,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const bool timed = p.role_cycles != nullptr && tid == 0;
     unsigned long long t_wait_f = 0;
     const long long t_begin = clock64();
-    float ssum[NCTA], ssq[NCTA];
+    constexpr int EW = NCTA > 32 ? 32 : NCTA;   // accumulator columns drained per step
+    constexpr int NSUB = NCTA / EW;
+    constexpr int NST = KSLICE ? 1 : NCTA;      // the K-slice variant keeps no statistics
+    float ssum[NST], ssq[NST];
 #pragma unroll
-    for (int i = 0; i < NCTA; ++i) ssum[i] = ssq[i] = 0.f;
+    for (int i = 0; i < NST; ++i) ssum[i] = ssq[i] = 0.f;
     int cur_split = -1;
     auto flush_stats = [&]() {
-      if (!p.stats || cur_split < 0) return;
+      if (KSLICE || !p.stats || cur_split < 0) return;
 #pragma unroll
-      for (int i = 0; i < NCTA; ++i) {
+      for (int i = 0; i < NST; ++i) {
         double a = ssum[i], b = ssq[i];
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
@@ -1150,11 +1168,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
 #pragma unroll
         for (int cb = 0; cb < M::SLOT_BLOCKS; ++cb) {
-          uint32_t r[NCTA];
-          tmem_ld<NCTA>(tmem_base + ((uint32_t)(warp * 32) << 16) + slot * SLOT_COLS + cb * NCTA, r);
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+          uint32_t r[EW];
+          const uint32_t tcol = tmem_base + ((uint32_t)(warp * 32) << 16) + slot * SLOT_COLS +
+                                cb * NCTA + sub * EW;
+          tmem_ld<EW>(tcol, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          tmem_zero<NCTA>(tmem_base + ((uint32_t)(warp * 32) << 16) + slot * SLOT_COLS + cb * NCTA);
-          if (cb == M::SLOT_BLOCKS - 1) {
+          tmem_zero<EW>(tcol);
+          if (cb == M::SLOT_BLOCKS - 1 && sub == NSUB - 1) {
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -1166,12 +1188,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               xo = 2 * mx + ((cb == 1 || cb == 2) ? 1 : 0);
               yo = 2 * my + (cb >= 2 ? 1 : 0);
             }
+            const int ch0 = (KSLICE ? 0 : it.split * NCTA) + sub * EW;  // first output channel
             if (p.addend) {
               const int cls = zo == 0 ? 0 : (zo == p.Do - 1 ? 2 : 1);
               const float4* ad = reinterpret_cast<const float4*>(
-                  p.addend + (((long long)cls * p.Ho + yo) * p.Wo + xo) * p.Cout + it.split * NCTA);
+                  p.addend + (((long long)cls * p.Ho + yo) * p.Wo + xo) * p.Cout + ch0);
 #pragma unroll
-              for (int q = 0; q < NCTA / 4; ++q) {
+              for (int q = 0; q < EW / 4; ++q) {
                 const float4 a4 = __ldg(ad + q);
                 r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + a4.x);
                 r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + a4.y);
@@ -1182,23 +1205,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (p.store1) {
               p.out[((long long)zo * p.Ho + yo) * p.Wo + xo] = __uint_as_float(r[0]);
             } else {
+              // (K-slice variant: p.out is the scratch, every slice stores its partial sums)
               float4* dst = reinterpret_cast<float4*>(
-                  p.out + (((long long)zo * p.Ho + yo) * p.Wo + xo) * p.Cout + it.split * NCTA);
+                  p.out + (KSLICE ? it.split * p.slice_stride : 0) +
+                  (((long long)zo * p.Ho + yo) * p.Wo + xo) * p.Cout + ch0);
 #pragma unroll
-              for (int q = 0; q < NCTA / 4; ++q)
+              for (int q = 0; q < EW / 4; ++q)
                 dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
                                      __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
             }
-            if (p.stats) {
-              const float wz = (zo >= p.zw_lo && zo < p.zw_hi) ? p.zw : 1.f;
+            if constexpr (!KSLICE) {
+              if (p.stats) {
+                const float wz = (zo >= p.zw_lo && zo < p.zw_hi) ? p.zw : 1.f;
 #pragma unroll
-              for (int i = 0; i < NCTA; ++i) {
-                const float v = __uint_as_float(r[i]);
-                ssum[i] = fmaf(wz, v, ssum[i]);
-                ssq[i] = fmaf(wz * v, v, ssq[i]);
+                for (int i = 0; i < EW; ++i) {
+                  const float v = __uint_as_float(r[i]);
+                  ssum[sub * EW + i] = fmaf(wz, v, ssum[sub * EW + i]);
+                  ssq[sub * EW + i] = fmaf(wz * v, v, ssq[sub * EW + i]);
+                }
               }
             }
           }
+        }
         }
       }
       // a CTA keeps one output-channel group, so one flush per item keeps the fp32
@@ -1255,11 +1283,69 @@ inline int tc_sm_count() {
   return cached;
 }
 
+// out[v][c] = sum over slices (in slice order) of part[s][v][c], C = 64; optional per-channel
+// sum / sum of squares (planes [zw_lo, zw_hi) weighted by zw, like the conv epilogue does)
+__global__ void __launch_bounds__(256)
+kslice_reduce_kernel(const float* __restrict__ part, int nsl, long long V, long long HW,
+                     float* __restrict__ out, double* __restrict__ stats, int zw_lo, int zw_hi,
+                     float zw) {
+  __shared__ double sh[2][16][64];
+  const int q = threadIdx.x & 15, r = threadIdx.x >> 4;  // channel quad, voxel row
+  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  const long long w0 = (long long)zw_lo * HW, w1 = (long long)zw_hi * HW;
+  for (long long v = (long long)blockIdx.x * 16 + r; v < V; v += (long long)gridDim.x * 16) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(part + v * 64) + q);
+    for (int k = 1; k < nsl; ++k) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(part + ((long long)k * V + v) * 64) + q);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(out + v * 64)[q] = a;
+    if (stats) {
+      const double wgt = (v >= w0 && v < w1) ? (double)zw : 1.0;
+      s[0] += wgt * a.x; ss[0] += wgt * (double)a.x * a.x;
+      s[1] += wgt * a.y; ss[1] += wgt * (double)a.y * a.y;
+      s[2] += wgt * a.z; ss[2] += wgt * (double)a.z * a.z;
+      s[3] += wgt * a.w; ss[3] += wgt * (double)a.w * a.w;
+    }
+  }
+  if (!stats) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sh[0][r][4 * q + i] = s[i];
+    sh[1][r][4 * q + i] = ss[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int c = threadIdx.x & 63, which = threadIdx.x >> 6;
+    double t = 0.0;
+    for (int k = 0; k < 16; ++k) t += sh[which][k][c];
+    atomicAdd(stats + 2 * c + which, t);
+  }
+}
+struct TcScratch {
+  float* p = nullptr;
+  size_t n = 0;
+  float* get(size_t count) {  // grow-only, lives as long as the library
+    if (n >= count) return p;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (cudaMalloc(&p, count * sizeof(float)) != cudaSuccess) return nullptr;
+    n = count;
+    return p;
+  }
+};
+inline TcScratch& tc_kslice_scratch() {
+  static TcScratch sc;
+  return sc;
+}
+
 struct TcOpts {
   int store1 = 0;
   const float* addend = nullptr;
   int zw_lo = 0, zw_hi = 0;
   float zw = 1.f;
+  long long slice_stride = 0;
 };
 template <int MODE, int CIN, int NCTA, class Loader>
 bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
@@ -1285,6 +1371,7 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
   p.out = out;
   p.stats = stats;
   p.store1 = opt.store1;
+  p.slice_stride = opt.slice_stride;
   p.addend = opt.addend;
   p.zw_lo = opt.zw_lo;
   p.zw_hi = opt.zw_hi;
@@ -1348,6 +1435,31 @@ bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats
   if (mode != w.mode) {
     if (err) *err = "conv_tc: weight image was built for a different conv mode";
     return false;
+  }
+  if (w.kslice) {
+    // the input-channel slices store partial outputs into a scratch; a second kernel adds them
+    // in slice order into `out` and accumulates the GroupNorm statistics
+    if (mode != TC_S2 || g.Cout != 64 || opt.addend || opt.store1) {
+      if (err) *err = "conv_tc: K-slice weights are for plain stride-2 convs with 64 outputs";
+      return false;
+    }
+    const long long V = (long long)g.Do * g.Ho * g.Wo;
+    float* part = tc_kslice_scratch().get((size_t)w.nsplit * V * 64);
+    if (!part) {
+      if (err) *err = "conv_tc: cannot allocate the K-slice scratch";
+      return false;
+    }
+    TcOpts o2 = opt;
+    o2.slice_stride = V * 64;
+    if (!tc_launch<TC_S2, 16, 64, Loader>(ld, w, part, nullptr, g, st, err, o2)) return false;
+    const int blocks = (int)std::min<long long>(148 * 8, (V + 15) / 16);
+    kslice_reduce_kernel<<<blocks, 256, 0, st>>>(part, w.nsplit, V, (long long)g.Ho * g.Wo, out,
+                                                 stats, opt.zw_lo, opt.zw_hi, opt.zw);
+    if (cudaGetLastError() != cudaSuccess) {
+      if (err) *err = "conv_tc: kslice_reduce_kernel launch failed";
+      return false;
+    }
+    return true;
   }
 #define TC_CASE(MD, CI, NC) \
   if (mode == MD && g.Cin == CI) \
