@@ -292,7 +292,13 @@ struct TcWeights {
     return true;
   }
   bool build(const float* packed, int cin, int cout, int m, std::string* err) {
-    if (m == TC_S1) return build_mode<TC_S1>(packed, cin, cout, err);
+    static const bool no_ks1 = getenv("DFM_NO_KSLICE") != nullptr;
+    // stride 1, 64 -> 64: four output-channel groups would each re-load the input and issue
+    // N = 48 MMAs (47-cycle issue floor for 48 columns); four input-channel slices issue
+    // N = 192 MMAs (96 cycles for 192 columns) on a quarter of the input each
+    static const bool ks1 = getenv("DFM_KSLICE_S1") != nullptr;  // opt-in until validated on GPU
+    if (m == TC_S1) return build_mode<TC_S1>(packed, cin, cout, err,
+                                             cin == 64 && cout == 64 && !no_ks1 && ks1);
     if (m == TC_S2) {
       // stride-2 layers are loader-bound: with output-channel groups every group re-loads and
       // re-transforms the whole input (2x for 32->64, 4x for 64->64); input-channel slices load
@@ -632,18 +638,19 @@ template <int MODE, int CIN, int NCTA, class Loader>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p,
                                                                  const Loader ld) {
   using M = TcMode<MODE>;
-  constexpr int NCH = M::CG / 8;                 // 16-byte channel chunks per stage
-  constexpr int NCG = CIN / M::CG;               // pipeline stages per input plane
+  constexpr int CG = M::CG < CIN ? M::CG : CIN;  // channels per stage
+  constexpr int NCH = CG / 8;                    // 16-byte channel chunks per stage
+  constexpr int NCG = CIN / CG;                  // pipeline stages per input plane
   constexpr uint32_t A_LBO = M::ROWS * 16;
   constexpr uint32_t A_SBO = (MODE == TC_S2 ? 1 : 1) * M::PITCH * 16;
   constexpr uint32_t A_HL = NCH * M::ROWS * 16;  // hi -> lo array offset in a stage
   constexpr uint32_t STAGE_BYTES = 2 * A_HL;
   constexpr uint32_t B_SBO = 128;
   constexpr int SLOT_COLS = M::SLOT_BLOCKS * NCTA;
-  // K-slice variant (stride 2, instantiated with CIN = 16 = the channels this CTA group loads,
+  // K-slice variant (stride 1 / 2, instantiated with CIN = 16 = the channels this CTA group loads,
   // NCTA = all output channels): every slice stores its partial sums; kslice_reduce_kernel adds
   // them in slice order (deterministic) and takes the GroupNorm statistics on the way
-  constexpr bool KSLICE = MODE == TC_S2 && CIN == 16;
+  constexpr bool KSLICE = CIN == 16;
   constexpr int TC_NSLOT = M::NSLOT * SLOT_COLS > 512 ? 512 / SLOT_COLS : M::NSLOT;
   constexpr uint32_t TMEM_COLS = TC_NSLOT * SLOT_COLS;  // 256 / 512
   constexpr int NPOS = M::PXB * M::PYB;
@@ -769,7 +776,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int s = stage_ctr % M::NSTAGE;
           mbar_wait_timed(empty_a(s), ((stage_ctr / M::NSTAGE) & 1) ^ 1, p.err, t_wait_e, timed);
           uint8_t* st = a_s + s * STAGE_BYTES;
-          const int c0 = cg * M::CG + chunk * 8 + (KSLICE ? it.split * CIN : 0);
+          const int c0 = cg * CG + chunk * 8 + (KSLICE ? it.split * CIN : 0);
           constexpr int LB = Loader::BATCH < NITEM ? Loader::BATCH : NITEM;
           if (!(p.dbg & 1))
 #pragma unroll
@@ -872,7 +879,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               // ~47 cycles per tcgen05.mma issue, so scalar work per MMA must be ~1 op).
               constexpr uint32_t B_LBO16 = 3 * NCTA;               // weight image rows
               constexpr uint32_t TAP16 = (CIN / 8) * B_LBO16;      // one tap, 16-byte units
-              constexpr int NKS = M::CG / 16;
+              constexpr int NKS = CG / 16;
               const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFF) + (uint32_t)(cg * NCH) * B_LBO16 +
                                      (B_LBO16 << 16);
               // first / one-past-last live plane index (0..3) of this input plane
@@ -997,7 +1004,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   const uint32_t b_lbo16 = NB[sh] * NCTA;
                   const uint32_t a16 = (uint32_t)((sh >> 1) * M::PITCH + (sh & 1));
 #pragma unroll
-                  for (int ks = 0; ks < M::CG / 16; ++ks) {
+                  for (int ks = 0; ks < CG / 16; ++ks) {
                     const uint32_t alo = a_lo_stage + a16 + 2 * ks * A_LBO16;
                     const uint64_t dah = pack64(alo, a_desc_hi);
                     const uint64_t dal = pack64(alo + A_HL16, a_desc_hi);
@@ -1351,7 +1358,8 @@ template <int MODE, int CIN, int NCTA, class Loader>
 bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
                const ConvGeom& g, cudaStream_t st, std::string* err, TcOpts opt = TcOpts()) {
   using M = TcMode<MODE>;
-  constexpr size_t STAGE_BYTES = (size_t)2 * (M::CG / 8) * M::ROWS * 16;
+  constexpr int CG = M::CG < CIN ? M::CG : CIN;
+  constexpr size_t STAGE_BYTES = (size_t)2 * (CG / 8) * M::ROWS * 16;
   const size_t smem = w.image_bytes + M::NSTAGE * STAGE_BYTES +
                       (2 * M::NSTAGE + 2 * M::NSLOT) * 8 + 16;
   auto kern = conv_tc_kernel<MODE, CIN, NCTA, Loader>;
@@ -1439,8 +1447,8 @@ bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats
   if (w.kslice) {
     // the input-channel slices store partial outputs into a scratch; a second kernel adds them
     // in slice order into `out` and accumulates the GroupNorm statistics
-    if (mode != TC_S2 || g.Cout != 64 || opt.addend || opt.store1) {
-      if (err) *err = "conv_tc: K-slice weights are for plain stride-2 convs with 64 outputs";
+    if ((mode != TC_S2 && mode != TC_S1) || g.Cout != 64 || opt.addend || opt.store1) {
+      if (err) *err = "conv_tc: K-slice weights are for plain convs with 64 outputs";
       return false;
     }
     const long long V = (long long)g.Do * g.Ho * g.Wo;
@@ -1451,7 +1459,10 @@ bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats
     }
     TcOpts o2 = opt;
     o2.slice_stride = V * 64;
-    if (!tc_launch<TC_S2, 16, 64, Loader>(ld, w, part, nullptr, g, st, err, o2)) return false;
+    const bool launched = mode == TC_S2
+                              ? tc_launch<TC_S2, 16, 64, Loader>(ld, w, part, nullptr, g, st, err, o2)
+                              : tc_launch<TC_S1, 16, 64, Loader>(ld, w, part, nullptr, g, st, err, o2);
+    if (!launched) return false;
     const int blocks = (int)std::min<long long>(148 * 8, (V + 15) / 16);
     kslice_reduce_kernel<<<blocks, 256, 0, st>>>(part, w.nsplit, V, (long long)g.Ho * g.Wo, out,
                                                  stats, opt.zw_lo, opt.zw_hi, opt.zw);
