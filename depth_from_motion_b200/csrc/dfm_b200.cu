@@ -311,7 +311,7 @@ int run_conv_impl(const L& simt_loader, TCFN tc_fn, const char* loader_name, con
       ProfScope ps(conv_class("conv_tc", g, loader_name), conv_flops(g), st);
       if (!tc_fn(gn ? gn->sums : nullptr, &err)) return fail(DFM_ERR_CUDA, err);
     }
-    g_launches.fetch_add(1);
+    g_launches.fetch_add(w.tc.kslice ? 2 : 1);  // K-slice convs run a slice-reduce kernel too
     g_tc_launches.fetch_add(1);
     return gn ? gn_finalize(*gn, V, 32, st) : DFM_OK;
   }
