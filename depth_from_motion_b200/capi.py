@@ -26,7 +26,8 @@ SYMBOLS = (
     'dfm_backbone_create', 'dfm_backbone_destroy', 'dfm_backbone_set_param',
     'dfm_backbone_set_depths', 'dfm_backbone_missing_params',
     'dfm_backbone_workspace_bytes', 'dfm_backbone_forward',
-    'dfm_backbone_forward_host', 'dfm_backbone_cost_device',
+    'dfm_backbone_forward_host', 'dfm_backbone_prefetch_host',
+    'dfm_backbone_cost_device',
     'dfm_backbone_stereo_feat_device',
     'dfm_backbone_debug_tensor', 'dfm_op_build_cost_volume', 'dfm_op_conv3d',
     'dfm_depth_head_forward', 'dfm_multiview_lift', 'dfm_neck_create',
@@ -116,6 +117,7 @@ def lib():
                                        vp, vp]
     L.dfm_backbone_forward_host.argtypes = [vp, vp, vp, POINTER(Geometry),
                                             c_int, vp, vp, vp, vp]
+    L.dfm_backbone_prefetch_host.argtypes = [vp, vp, vp]
     L.dfm_backbone_cost_device.argtypes = [vp]
     L.dfm_backbone_cost_device.restype = vp
     L.dfm_backbone_stereo_feat_device.argtypes = [vp]

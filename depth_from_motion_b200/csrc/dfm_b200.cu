@@ -457,7 +457,17 @@ struct dfm_backbone {
   int D, Ho, Wo;
   Tower st, mo;
   DevBuf cur_nhwc, prev_nhwc, depths, wagg, cost, volume_dbg;
-  DevBuf stage_cur, stage_prev;  // NCHW staging of the host-buffer entry point
+  // NCHW staging of the host-buffer entry point, double-buffered so that the next pair can be
+  // copied in (dfm_backbone_prefetch_host) while the current one is being processed
+  struct HostStage {
+    DevBuf cur, prev;
+    const float* h_cur = nullptr;
+    const float* h_prev = nullptr;
+    bool pending = false;      // holds a prefetched pair that no forward has consumed yet
+    cudaEvent_t ready = nullptr;
+    unsigned long long tick = 0;
+  } stage[2];
+  unsigned long long stage_tick = 0;
   bool depths_set = false;
   std::set<std::string> missing;
   std::map<std::string, std::pair<const DevBuf*, int>> dbg;  // name -> (buffer, channels)
@@ -890,8 +900,11 @@ int dfm_backbone_destroy(dfm_backbone_t* bb) {
   tower_release(bb->st);
   tower_release(bb->mo);
   for (DevBuf* b : {&bb->cur_nhwc, &bb->prev_nhwc, &bb->depths, &bb->wagg, &bb->cost,
-                    &bb->volume_dbg, &bb->stage_cur, &bb->stage_prev})
+                    &bb->volume_dbg, &bb->stage[0].cur, &bb->stage[0].prev, &bb->stage[1].cur,
+                    &bb->stage[1].prev})
     b->release();
+  for (auto& hs : bb->stage)
+    if (hs.ready) cudaEventDestroy(hs.ready);
   delete bb;
   return DFM_OK;
 }
@@ -1009,6 +1022,55 @@ const float* dfm_backbone_stereo_feat_device(const dfm_backbone_t* bb) {
   return bb ? bb->st.cur.p : nullptr;
 }
 
+}  // extern "C"
+
+namespace {
+// side stream + fork event of the host-buffer entry points (the library is not re-entrant)
+struct HostCopyCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, prev_done = nullptr;
+};
+int host_copy_ctx(HostCopyCtx** out) {
+  static HostCopyCtx ctx;
+  if (!ctx.stream) {
+    CU_TRY(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&ctx.fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ctx.prev_done, cudaEventDisableTiming));
+  }
+  *out = &ctx;
+  return DFM_OK;
+}
+int stage_alloc(dfm_backbone::HostStage& hs, size_t nfeat) {
+  DFM_TRY(hs.cur.alloc(nfeat));
+  DFM_TRY(hs.prev.alloc(nfeat));
+  if (!hs.ready) CU_TRY(cudaEventCreateWithFlags(&hs.ready, cudaEventDisableTiming));
+  return DFM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dfm_backbone_prefetch_host(dfm_backbone_t* bb, const float* h_cur, const float* h_prev) {
+  if (!bb || !h_cur || !h_prev) return fail(DFM_ERR_INVALID, "null argument");
+  HostCopyCtx* cx = nullptr;
+  DFM_TRY(host_copy_ctx(&cx));
+  const size_t nfeat = (size_t)bb->d.in_channels * bb->d.feat_h * bb->d.feat_w;
+  // a slot that holds no unconsumed pair, else the older of the two (its pair is dropped)
+  int slot = !bb->stage[0].pending ? 0 : !bb->stage[1].pending ? 1
+             : (bb->stage[0].tick <= bb->stage[1].tick ? 0 : 1);
+  dfm_backbone::HostStage& hs = bb->stage[slot];
+  DFM_TRY(stage_alloc(hs, nfeat));
+  // forward_host synchronises before it returns, so nothing on the device still reads this slot
+  CU_TRY(cudaMemcpyAsync(hs.cur.p, h_cur, nfeat * 4, cudaMemcpyHostToDevice, cx->stream));
+  CU_TRY(cudaMemcpyAsync(hs.prev.p, h_prev, nfeat * 4, cudaMemcpyHostToDevice, cx->stream));
+  CU_TRY(cudaEventRecord(hs.ready, cx->stream));
+  hs.h_cur = h_cur;
+  hs.h_prev = h_prev;
+  hs.pending = true;
+  hs.tick = ++bb->stage_tick;
+  return DFM_OK;
+}
+
 int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const float* h_prev,
                               const dfm_geometry_t* geom, int out_flags, float* h_cost,
                               float* h_stereo, float* h_mono, void* stream) {
@@ -1016,23 +1078,38 @@ int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const floa
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nfeat = (size_t)bb->d.in_channels * bb->d.feat_h * bb->d.feat_w;
   const size_t V = (size_t)bb->D * bb->Ho * bb->Wo;
-  DFM_TRY(bb->stage_cur.alloc(nfeat));
-  DFM_TRY(bb->stage_prev.alloc(nfeat));
-  float* d_cur = bb->stage_cur.p;
-  float* d_prev = bb->stage_prev.p;
-  // the prev-frame copy rides a second stream underneath the mono tower
-  static cudaStream_t copy_stream = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_prev = nullptr;
-  if (!copy_stream) {
-    CU_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    CU_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&ev_prev, cudaEventDisableTiming));
+  HostCopyCtx* cx = nullptr;
+  DFM_TRY(host_copy_ctx(&cx));
+  cudaEvent_t prev_ready = nullptr;
+  float* d_cur = nullptr;
+  float* d_prev = nullptr;
+  int hit = -1;
+  for (int i = 0; i < 2; ++i)
+    if (bb->stage[i].pending && bb->stage[i].h_cur == h_cur && bb->stage[i].h_prev == h_prev)
+      hit = i;
+  if (hit >= 0) {
+    // the pair was prefetched: both maps are (being) copied on the side stream
+    dfm_backbone::HostStage& hs = bb->stage[hit];
+    hs.pending = false;
+    d_cur = hs.cur.p;
+    d_prev = hs.prev.p;
+    CU_TRY(cudaStreamWaitEvent(st, hs.ready, 0));
+  } else {
+    const int slot = !bb->stage[0].pending ? 0 : !bb->stage[1].pending ? 1
+                     : (bb->stage[0].tick <= bb->stage[1].tick ? 0 : 1);
+    dfm_backbone::HostStage& hs = bb->stage[slot];
+    hs.pending = false;
+    DFM_TRY(stage_alloc(hs, nfeat));
+    d_cur = hs.cur.p;
+    d_prev = hs.prev.p;
+    // the prev-frame copy rides the side stream underneath the mono tower
+    CU_TRY(cudaEventRecord(cx->fork, st));  // staging buffers are free once prior work is done
+    CU_TRY(cudaStreamWaitEvent(cx->stream, cx->fork, 0));
+    CU_TRY(cudaMemcpyAsync(d_cur, h_cur, nfeat * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_prev, h_prev, nfeat * 4, cudaMemcpyHostToDevice, cx->stream));
+    CU_TRY(cudaEventRecord(cx->prev_done, cx->stream));
+    prev_ready = cx->prev_done;
   }
-  CU_TRY(cudaEventRecord(ev_fork, st));  // staging buffers are free once prior work is done
-  CU_TRY(cudaStreamWaitEvent(copy_stream, ev_fork, 0));
-  CU_TRY(cudaMemcpyAsync(d_cur, h_cur, nfeat * 4, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(d_prev, h_prev, nfeat * 4, cudaMemcpyHostToDevice, copy_stream));
-  CU_TRY(cudaEventRecord(ev_prev, copy_stream));
   float* d_st = nullptr;
   float* d_mo = nullptr;
   DevBuf tmp_s, tmp_m;
@@ -1044,7 +1121,7 @@ int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const floa
     DFM_TRY(tmp_m.alloc(V * 32));
     d_mo = tmp_m.p;
   }
-  int rc = backbone_forward_impl(bb, d_cur, d_prev, geom, nullptr, d_st, d_mo, stream, ev_prev);
+  int rc = backbone_forward_impl(bb, d_cur, d_prev, geom, nullptr, d_st, d_mo, stream, prev_ready);
   if (rc == DFM_OK && (out_flags & DFM_OUT_COST) && h_cost)
     if (cudaMemcpyAsync(h_cost, bb->cost.p, V * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
       rc = fail(DFM_ERR_CUDA, "D2H copy of cost failed");

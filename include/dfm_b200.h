@@ -99,6 +99,12 @@ int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_
 /* Same call with HOST buffers: copies the two feature maps host->device, runs the
  * path, copies the outputs selected by out_flags (DFM_OUT_*) device->host, and
  * synchronises.  Buffers should be page-locked for full PCIe bandwidth. */
+/* Optional: starts copying the NEXT pair host->device on a side stream and returns at once
+ * (page-locked buffers).  A later dfm_backbone_forward_host with the same two host pointers
+ * consumes the staged copy instead of copying again, so the transfer of pair i+1 overlaps the
+ * processing of pair i.  Two pairs can be staged; the host buffers must stay unchanged until
+ * the forward that consumes them returns. */
+int dfm_backbone_prefetch_host(dfm_backbone_t* bb, const float* h_cur, const float* h_prev);
 int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const float* h_prev,
                               const dfm_geometry_t* geom, int out_flags, float* h_cost,
                               float* h_stereo, float* h_mono, void* stream);

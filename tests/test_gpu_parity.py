@@ -508,3 +508,51 @@ def test_frustum_fused_depth_preds_and_backbone_twin():
     bb(prev.cuda(), cur.cuda(), copy.deepcopy(metas))
     a2 = m(stereo, modules.CostLogits(cost), c['metas'], sem)
     assert torch.equal(a2, b)
+
+
+def test_forward_host_and_prefetch_match_device_path():
+    """dfm_backbone_forward_host (host buffers in/out) and the prefetched variant
+    (dfm_backbone_prefetch_host for the next pair while the current one is processed) return
+    what dfm_backbone_forward returns on device tensors."""
+    import ctypes
+    cur, prev, metas, params, cfg, _ = load_kitti_case('kitti_plain')
+    m = _backbone(params, cfg, 'auto')
+    cost, stereo, mono = m(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
+    torch.cuda.synchronize()
+    L = capi.lib()
+    g = modules.geometry_from_meta(metas[0])
+    hc, hp = cur.contiguous().pin_memory(), prev.contiguous().pin_memory()
+    hc2, hp2 = prev.contiguous().pin_memory(), cur.contiguous().pin_memory()
+    outs = [torch.empty_like(t, device='cpu').pin_memory() for t in (cost, stereo, mono)]
+    flags = capi.DFM_OUT_COST | capi.DFM_OUT_STEREO | capi.DFM_OUT_MONO
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run(a, b):
+        capi.check(L.dfm_backbone_forward_host(
+            m._handle, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+            ctypes.byref(g), flags, *[ctypes.c_void_p(o.data_ptr()) for o in outs], stream),
+            'dfm_backbone_forward_host')
+        return [o.clone() for o in outs]
+
+    def pf(a, b):
+        capi.check(L.dfm_backbone_prefetch_host(
+            m._handle, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr())),
+            'dfm_backbone_prefetch_host')
+
+    plain = run(hc, hp)
+    for got, ref in zip(plain, (cost, stereo, mono)):
+        assert rel_err(got, ref) < 1e-6
+    swapped = run(hc2, hp2)
+    # prefetch both pairs, consume them in order, then once more with a stale third prefetch
+    pf(hc, hp)
+    pf(hc2, hp2)
+    a = run(hc, hp)
+    pf(hc, hp)
+    b = run(hc2, hp2)
+    c = run(hc, hp)
+    for got, ref in zip(a, plain):
+        assert rel_err(got, ref) < 1e-6
+    for got, ref in zip(b, swapped):
+        assert rel_err(got, ref) < 1e-6
+    for got, ref in zip(c, plain):
+        assert rel_err(got, ref) < 1e-6
