@@ -50,3 +50,17 @@ def test_two_rank_sharding_gloo(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert '"ok": true' in r.stdout
+
+
+def test_shard_pairs_edge_cases():
+    """Ragged and empty partitions: every pair has exactly one owner, order is kept, ranks
+    beyond the number of pairs get nothing."""
+    from depth_from_motion_b200.sharding import reduce_step_time, shard_pairs
+    for n, world in ((0, 2), (1, 4), (5, 2), (8, 8), (9, 4)):
+        pairs = list(range(n))
+        parts = [shard_pairs(pairs, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == pairs
+        assert all(p == sorted(p) for p in parts)
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    # without an initialised process group the reduction is the identity
+    assert reduce_step_time(3.5, 'cpu') == 3.5
