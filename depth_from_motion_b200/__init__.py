@@ -3,7 +3,7 @@
 Host-side mirror of the reference's plugin interface (registry + module
 classes) over the C-ABI CUDA library ``libdfm_b200.so`` (``include/dfm_b200.h``).
 """
-from . import capi  # noqa: F401
+from . import capi, checkpoint  # noqa: F401
 from .modules import (CostLogits, DepthHead, DfMBackbone,  # noqa: F401
                       DfMNeck, FrustumToVoxel, OutdoorImVoxelNeck, build_dfm_cost, conv3d,
                       multiview_lift)

@@ -203,3 +203,46 @@ def test_frustum_host_side_contract():
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 32, 8, 8, 16), modules.CostLogits(torch.zeros(1, 1, 8, 8, 16)),
           [dict(cam2img=np.eye(4).tolist(), pad_shape=(32, 64, 3))], torch.zeros(1, 32, 8, 16))
+
+
+def test_checkpoint_key_plumbing():
+    """A detector-style checkpoint (mmdet3d names, or LIGA-DfM names as handled by the
+    reference's tools/model_converters/convert_dfm_checkpoints.py:34-81) is split into the
+    hot-path modules and loads with strict=True."""
+    from depth_from_motion_b200 import checkpoint as ck
+    cfg = syn.depth_cfg_for(8)
+    rng = np.random.RandomState(5)
+    bb_sd = syn.make_backbone_params(rng, 8)
+    ft_sd = syn.make_frustum_case(7, 32, 64, 8, (8, 8, 4))['params']
+    det = {}
+    for k, v in bb_sd.items():
+        det['backbone_stereo.' + k] = v
+    for k, v in ft_sd.items():
+        det['feature_transformation.' + k] = v
+    det['backbone.layer1.0.conv1.weight'] = torch.zeros(3)
+    det['bbox_head_3d.conv_cls.weight'] = torch.zeros(3)
+    bb = modules.DfMBackbone(in_channels=32, depth_cfg=cfg)
+    ft = modules.FrustumToVoxel()
+    ck.load_hot_path({'state_dict': det}, backbone=bb, frustum=ft)
+    assert all(torch.equal(bb.state_dict()[k], v) for k, v in bb_sd.items())
+    assert all(torch.equal(ft.state_dict()[k], v) for k, v in ft_sd.items())
+    # LIGA-DfM names: backbone_3d.* is the stereo backbone except its image backbone / necks
+    # and the voxel convs
+    liga = {'global_step': torch.zeros(1)}
+    for k, v in bb_sd.items():
+        liga['backbone_3d.' + k] = v
+    for k, v in ft_sd.items():
+        liga['backbone_3d.rpn3d_convs.' + k[len('voxel_convs.'):]] = v
+    liga['backbone_3d.feature_backbone.conv1.weight'] = torch.zeros(3)
+    liga['lidar_model.backbone_3d.conv1.0.weight'] = torch.zeros(3)
+    assert ck.convert_liga_key('backbone_3d.feature_neck.x') == 'neck.x'
+    assert ck.convert_liga_key('backbone_3d.dres0.conv.weight') == \
+        'backbone_stereo.dres0.conv.weight'
+    assert ck.convert_liga_key('lidar_model.backbone_3d.conv1.0.weight').startswith('lidar_model')
+    bb2 = modules.DfMBackbone(in_channels=32, depth_cfg=cfg)
+    ft2 = modules.FrustumToVoxel()
+    ck.load_hot_path({'model_state': liga}, backbone=bb2, frustum=ft2)
+    assert all(torch.equal(bb2.state_dict()[k], v) for k, v in bb_sd.items())
+    assert all(torch.equal(ft2.state_dict()[k], v) for k, v in ft_sd.items())
+    with pytest.raises(KeyError):
+        ck.load_hot_path({'state_dict': {'x.y': torch.zeros(1)}}, backbone=bb2)
