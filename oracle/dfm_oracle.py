@@ -22,6 +22,8 @@ follows (paths relative to the reference checkout, commit e2321189):
     a7  DfMNeck / OutdoorImVoxelNeck / ResModule
                             mmdet3d/models/necks/dfm_neck.py:10-122
                             mmdet3d/models/necks/imvoxel_neck.py:8-117
+    a8  voxel_sample        mmdet3d/models/fusion_layers/point_fusion.py:324-410
+                            (oracle only: no shipped config reaches it)
     a9  points_cam2img / points_img2cam
                             mmdet3d/core/bbox/structures/utils.py:176-248
     f1  FrustumToVoxel.forward
@@ -415,6 +417,38 @@ def dfm_neck_forward(p, x, mono_channels):
 # helpers shared by tests / bench (deterministic synthetic inputs, NumPy legacy
 # MT19937 so both sides of a fixture regenerate identical tensors)
 # ----------------------------------------------------------------------------
+# ----------------------------------------------------------------------------
+# a8  voxel_sample (frustum-from-voxel resampling; not reached by a shipped config)
+# ----------------------------------------------------------------------------
+def voxel_sample(voxel_features, voxel_range, voxel_size, depth_samples, proj_mat,
+                 downsample_factor, img_scale_factor, img_crop_offset, img_flip,
+                 img_pad_shape, img_shape, aligned=True, padding_mode='zeros',
+                 align_corners=True):
+    """point_fusion.py:324-410: a (depth, v, u) frustum lattice at 1/downsample_factor
+    of the padded image is taken back through flip / crop / scale, unprojected with
+    points_img2cam, expressed in voxel-index units (-0.5: cell centres), normalised and
+    used to grid_sample the [1, C, Nx, Ny, Nz] voxel features -> [1, C, D, H, W]."""
+    h, w = img_pad_shape
+    h_out, w_out = round(h / downsample_factor), round(w / downsample_factor)
+    ws = torch.linspace(0, w_out - 1, w_out) * downsample_factor
+    hs = torch.linspace(0, h_out - 1, h_out) * downsample_factor
+    depths = depth_samples[::downsample_factor]
+    ds3, ys3, xs3 = torch.meshgrid(depths, hs, ws, indexing='ij')
+    grid = torch.stack([xs3, ys3, ds3], dim=-1).view(-1, 3)
+    if img_flip:
+        grid[:, 0] = img_shape[1] - grid[:, 0]
+    grid[:, :2] += img_crop_offset
+    grid[:, :2] /= img_scale_factor
+    grid3d = points_img2cam(grid, proj_mat)
+    vr = torch.tensor(voxel_range).view(1, 6)
+    vs = torch.tensor(voxel_size).view(1, 3)
+    grid3d = (grid3d - vr[:, :3]) / vs - 0.5
+    grid3d = grid3d / ((vr[:, 3:] - vr[:, :3]) / vs) * 2 - 1
+    grid3d = grid3d.view(1, len(depths), h_out, w_out, 3)[..., [2, 1, 0]]
+    return F.grid_sample(voxel_features, grid3d, mode='bilinear' if aligned else 'nearest',
+                         padding_mode=padding_mode, align_corners=align_corners)
+
+
 # ----------------------------------------------------------------------------
 # f1  FrustumToVoxel
 # ----------------------------------------------------------------------------

@@ -34,6 +34,20 @@ import torch.nn as nn
 REFERENCE_ROOT = os.environ.get('DFM_REFERENCE_ROOT', '/root/reference')
 
 
+def reference_function(rel_path, name, namespace):
+    """Executes ONE top-level function of a reference file verbatim (its source segment,
+    via ast) in ``namespace``: for functions whose module cannot be imported without
+    mmcv/mmdet (e.g. fusion_layers/point_fusion.py::voxel_sample)."""
+    import ast
+    src = open(os.path.join(REFERENCE_ROOT, rel_path)).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            ns = dict(namespace)
+            exec(compile(ast.get_source_segment(src, node), rel_path, 'exec'), ns)
+            return ns[name]
+    raise KeyError(name)
+
+
 def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, 'mmdet3d'))
 

@@ -141,3 +141,30 @@ def test_frustum_to_voxel_matches_reference_fixture():
     assert tuple(full.shape) == (20, 304, 288, 3)
     assert torch.equal(full, syn.frustum_coordinates(syn.KITTI_POINT_CLOUD_RANGE,
                                                      (288, 304, 20)))
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/mmdet3d'), reason='reference tree not mounted')
+@pytest.mark.parametrize('flip,aligned', [(False, True), (True, True), (False, False)])
+def test_voxel_sample_matches_reference_source(flip, aligned):
+    """SURVEY.md row a8 (oracle only): the restatement against the reference function executed
+    verbatim (point_fusion.py:324-410)."""
+    import torch.nn.functional as F
+    from oracle.ref_loader import load_reference, reference_function
+    ns = load_reference()
+    ref = reference_function('mmdet3d/models/fusion_layers/point_fusion.py', 'voxel_sample',
+                             dict(torch=torch, F=F, points_img2cam=ns.points_img2cam))
+    g = torch.Generator().manual_seed(3)
+    vox = torch.randn(1, 6, 20, 16, 8, generator=g)
+    vrange, vsize = [0.0, -8.0, -2.0, 20.0, 8.0, 2.0], [1.0, 1.0, 0.5]
+    depths = torch.linspace(2.0, 18.0, 16)
+    # lidar -> image: camera looks along +x
+    k = torch.tensor([[40., 0, 32, 0], [0, 40., 16, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+    l2c = torch.tensor([[0., -1, 0, 0], [0, 0, -1, 0.3], [1, 0, 0, 0.1], [0, 0, 0, 1]])
+    proj = k @ l2c
+    args = (vox, vrange, vsize, depths, proj, 4, torch.tensor([1.02, 0.98]),
+            torch.tensor([1.0, 2.0]), flip, (32, 64), (30, 62))
+    a = ref(*args, aligned=aligned)
+    b = O.voxel_sample(*args, aligned=aligned)
+    assert a.shape == b.shape == (1, 6, 4, 8, 16)
+    assert torch.equal(a, b)
+    assert float(a.abs().sum()) > 0
