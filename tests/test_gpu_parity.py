@@ -541,7 +541,7 @@ def test_forward_host_and_prefetch_match_device_path():
 
     plain = run(hc, hp)
     for got, ref in zip(plain, (cost, stereo, mono)):
-        assert rel_err(got, ref) < 1e-6
+        assert rel_err(got, ref) < 1e-5
     swapped = run(hc2, hp2)
     # prefetch both pairs, consume them in order, then once more with a stale third prefetch
     pf(hc, hp)
@@ -551,8 +551,8 @@ def test_forward_host_and_prefetch_match_device_path():
     b = run(hc2, hp2)
     c = run(hc, hp)
     for got, ref in zip(a, plain):
-        assert rel_err(got, ref) < 1e-6
+        assert rel_err(got, ref) < 1e-5
     for got, ref in zip(b, swapped):
-        assert rel_err(got, ref) < 1e-6
+        assert rel_err(got, ref) < 1e-5
     for got, ref in zip(c, plain):
-        assert rel_err(got, ref) < 1e-6
+        assert rel_err(got, ref) < 1e-5
