@@ -18,7 +18,7 @@ DFM_CONV_AUTO, DFM_CONV_SIMT, DFM_CONV_TC = 0, 1, 2
 DFM_OUT_COST, DFM_OUT_STEREO, DFM_OUT_MONO = 1, 2, 4
 DFM_LAYOUT_NCDHW, DFM_LAYOUT_DHWC = 0, 1
 
-# every symbol include/dfm_b200.h declares (tests/test_capi_symbols.py checks the
+# every symbol include/dfm_b200.h declares (tests/test_host_logic.py checks the
 # header against this list and against the built library)
 SYMBOLS = (
     'dfm_last_error', 'dfm_version', 'dfm_device_info', 'dfm_launch_counters',
