@@ -1,27 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- frames/s of the DfM plane-sweep cost-volume path (BASELINE.json metric).
 
-A step = one pass of the hot path (DfMBackbone: warp + volume + 3-D aggregation +
-gate, then DepthHead) over one synthetic KITTI-shape pair: 370x1224 padded to
-384x1248, D=112 planes (BASELINE.json configs[1]).
+  python bench.py --gpus N --steps K --warmup W            # the CUDA path (default workload)
+  python bench.py --impl reference ...                     # the reference's own CPU path
+  python bench.py --workload waymo_mv | waymo_10sweep      # BASELINE.json configs[3] / [4]
 
-  python bench.py --gpus N --steps K --warmup W          # the CUDA path
-  python bench.py --impl reference ...                   # the reference's CPU path
+Workloads (one "step" = one pass of the hot path over one synthetic input):
+  kitti          BASELINE.json configs[1]: one KITTI-shape pair, 370x1224 padded to 384x1248,
+                 D=112 planes: DfMBackbone (warp + volume + 3-D aggregation + gate) + DepthHead
+  waymo_mv       configs[3]: 5 views x [64,208,312] features -> lifting -> OutdoorImVoxelNeck
+  waymo_10sweep  configs[4]: 2 frames x 5 views (the shipped 10-sweep config selects ONE
+                 reference frame) -> lifting (concat) -> DfMNeck
 
-N > 1 is launched by torchrun, one rank per GPU: the pairs are sharded over ranks
-(independent frames; the reference cannot batch, dfm_backbone.py:160), no data-path
-collective, "scaling": "weak".
+N > 1 is launched by torchrun, one rank per GPU: frames / samples are sharded over ranks
+(independent; the reference cannot batch, dfm_backbone.py:160), no data-path collective,
+"scaling": "weak" -- N replicas of the single-GPU path, not a partition of one frame.
 
 One JSON line on stdout (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel (tcgen05 3x3x3 conv, 32->32 full resolution): algorithmic
-                FLOPs per launch / mean launch duration (CUDA events inside the timed
-                region, on the launching stream) against the measured bf16 peak
-  cpu_baseline  the oracle (PyTorch-CPU port of the reference) timed on this host
-  e2e           same metric through the C-ABI host-buffer entry point, pinned host
-                buffers, H2D + D2H copies inside the timed region
+  roofline            dominant kernel: algorithmic FLOPs (bytes) per launch / mean launch duration
+                      (CUDA events inside the timed region, on the launching stream) vs the
+                      measured peak in MEASURED_PEAKS.json
+  cpu_baseline        the oracle (PyTorch-CPU port of the reference) on this host's cores
+  gpu_eager_baseline  the same reference ops in PyTorch/cuDNN eager on this GPU, TF32 off / on
+                      (protocol of tools/analysis_tools/benchmark.py:66-91: 5 warm-up frames)
+  e2e                 same metric through the host-buffer C-ABI entry point a deployment
+                      calls (pinned host inputs in, pinned host outputs out, H2D + D2H inside
+                      the timed region)
 """
 import argparse
-import copy
 import json
 import os
 import statistics
@@ -39,8 +45,18 @@ ORI_SHAPE = (370, 1224, 3)
 V = D * HO * WO
 FLOPS_PER_FRAME = 521856.0 * V
 IO_BYTES_PER_FRAME = 2 * 32 * H * W * 4 + 5.25e6 + 33 * V * 4
-WORKLOAD = 'dfm_r34_1x8_kitti-3d-3class D=112 384x1248 batch=1'
-NCU_DOMINANT_TRAFFIC_BYTES = 973.3e6   # 587.2 MB read + 386.1 MB written, profiles/r01_ncu_conv_tc.csv
+KITTI_WORKLOAD = 'dfm_r34_1x8_kitti-3d-3class D=112 384x1248 batch=1'
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the
+# committed `ncu --set full` capture (profiles/): kitti: conv_tc 32->32 full resolution
+NCU_TRAFFIC = {'kitti': (973.3e6, 'profiles/r01_ncu_conv_tc.csv')}
+WAYMO = {
+    'waymo_mv': dict(T=1, agg='mean', neck='OutdoorImVoxelNeck', flops=3.212e12,
+                     name='multiview-dfm_r101_dcn_2x16_waymoD5 (5 views, 832x1248 input) '
+                          'lifting + OutdoorImVoxelNeck, 1 sample'),
+    'waymo_10sweep': dict(T=2, agg='concat', neck='DfMNeck', flops=7.649e12,
+                          name='multiview-dfm_r101_dcn 10sweeps config (2 frames x 5 views) '
+                               'lifting(concat) + DfMNeck, 1 sample'),
+}
 
 
 def peaks():
@@ -90,63 +106,138 @@ class ClockSampler:
                     samples=len(rows), reasons=reasons)
 
 
-def oracle_frame_seconds(planes, threads, repeats=1):
-    """Time of one reference-path frame (backbone + depth head) on the host cores."""
+# ------------------------------------------------------------------------------------
+# the reference's own path (oracle port), on the host cores or in eager mode on the GPU
+# ------------------------------------------------------------------------------------
+def _oracle_kitti_frame(device, seed=0):
+    """A closure running one whole reference frame (DfMBackbone.forward + DepthHead.forward,
+    dfm_backbone.py:143-214, depth_head.py:190-212) on `device`."""
     import torch
 
     from depth_from_motion_b200 import synthetic as syn
     from oracle import dfm_oracle as O
-    torch.set_num_threads(threads)
-    cur, prev, metas, params = syn.make_kitti_pair(0, H, W, planes, ori_shape=ORI_SHAPE)
-    cfg = syn.depth_cfg_for(planes)
-    ts = []
-    with torch.no_grad():
-        for _ in range(repeats):
-            t0 = time.perf_counter()
+    cur, prev, metas, params = syn.make_kitti_pair(seed, H, W, D, ori_shape=ORI_SHAPE)
+    cfg = syn.depth_cfg_for(D)
+    cur, prev = cur.to(device), prev.to(device)
+    params = {k: v.to(device) for k, v in params.items()}
+    samples = O.depth_samples(cfg).to(device)
+
+    def frame():
+        with torch.no_grad():
             cost, _, _ = O.dfm_backbone_forward(params, cur, prev, metas, cfg)
-            O.depth_head_forward(cost, O.depth_samples(cfg))
-            ts.append(time.perf_counter() - t0)
-    return statistics.median(ts)
+            return O.depth_head_forward(cost, samples)[2]
+    return frame
+
+
+def _oracle_waymo_sample(device, wl, seed=0):
+    import numpy as np
+    import torch
+
+    from depth_from_motion_b200 import modules
+    from depth_from_motion_b200 import synthetic as syn
+    from oracle import dfm_oracle as O
+    spec = WAYMO[wl]
+    t, nv = spec['T'], 5
+    feats, meta = syn.make_waymo_sample(seed, t, nv)
+    rng = np.random.RandomState(seed + 1)
+    mod = (modules.DfMNeck(64, 256, num_frames=2) if spec['neck'] == 'DfMNeck'
+           else modules.OutdoorImVoxelNeck(64, 256))
+    sd = {k: v.to(device) for k, v in syn.make_neck_params(rng, mod.state_dict()).items()}
+    xs, ys, zs = modules.aligned_voxel_centers(syn.WAYMO_N_VOXELS, syn.WAYMO_RANGE)
+    zz, yy, xx = torch.meshgrid(zs, ys, xs, indexing='ij')
+    pts = torch.stack([xx, yy, zz], -1).reshape(-1, 3).to(device)
+    l2i = [torch.tensor(m, dtype=torch.float32, device=device) for m in meta['ori_lidar2img']]
+    feats = feats.to(device)
+    sf = pts.new_tensor(meta['scale_factor'][:2])
+    crop = pts.new_tensor(meta['img_crop_offset'])
+
+    def sample():
+        with torch.no_grad():
+            vol = O.multiview_lift(feats, pts, syn.WAYMO_N_VOXELS, l2i, nv, t, sf, crop, False,
+                                   meta['input_shape'], meta['img_shape'], spec['agg'])[None]
+            if spec['neck'] == 'DfMNeck':
+                return O.dfm_neck_forward(sd, vol, 64)[0]
+            return O.imvoxel_neck_forward(sd, vol)[0]
+    return sample
+
+
+def _reference_step(workload, device):
+    return _oracle_kitti_frame(device) if workload == 'kitti' else \
+        _oracle_waymo_sample(device, workload)
 
 
 def run_reference(args):
-    """--impl reference: the reference's own PyTorch CPU path (oracle port; the
-    reference has no native code to compile) on the host cores."""
+    """--impl reference: the reference's own PyTorch path on the host cores (the oracle port:
+    the reference has no native code to compile and mmcv is not installable here, DESIGN.md
+    section 6).  Every step is ONE WHOLE unit of the stated workload -- no extrapolation."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    import torch
     cores = os.cpu_count() or 1
-    slab = 16
-    t_full = oracle_frame_seconds(D, cores)           # one whole D=112 frame
-    t_slab0 = oracle_frame_seconds(slab, cores)       # also warms the slab path
-    ratio = t_full / t_slab0
-    for _ in range(max(args.warmup - 1, 0)):
-        oracle_frame_seconds(slab, cores)
-    t0 = time.perf_counter()
+    torch.set_num_threads(cores)
+    step = _reference_step(args.workload, 'cpu')
+    for _ in range(args.warmup):
+        step()
+    ts = []
     for _ in range(args.steps):
-        oracle_frame_seconds(slab, cores)
-    per_step = (time.perf_counter() - t0) / args.steps
-    fps = 1.0 / (per_step * ratio)
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    per_step = sum(ts) / len(ts)
+    fps = 1.0 / per_step
+    name = KITTI_WORKLOAD if args.workload == 'kitti' else WAYMO[args.workload]['name']
     line = dict(
         impl='reference', metric='frames/sec', value=fps, unit='frames/s', n_gpus=args.gpus,
-        steps=args.steps, warmup=args.warmup, ms_per_step=per_step * ratio * 1e3,
+        steps=args.steps, warmup=args.warmup, ms_per_step=per_step * 1e3,
         higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-        data='synthetic', config=dict(workload=WORKLOAD),
+        data='synthetic', config=dict(workload=name),
         cpu_baseline=dict(value=fps, unit='frames/s', cores=cores, kind='port',
-                          sample=f'each step = the same pair at D={slab} planes '
-                                 f'({per_step:.2f} s), scaled by the measured full-frame/'
-                                 f'slab time ratio {ratio:.2f} (one D=112 frame: {t_full:.1f} s)'),
+                          sample=f'every step is one whole unit of this workload through the '
+                                 f'oracle (PyTorch-CPU restatement of the reference path); '
+                                 f'{args.warmup} warm-up + {args.steps} timed, '
+                                 f'median {statistics.median(ts):.2f} s, '
+                                 f'min {min(ts):.2f} s, max {max(ts):.2f} s'),
         e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
+def gpu_eager_baseline(workload, nwarm=5, nrep=10):
+    """The reference modules' own op sequence in PyTorch/cuDNN eager mode on this GPU (the
+    same-box bar of SURVEY.md section 2.2 / 8d), cuDNN TF32 off (true fp32) and on (torch's
+    default, what the reference's authors ran), tools/analysis_tools/benchmark.py:66-91."""
+    import torch
+    out = {}
+    step = _reference_step(workload, 'cuda')
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for key, tf32 in (('tf32_off', False), ('tf32_on', True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(nwarm):
+                step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(nrep):
+                step()
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) / nrep * 1e3
+            out[key] = dict(ms_per_frame=round(ms, 3), frames_per_s=round(1e3 / ms, 2))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    out['what'] = ('oracle/dfm_oracle.py (the reference ops, same order) on cuda tensors, '
+                   f'{nwarm} warm-up + {nrep} timed frames, torch {torch.__version__}, cuDNN '
+                   f'{torch.backends.cudnn.version()}')
+    del step
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------
+# the CUDA path
+# ------------------------------------------------------------------------------------
+def _setup_dist():
     import torch
     import torch.distributed as dist
-
-    from depth_from_motion_b200 import capi, modules
-    from depth_from_motion_b200 import synthetic as syn
-
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -154,31 +245,18 @@ def run_ours(args):
         raise SystemExit('bench.py needs a B200: there is no CPU path (use --impl reference)')
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = 'WARN'  # keep NCCL's version banner off stdout (one JSON line)
+        # NCCL's INFO lines (if the caller set NCCL_DEBUG) must not interleave with the one
+        # JSON line on stdout: send them to stderr's file unless the caller chose a file
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    capi.lib()
+    return rank, world, local
 
-    # two different pairs per rank so consecutive steps never re-read the same inputs;
-    # the per-step working set (~7 GB of activations) is far larger than the 126 MB L2
-    pairs = []
-    for i in range(2):
-        cur, prev, metas, params = syn.make_kitti_pair(100 + 2 * rank + i, H, W, D,
-                                                       ori_shape=ORI_SHAPE)
-        pairs.append((cur.cuda(), prev.cuda(), metas, cur.pin_memory(), prev.pin_memory()))
-    cfg = syn.depth_cfg_for(D)
-    model = modules.DfMBackbone(in_channels=C, depth_cfg=cfg).cuda().eval()
-    model.load_state_dict(params, strict=True)
-    model.downsampled_depth = _depths(cfg, 4)
-    head = modules.DepthHead(
-        depth_cfg=dict(mode='UD', num_bins=cfg['num_bins'], min_depth=2, max_depth=59.6),
-        with_convs=False, num_views=1, depth_loss=dict(type='ce', loss_weight=1.0))
-    head.depth_samples = _depths(cfg, 1)
-    head.downsample_factor = 4
 
-    def step(i):
-        cur, prev, metas, _, _ = pairs[i % 2]
-        cost, stereo, mono = model(cur, prev, metas)
-        return head(cost)
+def _timed_loop(step, args, world, rank, local, capi):
+    """W warm-up steps, then exactly K timed steps between barrier + synchronize on both
+    sides, CUDA events on the launching stream, clocks sampled during the timed region."""
+    import torch
+    import torch.distributed as dist
 
     def barrier():
         if world > 1:
@@ -209,77 +287,103 @@ def run_ours(args):
         l1, tc1 = capi.launch_counters()
         capi.sync_check()
     from depth_from_motion_b200.sharding import reduce_step_time
-    ms_total = reduce_step_time(ms, 'cuda')
+    return reduce_step_time(ms, 'cuda'), prof, clocks, l1 - l0, tc1 - tc0, barrier
+
+
+def _kernel_table(prof, steps):
+    return {k: dict(launches=v['launches'] // steps, ms=round(v['ms'] / steps, 4),
+                    tflops=round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 1))
+            for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])}
+
+
+def run_kitti(args):
+    import torch
+    import torch.distributed as dist
+
+    from depth_from_motion_b200 import capi, modules
+    from depth_from_motion_b200 import synthetic as syn
+    from depth_from_motion_b200.sharding import reduce_step_time
+
+    rank, world, local = _setup_dist()
+    capi.lib()
+
+    # two different pairs per rank so consecutive steps never re-read the same inputs;
+    # the per-step working set (~7 GB of activations) is far larger than the 126 MB L2
+    pairs = []
+    for i in range(2):
+        cur, prev, metas, params = syn.make_kitti_pair(100 + 2 * rank + i, H, W, D,
+                                                       ori_shape=ORI_SHAPE)
+        metas[0]['cam2img'] = syn.KITTI_P2.astype('float32').tolist()
+        pairs.append((cur.cuda(), prev.cuda(), metas, cur.pin_memory(), prev.pin_memory()))
+    cfg = syn.depth_cfg_for(D)
+    model = modules.DfMBackbone(in_channels=C, depth_cfg=cfg).cuda().eval()
+    model.load_state_dict(params, strict=True)
+    model.downsampled_depth = _depths(cfg, 4)
+    head = modules.DepthHead(
+        depth_cfg=dict(mode='UD', num_bins=cfg['num_bins'], min_depth=2, max_depth=59.6),
+        with_convs=False, num_views=1, depth_loss=dict(type='ce', loss_weight=1.0))
+    head.depth_samples = _depths(cfg, 1)
+    head.downsample_factor = 4
+
+    def step(i):
+        cur, prev, metas, _, _ = pairs[i % 2]
+        cost, stereo, mono = model(cur, prev, metas)
+        return head(cost)
+
+    ms_total, prof, clocks, launches, tc_launches, barrier = _timed_loop(
+        step, args, world, rank, local, capi)
     fps = world * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
-    import ctypes
-    L = capi.lib()
-    h_cost = torch.empty((1, 1, D, HO, WO)).pin_memory()
-    h_pred = torch.empty((1, 1, H, W)).pin_memory()
-    d_pred = torch.empty((1, 1, H, W), device='cuda')
-    samples_dev = head.depth_samples.cuda()
-
-    def prefetch(i):
-        _, _, _, hc, hp = pairs[i % 2]
-        capi.check(L.dfm_backbone_prefetch_host(
-            model._handle, ctypes.c_void_p(hc.data_ptr()), ctypes.c_void_p(hp.data_ptr())),
-            'dfm_backbone_prefetch_host')
-
-    use_prefetch = [True]
+    # ---- e2e: DfM.simple_test's hot-path segment through the host-buffer C-ABI call -------
+    # pinned host (cur, prev, sem) in -> voxel features + depth_preds out (what the BEV stage
+    # consumes, detectors/dfm.py:416-429); every step copies one pair H2D (the NEXT pair, on a
+    # side stream, overlapped with this step's compute) and its outputs D2H, all inside the
+    # timed region
+    fc = syn.make_frustum_case(7 + rank, H, W, D, (288, 304, 20))
+    frustum = modules.FrustumToVoxel().eval()
+    frustum.load_state_dict(fc['params'], strict=True)
+    frustum = frustum.cuda()
+    frustum.coordinates_3d = fc['coordinates_3d']
+    frustum.depth_cfg = cfg
+    h_sem = fc['sem'].contiguous().pin_memory()
+    pipe = modules.HotPathPipeline(model, head, frustum)
+    del fc
+    use_prefetch = [False]
 
     def e2e_step(i):
         _, _, metas, hc, hp = pairs[i % 2]
-        g = modules.geometry_from_meta(metas[0])
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        # every step starts the host->device copy of the NEXT step's pair (side stream), then
-        # processes its own pair, whose copy was started one step earlier: one pair copied per
-        # step, inside the timed region, overlapped with compute
         if use_prefetch[0]:
-            prefetch(i + 1)
-        capi.check(L.dfm_backbone_forward_host(
-            model._handle, ctypes.c_void_p(hc.data_ptr()), ctypes.c_void_p(hp.data_ptr()),
-            ctypes.byref(g), capi.DFM_OUT_COST, ctypes.c_void_p(h_cost.data_ptr()), None, None,
-            stream), 'dfm_backbone_forward_host')
-        capi.check(L.dfm_depth_head_forward(
-            L.dfm_backbone_cost_device(model._handle), ctypes.c_void_p(samples_dev.data_ptr()),
-            D, HO, WO, 4, None, None, ctypes.c_void_p(d_pred.data_ptr()), stream),
-            'dfm_depth_head_forward')
-        h_pred.copy_(d_pred, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+            nxt = pairs[(i + 1) % 2]
+            pipe.prefetch(nxt[3], nxt[4])
+        return pipe(hc, hp, h_sem, metas)
 
-    # self-check of the prefetched path against the plain call (same CUDA kernels either way);
-    # on any disagreement the e2e loop copies synchronously inside forward_host instead
-    use_prefetch[0] = False
-    e2e_step(0)
-    ref_cost = h_cost.clone()
+    # self-check of the prefetched path against the plain call (same CUDA kernels either way)
+    ref_vox = e2e_step(0)[0].clone()
     try:
-        prefetch(0)
+        pipe.prefetch(pairs[0][3], pairs[0][4])
         use_prefetch[0] = True
-        e2e_step(0)
-        if not torch.allclose(h_cost, ref_cost, rtol=1e-5, atol=1e-6):
+        if not torch.allclose(e2e_step(0)[0], ref_vox, rtol=1e-5, atol=1e-6):
             raise RuntimeError('prefetched result differs')
     except RuntimeError as exc:
         print(f'[bench] prefetch path disabled: {exc}', file=sys.stderr)
         use_prefetch[0] = False
-    if use_prefetch[0]:
-        prefetch(0)
     nwarm = min(args.warmup, 3)
-    for i in range(nwarm):
+    for i in range(1, 1 + nwarm):
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record()
-    for i in range(nwarm, nwarm + args.steps):  # step indices continue: pair i was prefetched
+    for i in range(1 + nwarm, 1 + nwarm + args.steps):
         e2e_step(i)
     ee1.record()
     barrier()
     e2e_ms = reduce_step_time(max(ee0.elapsed_time(ee1), (time.perf_counter() - t0) * 1e3),
                               'cuda')
     e2e_fps = world * args.steps / (e2e_ms * 1e-3)
-    h2d = 2 * C * H * W * 4
-    d2h = (D * HO * WO + H * W) * 4
+    vox_out, pred_out = pipe._out
+    h2d = 2 * C * H * W * 4 + h_sem.numel() * 4 + D * 4 * 4
+    d2h = (vox_out.numel() + pred_out.numel()) * 4
 
     if rank != 0:
         if world > 1:
@@ -287,7 +391,6 @@ def run_ours(args):
         return
 
     pk = peaks()
-    # dominant kernel: the full-resolution 32->32 tensor-core conv
     dom_key = f'conv_tc<32->32,s1,src>@{D}x{HO}x{WO}'
     roof = None
     tc_ms = sum(v['ms'] for k, v in prof.items() if k.startswith('conv_tc'))
@@ -299,10 +402,8 @@ def run_ours(args):
         ach = per_launch_flops / per_launch_s / 1e12
         roof = dict(bound='tensor', kernel=dom_key, achieved=round(ach, 2), peak=pk['bf16'],
                     unit='TFLOP/s', frac=round(ach / pk['bf16'], 4),
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch,
-                    # from the committed ncu --set full capture (profiles/r01_ncu_conv_tc.csv);
-                    # algorithmic bytes: 429.4 MB in + 429.4 MB out
-                    traffic=NCU_DOMINANT_TRAFFIC_BYTES,
+                    traffic=NCU_TRAFFIC['kitti'][0], traffic_source=NCU_TRAFFIC['kitti'][1],
+                    algorithmic_bytes=2 * V * 32 * 4,
                     executed_bf16_tflops=round(3 * ach, 1),
                     executed_frac_of_peak=round(3 * ach / pk['bf16'], 4),
                     peak_source=pk['src'] + ' bf16 dense (sustained)',
@@ -320,42 +421,184 @@ def run_ours(args):
             roof = dict(bound='tensor', kernel=k, achieved=round(ach, 2), peak=pk['bf16'],
                         unit='TFLOP/s', frac=round(ach / pk['bf16'], 4), traffic=None,
                         peak_source=pk['src'])
+    # HBM-bound kernels of the step against the measured copy bandwidth (algorithmic bytes)
+    hbm_rows = {}
+    alg = {'depth_head': 2 * (4 * D) * H * W * 4 + V * 4,
+           'cout1_logits': V * 32 * 4 + V * 4,
+           'gate': 3 * V * 4}
+    for key, nbytes in alg.items():
+        rows = [v for k, v in prof.items() if k == key or k.startswith(key)]
+        if rows:
+            ms = sum(v['ms'] for v in rows) / args.steps
+            if key == 'cout1_logits':   # stereo (D planes) + shortened mono tower (40 planes)
+                nbytes = nbytes * (1 + 40.0 / D)
+            hbm_rows[key] = dict(ms=round(ms, 4), algorithmic_gb=round(nbytes / 1e9, 3),
+                                 gbs=round(nbytes / ms / 1e6, 1),
+                                 frac_of_hbm_peak=round(nbytes / ms / 1e6 / pk['hbm'], 3))
     cores = os.cpu_count() or 1
-    cpu = None
+    cpu = eager = None
     if world == 1 and not args.no_cpu_baseline:
-        t_cpu = oracle_frame_seconds(D, cores)
+        import torch as _t
+        _t.set_num_threads(cores)
+        frame = _oracle_kitti_frame('cpu')
+        frame()                                   # warm-up (thread pool, allocator)
+        t0 = time.perf_counter()
+        frame()
+        t_cpu = time.perf_counter() - t0
         cpu = dict(value=1.0 / t_cpu, unit='frames/s', cores=cores, kind='port',
                    sample=f'one whole frame of this workload (D={D}, {H}x{W}) through the '
-                          f'oracle (PyTorch-CPU restatement of the reference path), '
-                          f'{t_cpu:.1f} s')
+                          f'oracle (PyTorch-CPU restatement of the reference path) after one '
+                          f'warm-up frame, {t_cpu:.1f} s')
+    if world == 1 and not args.no_gpu_eager:
+        eager = gpu_eager_baseline('kitti')
     line = dict(
         metric='frames/sec', value=fps, unit='frames/s', n_gpus=world, steps=args.steps,
         warmup=args.warmup, ms_per_step=ms_total / args.steps, higher_is_better=True,
         scaling='weak', vs_baseline=None, dtype='f32 (bf16x2 split operands, fp32 accumulate)',
         data='synthetic',
-        config=dict(workload=WORKLOAD, pairs_per_step=world, planes=D, feature_hw=[H, W],
+        config=dict(workload=KITTI_WORKLOAD, pairs_per_step=world, planes=D, feature_hw=[H, W],
                     l2='per-step working set ~7 GB >> 126 MB L2; two input pairs alternate',
+                    multi_gpu='replicas: one independent pair per rank, no data-path collective',
                     outputs='cost + stereo_feat + mono_feat + DepthHead(volume, softmax, preds)'),
         clocks=clocks,
+        comm=dict(backend='nccl' if world > 1 else None, world_size=world,
+                  collective='all_reduce(MAX) of the step time only'),
         e2e=dict(value=e2e_fps, unit='frames/s', h2d_bytes_per_step=h2d,
-                 d2h_bytes_per_step=d2h,
-                 prefetch=use_prefetch[0],
-                 what='dfm_backbone_prefetch_host(next pair) + dfm_backbone_forward_host (pinned '
-                      'host features in, logits out) + dfm_depth_head_forward '
-                      '(depth_preds out); stereo_feat stays on device for the next stage'),
-        gpu_launches=l1 - l0, tc_launches=tc1 - tc0,
-        roofline=roof,
+                 d2h_bytes_per_step=d2h, prefetch=use_prefetch[0],
+                 ms_per_step=round(e2e_ms / args.steps, 4),
+                 what='dfm_pipeline_forward_host: pinned host cur/prev stereo features + sem '
+                      'features in -> DfMBackbone -> DepthHead reduction -> FrustumToVoxel -> '
+                      'pinned host voxel features [1,32,5,304,288] + depth_preds [1,1,384,1248] '
+                      'out (what DfM.simple_test hands to the BEV stage, detectors/dfm.py:'
+                      '416-429); the next pair is prefetched on a side stream'),
+        gpu_launches=launches, tc_launches=tc_launches,
+        roofline=roof, hbm_kernels=hbm_rows,
         tensor=dict(achieved_tflops=round(FLOPS_PER_FRAME * fps / world / 1e12, 2),
                     frac_of_bf16_peak=round(FLOPS_PER_FRAME * fps / world / 1e12 / pk['bf16'], 4)),
         hbm=dict(compulsory_gbs=round(IO_BYTES_PER_FRAME * fps / world / 1e9, 1),
                  frac_of_peak=round(IO_BYTES_PER_FRAME * fps / world / 1e9 / pk['hbm'], 4)),
         conv_ms_per_step=round(conv_ms / args.steps, 3),
         tc_conv_ms_per_step=round(tc_ms / args.steps, 3),
-        kernels={k: dict(launches=v['launches'] // args.steps,
-                         ms=round(v['ms'] / args.steps, 4),
-                         tflops=round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 1))
-                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])},
-        cpu_baseline=cpu)
+        kernels=_kernel_table(prof, args.steps),
+        cpu_baseline=cpu, gpu_eager_baseline=eager)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_waymo(args):
+    """BASELINE.json configs[3] / [4]: per sample, MultiViewDfM.feature_transformation =
+    multi-view lifting (multiview_dfm.py:119-209) + neck_3d (imvoxel_neck.py / dfm_neck.py)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from depth_from_motion_b200 import capi, modules
+    from depth_from_motion_b200 import synthetic as syn
+    from depth_from_motion_b200.sharding import reduce_step_time
+
+    rank, world, local = _setup_dist()
+    capi.lib()
+    spec = WAYMO[args.workload]
+    t, nv = spec['T'], 5
+    samples = []
+    for i in range(2):
+        feats, meta = syn.make_waymo_sample(200 + 2 * rank + i, t, nv)
+        samples.append((feats.cuda(), meta, feats.pin_memory()))
+    rng = np.random.RandomState(5)
+    neck = (modules.DfMNeck(64, 256, num_frames=2) if spec['neck'] == 'DfMNeck'
+            else modules.OutdoorImVoxelNeck(64, 256))
+    neck.load_state_dict(syn.make_neck_params(rng, neck.state_dict()), strict=True)
+    neck = neck.cuda().eval()
+
+    class Host(modules.MultiViewDfMFeatureTransformation):
+        n_voxels, voxel_range = syn.WAYMO_N_VOXELS, syn.WAYMO_RANGE
+        temporal_aggregate, valid_sample, neck_3d = spec['agg'], True, neck
+    host = Host()
+
+    def step(i):
+        feats, meta, _ = samples[i % 2]
+        return host.feature_transformation(feats[None], [meta], nv, t)[0]
+
+    ms_total, prof, clocks, launches, tc_launches, barrier = _timed_loop(
+        step, args, world, rank, local, capi)
+    sps = world * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: pinned host features in, pinned host BEV out --------------------------------
+    h_bev = torch.empty((1, 256, 300, 220)).pin_memory()
+    d_in = torch.empty_like(samples[0][0])
+
+    def e2e_step(i):
+        _, meta, hf = samples[i % 2]
+        d_in.copy_(hf, non_blocking=True)
+        bev = host.feature_transformation(d_in[None], [meta], nv, t)[0]
+        h_bev.copy_(bev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    with torch.no_grad():
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(3, 3 + args.steps):
+            e2e_step(i)
+        barrier()
+        e2e_ms = reduce_step_time((time.perf_counter() - t0) * 1e3, 'cuda')
+    e2e_sps = world * args.steps / (e2e_ms * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    neck_ms = sum(v['ms'] for k, v in prof.items() if k.startswith('conv_')) / args.steps
+    lift_ms = sum(v['ms'] for k, v in prof.items() if k.startswith('lift')) / args.steps
+    in_bytes = samples[0][0].numel() * 4
+    out_bytes = 64 * (t if spec['agg'] == 'concat' else 1) * 220 * 300 * 12 * 4
+    ach = spec['flops'] / (neck_ms * 1e-3) / 1e12 if neck_ms else 0.0
+    roof = dict(bound='tensor', kernel=f'conv_tc_neck (all 9/18 conv layers of {spec["neck"]})',
+                achieved=round(ach, 2), peak=pk['bf16'], unit='TFLOP/s',
+                frac=round(ach / pk['bf16'], 4), traffic=None,
+                executed_bf16_tflops=round(3 * ach, 1),
+                peak_source=pk['src'] + ' bf16 dense (sustained)',
+                ms_per_step=round(neck_ms, 3), share_of_step=round(neck_ms * args.steps / ms_total, 4),
+                note='algorithmic fp32 conv FLOPs of the neck (SURVEY.md 8d) / summed conv time')
+    roof_lift = dict(bound='hbm', kernel='lift (NCHW->NHWC staging + lift_voxel_kernel)',
+                     achieved=round((in_bytes + out_bytes) / (lift_ms * 1e-3) / 1e9, 1) if lift_ms else None,
+                     peak=pk['hbm'], unit='GB/s',
+                     frac=round((in_bytes + out_bytes) / (lift_ms * 1e-3) / 1e9 / pk['hbm'], 4) if lift_ms else None,
+                     algorithmic_bytes=in_bytes + out_bytes, ms_per_step=round(lift_ms, 4))
+    cores = os.cpu_count() or 1
+    cpu = eager = None
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(cores)
+        fn = _oracle_waymo_sample('cpu', args.workload)
+        t0 = time.perf_counter()
+        fn()
+        t_cpu = time.perf_counter() - t0
+        cpu = dict(value=1.0 / t_cpu, unit='frames/s', cores=cores, kind='port',
+                   sample=f'one whole sample of this workload through the oracle, {t_cpu:.1f} s')
+    if world == 1 and not args.no_gpu_eager:
+        eager = gpu_eager_baseline(args.workload, nwarm=2, nrep=3)
+    line = dict(
+        metric='frames/sec', value=sps, unit='frames/s', n_gpus=world, steps=args.steps,
+        warmup=args.warmup, ms_per_step=ms_total / args.steps, higher_is_better=True,
+        scaling='weak', vs_baseline=None, dtype='f32 (bf16x2 split operands, fp32 accumulate)',
+        data='synthetic',
+        config=dict(workload=spec['name'], samples_per_step=world, frames=t, views=nv,
+                    n_voxels=syn.WAYMO_N_VOXELS, frame_unit='one multi-view sample',
+                    l2='volume 0.2-0.4 GB and 0.4-1.5 GB of activations per layer >> 126 MB L2; '
+                       'two input samples alternate',
+                    multi_gpu='replicas: one independent sample per rank'),
+        clocks=clocks,
+        comm=dict(backend='nccl' if world > 1 else None, world_size=world,
+                  collective='all_reduce(MAX) of the step time only'),
+        e2e=dict(value=e2e_sps, unit='frames/s', h2d_bytes_per_step=in_bytes,
+                 d2h_bytes_per_step=h_bev.numel() * 4, ms_per_step=round(e2e_ms / args.steps, 3),
+                 what='pinned host FPN features [T*5,64,208,312] -> H2D -> '
+                      'MultiViewDfM.feature_transformation (lifting + neck_3d) -> BEV '
+                      '[1,256,300,220] D2H to pinned host memory'),
+        gpu_launches=launches, tc_launches=tc_launches, roofline=roof, roofline_lift=roof_lift,
+        kernels=_kernel_table(prof, args.steps), cpu_baseline=cpu, gpu_eager_baseline=eager)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -377,13 +620,17 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='kitti', choices=['kitti'] + sorted(WAYMO))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gpu-eager', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'kitti':
+        run_kitti(args)
     else:
-        run_ours(args)
+        run_waymo(args)
 
 
 if __name__ == '__main__':

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('DFM_B200_LIB') or os.path.join(_HERE, 'libdfm_b200.so')
 
 DFM_OK = 0
-DFM_CONV_AUTO, DFM_CONV_SIMT, DFM_CONV_TC = 0, 1, 2
+DFM_CONV_AUTO, DFM_CONV_SIMT, DFM_CONV_TC, DFM_CONV_TC_NECK = 0, 1, 2, 3
 DFM_OUT_COST, DFM_OUT_STEREO, DFM_OUT_MONO = 1, 2, 4
 DFM_LAYOUT_NCDHW, DFM_LAYOUT_DHWC = 0, 1
 
@@ -34,6 +34,7 @@ SYMBOLS = (
     'dfm_neck_destroy', 'dfm_neck_set_param', 'dfm_neck_missing_params',
     'dfm_neck_forward', 'dfm_frustum_create', 'dfm_frustum_destroy',
     'dfm_frustum_set_param', 'dfm_frustum_missing_params', 'dfm_frustum_forward',
+    'dfm_pipeline_forward_host',
 )
 
 
@@ -145,6 +146,9 @@ def lib():
     L.dfm_frustum_missing_params.argtypes = [vp]
     L.dfm_frustum_forward.argtypes = [vp, vp, c_int, vp, vp, vp, vp, vp,
                                       POINTER(c_double), c_int, c_int, vp, vp]
+    L.dfm_pipeline_forward_host.argtypes = [vp, vp, vp, vp, vp, POINTER(Geometry),
+                                            POINTER(c_double), c_int, c_int, vp, vp, vp,
+                                            vp, vp]
     _lib = L
     return L
 

@@ -8,6 +8,20 @@
 
 namespace dfm {
 
+// Scratch / caches that outlive a call are kept per CUDA device (one process may drive
+// several GPUs; the library as a whole is still not re-entrant, see include/dfm_b200.h).
+constexpr int kMaxDevices = 64;
+inline int cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+template <class T, int TAG = 0>
+inline T& per_device() {
+  static T slots[kMaxDevices];
+  return slots[cur_device()];
+}
+
 // One additive term of a layer input, read from a channels-last fp32 tensor
 // [D][H][W][C]:  term(c) = act(x * scale[c] + shift[c]).  scale == nullptr means the
 // identity affine.  This is how GroupNorm / BatchNorm + ReLU + residual adds of the

@@ -335,7 +335,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
         : "memory");
     if (ok) return;
   }
-  atomicExch(err, 1);
+  // err is mapped host memory (TcErrFlag)
+  *reinterpret_cast<volatile int*>(err) = 1;
+  __threadfence_system();
 }
 __device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, int* err,
                                                 unsigned long long& acc, bool timed) {
@@ -1257,12 +1259,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // ----------------------------------------------------------------------------------
 // host launch
 // ----------------------------------------------------------------------------------
+// Error flag of the tensor-core kernels: page-locked host memory mapped into every device's
+// address space (portable), written by a kernel whose mbarrier wait timed out and read by the
+// host without any synchronisation, so every entry point can poll it for free.
 struct TcErrFlag {
+  int* host = nullptr;
   int* dev = nullptr;
   int* get() {
-    if (!dev) {
-      cudaMalloc(&dev, sizeof(int));
-      cudaMemset(dev, 0, sizeof(int));
+    if (!host) {
+      if (cudaHostAlloc(&host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) !=
+          cudaSuccess) {
+        host = nullptr;
+        cudaGetLastError();
+        return nullptr;
+      }
+      *host = 0;
+      cudaHostGetDevicePointer(&dev, host, 0);
     }
     return dev;
   }
@@ -1272,21 +1284,18 @@ inline TcErrFlag& tc_err_flag() {
   return f;
 }
 // returns non-zero if any tensor-core kernel timed out on a barrier since the last call
+// (kernels that have completed; callers that need the current stream's state synchronise
+// first, dfm_sync_check)
 inline int tc_consume_error() {
-  int h = 0;
-  if (tc_err_flag().dev) {
-    cudaMemcpy(&h, tc_err_flag().dev, sizeof(int), cudaMemcpyDeviceToHost);
-    if (h) cudaMemset(tc_err_flag().dev, 0, sizeof(int));
-  }
+  TcErrFlag& f = tc_err_flag();
+  if (!f.host) return 0;
+  const int h = *reinterpret_cast<volatile int*>(f.host);
+  if (h) *reinterpret_cast<volatile int*>(f.host) = 0;
   return h;
 }
 inline int tc_sm_count() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-  }
+  int& cached = per_device<int, 1>();
+  if (!cached) cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, cur_device());
   return cached;
 }
 
@@ -1342,10 +1351,7 @@ struct TcScratch {
     return p;
   }
 };
-inline TcScratch& tc_kslice_scratch() {
-  static TcScratch sc;
-  return sc;
-}
+inline TcScratch& tc_kslice_scratch() { return per_device<TcScratch>(); }
 
 struct TcOpts {
   int store1 = 0;
@@ -1363,7 +1369,9 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
   const size_t smem = w.image_bytes + M::NSTAGE * STAGE_BYTES +
                       (2 * M::NSTAGE + 2 * M::NSLOT) * 8 + 16;
   auto kern = conv_tc_kernel<MODE, CIN, NCTA, Loader>;
-  static size_t attr_smem = 0;
+  struct AttrTag { size_t v = 0; };
+  static AttrTag attr_dev[kMaxDevices];  // per kernel instantiation and device
+  size_t& attr_smem = attr_dev[cur_device()].v;
   if (smem > attr_smem) {
     if (smem > 232448 ||
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=

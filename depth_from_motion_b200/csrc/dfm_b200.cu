@@ -468,6 +468,8 @@ struct dfm_backbone {
     unsigned long long tick = 0;
   } stage[2];
   unsigned long long stage_tick = 0;
+  // grow-only device scratch of the host-buffer entry points (no cudaMalloc per call)
+  DevBuf out_st, out_mo, pipe_sem, pipe_vox, pipe_preds, pipe_samples;
   bool depths_set = false;
   std::set<std::string> missing;
   std::map<std::string, std::pair<const DevBuf*, int>> dbg;  // name -> (buffer, channels)
@@ -843,8 +845,10 @@ int dfm_backbone_create(const dfm_backbone_desc_t* desc, dfm_backbone_t** out) {
     return fail(DFM_ERR_INVALID, "only in_channels == cv_channels == 32 is implemented");
   const int csf = desc->cost_sample_factor, fsf = desc->feat_sample_factor;
   if (csf < 1 || fsf < 1) return fail(DFM_ERR_INVALID, "sample factors must be >= 1");
-  const int Ho = (int)std::lround((double)desc->feat_h / csf);
-  const int Wo = (int)std::lround((double)desc->feat_w / csf);
+  // Python's round() (dfm_backbone.py:243-244) rounds halves to even: std::nearbyint in the
+  // default rounding mode, not std::lround (half away from zero)
+  const int Ho = (int)std::nearbyint((double)desc->feat_h / csf);
+  const int Wo = (int)std::nearbyint((double)desc->feat_w / csf);
   const int D = desc->num_planes;
   if (D % 4 || Ho % 4 || Wo % 4 || D < 4 || Ho < 4 || Wo < 4)
     return fail(DFM_ERR_INVALID,
@@ -901,7 +905,8 @@ int dfm_backbone_destroy(dfm_backbone_t* bb) {
   tower_release(bb->mo);
   for (DevBuf* b : {&bb->cur_nhwc, &bb->prev_nhwc, &bb->depths, &bb->wagg, &bb->cost,
                     &bb->volume_dbg, &bb->stage[0].cur, &bb->stage[0].prev, &bb->stage[1].cur,
-                    &bb->stage[1].prev})
+                    &bb->stage[1].prev, &bb->out_st, &bb->out_mo, &bb->pipe_sem, &bb->pipe_vox,
+                    &bb->pipe_preds, &bb->pipe_samples})
     b->release();
   for (auto& hs : bb->stage)
     if (hs.ready) cudaEventDestroy(hs.ready);
@@ -962,6 +967,9 @@ int backbone_forward_impl(dfm_backbone_t* bb, const float* d_cur, const float* d
                           const dfm_geometry_t* geom, float* d_cost, float* d_stereo,
                           float* d_mono, void* stream, cudaEvent_t prev_ready) {
   if (!bb || !d_cur || !d_prev || !geom) return fail(DFM_ERR_INVALID, "null argument");
+  if (dfm::tc_consume_error())
+    return fail(DFM_ERR_CUDA, "an earlier tensor-core conv kernel timed out on an mbarrier "
+                              "hand-over: its outputs were invalid");
   if (!bb->missing.empty())
     return fail(DFM_ERR_STATE, "missing parameter: " + *bb->missing.begin() + " (+" +
                                    std::to_string(bb->missing.size() - 1) + " more)");
@@ -1031,7 +1039,7 @@ struct HostCopyCtx {
   cudaEvent_t fork = nullptr, prev_done = nullptr;
 };
 int host_copy_ctx(HostCopyCtx** out) {
-  static HostCopyCtx ctx;
+  HostCopyCtx& ctx = dfm::per_device<HostCopyCtx>();
   if (!ctx.stream) {
     CU_TRY(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&ctx.fork, cudaEventDisableTiming));
@@ -1044,6 +1052,51 @@ int stage_alloc(dfm_backbone::HostStage& hs, size_t nfeat) {
   DFM_TRY(hs.cur.alloc(nfeat));
   DFM_TRY(hs.prev.alloc(nfeat));
   if (!hs.ready) CU_TRY(cudaEventCreateWithFlags(&hs.ready, cudaEventDisableTiming));
+  return DFM_OK;
+}
+}  // namespace
+
+namespace {
+// Device copies of a host (cur, prev) pair: the staged copy of a matching
+// dfm_backbone_prefetch_host, else a fresh copy whose prev half rides the side stream
+// underneath the mono tower (*prev_ready is the event to wait for before reading d_prev).
+int stage_host_pair(dfm_backbone_t* bb, const float* h_cur, const float* h_prev, cudaStream_t st,
+                    float** d_cur_out, float** d_prev_out, cudaEvent_t* prev_ready) {
+  const size_t nfeat = (size_t)bb->d.in_channels * bb->d.feat_h * bb->d.feat_w;
+  HostCopyCtx* cx = nullptr;
+  DFM_TRY(host_copy_ctx(&cx));
+  *prev_ready = nullptr;
+  float* d_cur = nullptr;
+  float* d_prev = nullptr;
+  int hit = -1;
+  for (int i = 0; i < 2; ++i)
+    if (bb->stage[i].pending && bb->stage[i].h_cur == h_cur && bb->stage[i].h_prev == h_prev)
+      hit = i;
+  if (hit >= 0) {
+    // the pair was prefetched: both maps are (being) copied on the side stream
+    dfm_backbone::HostStage& hs = bb->stage[hit];
+    hs.pending = false;
+    d_cur = hs.cur.p;
+    d_prev = hs.prev.p;
+    CU_TRY(cudaStreamWaitEvent(st, hs.ready, 0));
+  } else {
+    const int slot = !bb->stage[0].pending ? 0 : !bb->stage[1].pending ? 1
+                     : (bb->stage[0].tick <= bb->stage[1].tick ? 0 : 1);
+    dfm_backbone::HostStage& hs = bb->stage[slot];
+    hs.pending = false;
+    DFM_TRY(stage_alloc(hs, nfeat));
+    d_cur = hs.cur.p;
+    d_prev = hs.prev.p;
+    // the prev-frame copy rides the side stream underneath the mono tower
+    CU_TRY(cudaEventRecord(cx->fork, st));  // staging buffers are free once prior work is done
+    CU_TRY(cudaStreamWaitEvent(cx->stream, cx->fork, 0));
+    CU_TRY(cudaMemcpyAsync(d_cur, h_cur, nfeat * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_prev, h_prev, nfeat * 4, cudaMemcpyHostToDevice, cx->stream));
+    CU_TRY(cudaEventRecord(cx->prev_done, cx->stream));
+    *prev_ready = cx->prev_done;
+  }
+  *d_cur_out = d_cur;
+  *d_prev_out = d_prev;
   return DFM_OK;
 }
 }  // namespace
@@ -1078,48 +1131,19 @@ int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const floa
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nfeat = (size_t)bb->d.in_channels * bb->d.feat_h * bb->d.feat_w;
   const size_t V = (size_t)bb->D * bb->Ho * bb->Wo;
-  HostCopyCtx* cx = nullptr;
-  DFM_TRY(host_copy_ctx(&cx));
   cudaEvent_t prev_ready = nullptr;
   float* d_cur = nullptr;
   float* d_prev = nullptr;
-  int hit = -1;
-  for (int i = 0; i < 2; ++i)
-    if (bb->stage[i].pending && bb->stage[i].h_cur == h_cur && bb->stage[i].h_prev == h_prev)
-      hit = i;
-  if (hit >= 0) {
-    // the pair was prefetched: both maps are (being) copied on the side stream
-    dfm_backbone::HostStage& hs = bb->stage[hit];
-    hs.pending = false;
-    d_cur = hs.cur.p;
-    d_prev = hs.prev.p;
-    CU_TRY(cudaStreamWaitEvent(st, hs.ready, 0));
-  } else {
-    const int slot = !bb->stage[0].pending ? 0 : !bb->stage[1].pending ? 1
-                     : (bb->stage[0].tick <= bb->stage[1].tick ? 0 : 1);
-    dfm_backbone::HostStage& hs = bb->stage[slot];
-    hs.pending = false;
-    DFM_TRY(stage_alloc(hs, nfeat));
-    d_cur = hs.cur.p;
-    d_prev = hs.prev.p;
-    // the prev-frame copy rides the side stream underneath the mono tower
-    CU_TRY(cudaEventRecord(cx->fork, st));  // staging buffers are free once prior work is done
-    CU_TRY(cudaStreamWaitEvent(cx->stream, cx->fork, 0));
-    CU_TRY(cudaMemcpyAsync(d_cur, h_cur, nfeat * 4, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(d_prev, h_prev, nfeat * 4, cudaMemcpyHostToDevice, cx->stream));
-    CU_TRY(cudaEventRecord(cx->prev_done, cx->stream));
-    prev_ready = cx->prev_done;
-  }
+  DFM_TRY(stage_host_pair(bb, h_cur, h_prev, st, &d_cur, &d_prev, &prev_ready));
   float* d_st = nullptr;
   float* d_mo = nullptr;
-  DevBuf tmp_s, tmp_m;
   if ((out_flags & DFM_OUT_STEREO) && h_stereo) {
-    DFM_TRY(tmp_s.alloc(V * 32));
-    d_st = tmp_s.p;
+    DFM_TRY(bb->out_st.alloc(V * 32));
+    d_st = bb->out_st.p;
   }
   if ((out_flags & DFM_OUT_MONO) && h_mono) {
-    DFM_TRY(tmp_m.alloc(V * 32));
-    d_mo = tmp_m.p;
+    DFM_TRY(bb->out_mo.alloc(V * 32));
+    d_mo = bb->out_mo.p;
   }
   int rc = backbone_forward_impl(bb, d_cur, d_prev, geom, nullptr, d_st, d_mo, stream, prev_ready);
   if (rc == DFM_OK && (out_flags & DFM_OUT_COST) && h_cost)
@@ -1132,8 +1156,6 @@ int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const floa
     if (cudaMemcpyAsync(h_mono, d_mo, V * 32 * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
       rc = fail(DFM_ERR_CUDA, "D2H copy of mono feature failed");
   cudaError_t e = cudaStreamSynchronize(st);
-  tmp_s.release();
-  tmp_m.release();
   if (rc == DFM_OK && e != cudaSuccess) rc = fail(DFM_ERR_CUDA, cudaGetErrorString(e));
   if (rc == DFM_OK && dfm::tc_consume_error())
     rc = fail(DFM_ERR_CUDA, "tensor-core conv kernel: mbarrier hand-over timed out");
@@ -1160,8 +1182,13 @@ int dfm_op_build_cost_volume(const float* d_cur, const float* d_prev, int C, int
   if (!d_cur || !d_prev || !h_depths || !geom || !d_volume)
     return fail(DFM_ERR_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  const int Ho = (int)std::lround((double)H / cost_sample_factor);
-  const int Wo = (int)std::lround((double)W / cost_sample_factor);
+  if (cost_sample_factor < 1 || feat_sample_factor < 1 || C < 1 || D < 1 || H < 1 || W < 1)
+    return fail(DFM_ERR_INVALID, "bad shape / sample factor");
+  const int Ho = (int)std::nearbyint((double)H / cost_sample_factor);  // round-half-even
+  const int Wo = (int)std::nearbyint((double)W / cost_sample_factor);
+  if (Ho < 1 || Wo < 1 || (long long)(Ho - 1) * cost_sample_factor > H - 1 ||
+      (long long)(Wo - 1) * cost_sample_factor > W - 1)
+    return fail(DFM_ERR_INVALID, "feature size not compatible with cost_sample_factor");
   DevBuf cur, prev, dep;
   const long long HW = (long long)H * W;
   DFM_TRY(cur.alloc(HW * C));
@@ -1204,13 +1231,32 @@ int dfm_op_conv3d(const float* d_x, int Cin, int Di, int Hi, int Wi, const float
   DFM_TRY(xin.alloc(Vi * Cin));
   DFM_TRY(yout.alloc(Vo * Cout));
   DFM_TRY(to_nhwc(d_x, xin.p, Cin, Vi, st));
-  int rc = run_conv(src1(term(xin, nullptr, 0)), w, yout.p, g, conv_impl, st);
+  int rc = DFM_OK;
+  // the K-outer kernel of the BEV necks (conv_tc_neck.cuh) serves the shapes the resident-weight
+  // kernel does not: 64..256 channels, a short (<= 16) W axis, strides (1,1,1) / (1,1,2)
+  const int zm = dfm::nk_zmode(g);
+  const bool want_neck = zm >= 0 && conv_impl != DFM_CONV_SIMT &&
+                         (conv_impl == DFM_CONV_TC_NECK || !w.tc.ready());
+  if (conv_impl == DFM_CONV_TC_NECK && zm < 0)
+    rc = fail(DFM_ERR_INVALID, "conv3d: the BEV-neck tensor-core kernel does not serve this shape");
+  if (rc == DFM_OK && want_neck) {
+    const std::vector<float> packed = repack_simt(h_w, Cin, Cout, 0);
+    std::string err;
+    if (!w.ntc.build(packed.data(), Cin, Cout, zm, &err) ||
+        !dfm::neck_tc_conv(src1(term(xin, nullptr, 0)), w.ntc, yout.p, g, st, &err))
+      rc = fail(DFM_ERR_CUDA, err);
+    g_launches.fetch_add(1);
+    g_tc_launches.fetch_add(1);
+  } else if (rc == DFM_OK) {
+    rc = run_conv(src1(term(xin, nullptr, 0)), w, yout.p, g, conv_impl, st);
+  }
   if (rc == DFM_OK) rc = to_ncdhw(yout.p, d_y, Cout, Vo, st);
   cudaError_t e = cudaStreamSynchronize(st);
   xin.release();
   yout.release();
   w.simt.release();
   w.tc.release();
+  w.ntc.release();
   if (rc == DFM_OK && e != cudaSuccess) rc = fail(DFM_ERR_CUDA, cudaGetErrorString(e));
   if (rc == DFM_OK && dfm::tc_consume_error())
     rc = fail(DFM_ERR_CUDA, "tensor-core conv kernel: mbarrier hand-over timed out");
@@ -1240,3 +1286,4 @@ int dfm_depth_head_forward(const float* d_cost, const float* d_depth_samples, in
 
 #include "neck_api.inc"
 #include "frustum_api.inc"
+#include "pipeline_api.inc"

@@ -630,10 +630,29 @@ struct LiftParams {
   int flip, in_h, in_w, concat;
 };
 
+// points_cam2img + scale/crop of point_sample (structures/utils.py:199-214,
+// point_fusion.py:63-69) with the reference's rounding sequence spelled out: the fp32
+// [N,4] x [4,4]^T product accumulates k = 0..3 with one fused multiply-add per step (what
+// the CPU GEMM micro-kernel does; checked bit-for-bit against torch.matmul), the perspective
+// divide, the scale multiply and the crop subtraction round separately.  Nearest-tap
+// sampling is discontinuous, so letting nvcc contract these into different FMAs moves
+// voxels that project onto a rounding tie to the neighbouring tap.
+__device__ __forceinline__ void lift_project(const float* m, float px, float py, float pz,
+                                             float sx, float sy, float crx, float cry,
+                                             float& cx, float& cy, float& d) {
+  const float a = __fadd_rn(__fmaf_rn(pz, m[2], __fmaf_rn(py, m[1], __fmul_rn(px, m[0]))), m[3]);
+  const float b = __fadd_rn(__fmaf_rn(pz, m[6], __fmaf_rn(py, m[5], __fmul_rn(px, m[4]))), m[7]);
+  d = __fadd_rn(__fmaf_rn(pz, m[10], __fmaf_rn(py, m[9], __fmul_rn(px, m[8]))), m[11]);
+  cx = __fsub_rn(__fmul_rn(__fdiv_rn(a, d), sx), crx);
+  cy = __fsub_rn(__fmul_rn(__fdiv_rn(b, d), sy), cry);
+}
+
 __device__ __forceinline__ int nearest_index(float coord, int size, float norm_size) {
   // grid_sample(mode='nearest', align_corners=True): unnormalise then nearbyint
-  const float g = coord / norm_size * 2.f - 1.f;
-  const float ix = (g + 1.f) * 0.5f * (float)(size - 1);
+  // norm = coord / size * 2 - 1 (point_fusion.py:82-83); ATen unnormalises with
+  // ((g + 1) / 2) * (size - 1); the *2 and /2 are exact, the rest rounds once per step
+  const float g = __fsub_rn(__fmul_rn(__fdiv_rn(coord, norm_size), 2.f), 1.f);
+  const float ix = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), (float)(size - 1));
   return (int)nearbyintf(ix);
 }
 
@@ -659,12 +678,9 @@ lift_kernel(LiftParams p, const float* __restrict__ feats, const float* __restri
     for (int v = 0; v < p.Nv; ++v) {
       const int s = f * p.Nv + v;
       const float* m = p.proj[s];
-      const float a = m[0] * px + m[1] * py + m[2] * pz + m[3];
-      const float b = m[4] * px + m[5] * py + m[6] * pz + m[7];
-      const float d = m[8] * px + m[9] * py + m[10] * pz + m[11];
-      float cx = a / d * p.scale_x - p.crop_x;
-      const float cy = b / d * p.scale_y - p.crop_y;
-      if (p.flip) cx = (float)p.img_w[s] - cx;
+      float cx, cy, d;
+      lift_project(m, px, py, pz, p.scale_x, p.scale_y, p.crop_x, p.crop_y, cx, cy, d);
+      if (p.flip) cx = __fsub_rn((float)p.img_w[s], cx);
       const bool valid = cx < (float)p.in_w && cx > 0.f && cy < (float)p.in_h && cy > 0.f &&
                          d > 0.f;
       if (!valid) continue;
@@ -679,11 +695,12 @@ lift_kernel(LiftParams p, const float* __restrict__ feats, const float* __restri
       }
     }
     if (p.concat) {
-      const float inv = 1.f / (float)max(nvalid, 1);
+      // sum / clamp(count, 1): a true division like multiview_dfm.py:194-203
+      const float den = (float)max(nvalid, 1);
       for (int j = 0; j < CL; ++j) {
         const int c = lane + 32 * j;
         if (c < p.C)
-          out[((long long)(f * p.C + c)) * nvox + ovox] = nvalid > 0 ? acc[j] * inv : 0.f;
+          out[((long long)(f * p.C + c)) * nvox + ovox] = nvalid > 0 ? __fdiv_rn(acc[j], den) : 0.f;
       }
     } else {
       for (int j = 0; j < CL; ++j) tot[j] += nvalid > 0 ? acc[j] : 0.f;
@@ -691,10 +708,10 @@ lift_kernel(LiftParams p, const float* __restrict__ feats, const float* __restri
     }
   }
   if (!p.concat) {
-    const float inv = 1.f / (float)max(tot_n, 1);
+    const float den = (float)max(tot_n, 1);
     for (int j = 0; j < CL; ++j) {
       const int c = lane + 32 * j;
-      if (c < p.C) out[(long long)c * nvox + ovox] = tot_n > 0 ? tot[j] * inv : 0.f;
+      if (c < p.C) out[(long long)c * nvox + ovox] = tot_n > 0 ? __fdiv_rn(tot[j], den) : 0.f;
     }
   }
 }
@@ -727,12 +744,9 @@ lift_voxel_kernel(LiftParams p, const float* __restrict__ feats, const float* __
     for (int v = 0; v < p.Nv; ++v) {
       const int s = f * p.Nv + v;
       const float* m = p.proj[s];
-      const float a = m[0] * px + m[1] * py + m[2] * pz + m[3];
-      const float b = m[4] * px + m[5] * py + m[6] * pz + m[7];
-      const float d = m[8] * px + m[9] * py + m[10] * pz + m[11];
-      float cx = a / d * p.scale_x - p.crop_x;
-      const float cy = b / d * p.scale_y - p.crop_y;
-      if (p.flip) cx = (float)p.img_w[s] - cx;
+      float cx, cy, d;
+      lift_project(m, px, py, pz, p.scale_x, p.scale_y, p.crop_x, p.crop_y, cx, cy, d);
+      if (p.flip) cx = __fsub_rn((float)p.img_w[s], cx);
       const bool valid = cx < (float)p.in_w && cx > 0.f && cy < (float)p.in_h && cy > 0.f &&
                          d > 0.f;
       if (!valid) continue;
@@ -752,9 +766,10 @@ lift_voxel_kernel(LiftParams p, const float* __restrict__ feats, const float* __
       }
     }
     if (p.concat) {
-      const float inv = nvalid > 0 ? 1.f / (float)nvalid : 0.f;
+      const float den = (float)max(nvalid, 1);  // acc is all zero when nvalid == 0
 #pragma unroll
-      for (int c = 0; c < C; ++c) out[((long long)(f * C + c)) * nvox + ovox] = acc[c] * inv;
+      for (int c = 0; c < C; ++c)
+        out[((long long)(f * C + c)) * nvox + ovox] = __fdiv_rn(acc[c], den);
     } else {
       if (nvalid > 0) {
 #pragma unroll
@@ -764,9 +779,9 @@ lift_voxel_kernel(LiftParams p, const float* __restrict__ feats, const float* __
     }
   }
   if (!p.concat) {
-    const float inv = tot_n > 0 ? 1.f / (float)tot_n : 0.f;
+    const float den = (float)max(tot_n, 1);  // tot is all zero when tot_n == 0
 #pragma unroll
-    for (int c = 0; c < C; ++c) out[(long long)c * nvox + ovox] = tot[c] * inv;
+    for (int c = 0; c < C; ++c) out[(long long)c * nvox + ovox] = __fdiv_rn(tot[c], den);
   }
 }
 

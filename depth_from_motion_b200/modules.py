@@ -19,6 +19,7 @@ called.  There is no PyTorch fallback: without the built library or a B200 the
 modules raise.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -28,7 +29,7 @@ from . import capi
 from .registry import BACKBONES, HEADS, NECKS
 
 _IMPL = {'auto': capi.DFM_CONV_AUTO, 'simt': capi.DFM_CONV_SIMT,
-         'tc': capi.DFM_CONV_TC}
+         'tc': capi.DFM_CONV_TC, 'tc_neck': capi.DFM_CONV_TC_NECK}
 
 
 def _ptr(t):
@@ -47,19 +48,45 @@ def _check_cuda(t, name):
         raise RuntimeError(f'{name} must be float32, got {t.dtype}')
 
 
+_STRICT_PARAM_CHECK = bool(int(os.environ.get('DFM_PARAM_CHECK', '0')))
+
+
 class _ParamSync:
-    """Uploads parameters to a C handle whenever any of them changed."""
+    """Uploads parameters to a C handle whenever any of them changed.
+
+    Change detection per forward is (storage pointer, tensor version) of every
+    ``state_dict`` entry -- free, and it sees optimizer steps, ``copy_`` / ``fill_`` on
+    the parameter, re-assignment and ``load_state_dict``.  It does NOT see in-place
+    writes through ``param.data`` (``p.data.copy_(w)`` leaves ``p._version``
+    untouched; EMA hooks and legacy init code do this).  Three safety nets:
+    ``load_state_dict`` and ``train()`` / ``eval()`` always force a re-upload (the
+    mirrors call ``mark_dirty`` from those hooks), callers that write through
+    ``.data`` call ``module.sync_params()`` (or ``mark_dirty()``), and
+    ``DFM_PARAM_CHECK=1`` adds a content fingerprint (sum and abs-sum of every
+    tensor, one device sync per forward) for debugging such code."""
 
     def __init__(self):
+        self._sig = None
+        self._finger = None
+
+    def mark_dirty(self):
         self._sig = None
 
     def signature(self, module):
         return tuple((k, v.data_ptr(), v._version)
                      for k, v in module.state_dict(keep_vars=True).items())
 
+    @staticmethod
+    def fingerprint(module):
+        vals = [v.detach().double() for v in module.state_dict().values()
+                if v.is_floating_point()]
+        return torch.stack([torch.stack((v.sum(), v.abs().sum())) for v in vals]).cpu()
+
     def sync(self, module, set_fn):
         sig = self.signature(module)
-        if sig == self._sig:
+        finger = self.fingerprint(module) if _STRICT_PARAM_CHECK else None
+        if sig == self._sig and (finger is None or (
+                self._finger is not None and torch.equal(finger, self._finger))):
             return
         for k, v in module.state_dict().items():
             if k.endswith('num_batches_tracked'):
@@ -67,6 +94,42 @@ class _ParamSync:
             h = v.detach().to('cpu', torch.float32).contiguous()
             set_fn(k.encode(), ctypes.c_void_p(h.data_ptr()), h.numel())
         self._sig = sig
+        self._finger = finger
+
+
+class _CudaMirror(nn.Module):
+    """Shared plumbing of the mirror modules: parameter re-upload hooks and the
+    forward-only guard (the CUDA path has no backward; the reference trains these
+    modules with autograd, which stays out of scope -- SURVEY.md section 3.3)."""
+
+    def mark_dirty(self):
+        """Force a parameter re-upload at the next forward (call after writing
+        weights through ``param.data``)."""
+        sync = getattr(self, '_sync', None)
+        if sync is not None:
+            sync.mark_dirty()
+
+    sync_params = mark_dirty
+
+    def train(self, mode=True):
+        self.mark_dirty()
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.mark_dirty()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _forward_only(self, *tensors):
+        # eval-mode calls outside no_grad() just return tensors without a graph, which is
+        # what inference code expects; training-mode calls would silently train nothing
+        if not (self.training and torch.is_grad_enabled()):
+            return
+        if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors) or \
+                any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError(
+                f'{type(self).__name__} (depth_from_motion_b200) is forward-only: call '
+                '.eval() or run it under torch.no_grad(); autograd through the CUDA path '
+                'is not implemented')
 
 
 class _ConvGN(nn.Module):
@@ -124,7 +187,7 @@ def geometry_from_meta(img_meta):
 
 
 @BACKBONES.register_module()
-class DfMBackbone(nn.Module):
+class DfMBackbone(_CudaMirror):
     """Drop-in for the reference ``DfMBackbone`` (dfm_backbone.py:14-214)."""
 
     def __init__(self, in_channels, num_hg=1, cost_sample_factor=4,
@@ -146,6 +209,9 @@ class DfMBackbone(nn.Module):
         self.depth_cfg = depth_cfg
         self.conv_impl = conv_impl
         groups = norm_cfg.get('num_groups', 32)
+        # the kernels take GroupNorm statistics per group of C/32 channels
+        # (nn.GroupNorm(32, C), conv_modules.py:42-43, which hard-codes 32 as well)
+        assert groups == 32, 'only GroupNorm(num_groups=32) is implemented'
         cv = cv_channels
 
         def pred():
@@ -235,6 +301,7 @@ class DfMBackbone(nn.Module):
                 cur_sem_feats=None):
         _check_cuda(cur_stereo_feats, 'cur_stereo_feats')
         _check_cuda(prev_stereo_feats, 'prev_stereo_feats')
+        self._forward_only(cur_stereo_feats, prev_stereo_feats)
         b, c, h, w = cur_stereo_feats.shape
         # the reference only supports batch size 1 (dfm_backbone.py:160)
         assert b == 1, 'only support batch size 1 for now'
@@ -321,7 +388,7 @@ def conv3d(x, weight, stride=(1, 1, 1), padding=(1, 1, 1), transposed=False,
 
 
 @HEADS.register_module()
-class DepthHead(nn.Module):
+class DepthHead(_CudaMirror):
     """Drop-in for the reference ``DepthHead`` forward (depth_head.py:13-212).
     ``loss`` is training-side PyTorch in the reference and is out of scope
     (SURVEY.md section 8a row a5)."""
@@ -351,6 +418,7 @@ class DepthHead(nn.Module):
         depth_head.py:190-212.  ``return_volumes=False`` skips the two
         [B,N,fD,fH,fW] outputs (returns None for them)."""
         _check_cuda(stereo_features, 'stereo_features')
+        self._forward_only(stereo_features)
         if self.with_convs:
             raise NotImplementedError(
                 'DepthHead(with_convs=True) is not on the shipped DfM path '
@@ -382,7 +450,7 @@ class DepthHead(nn.Module):
         return vol, sm, preds
 
 
-class _NeckBase(nn.Module):
+class _NeckBase(_CudaMirror):
     def _make_tower(self, c0, c1, c2, cout):
         def cm(ci, co, **kw):
             m = nn.Module()
@@ -509,7 +577,7 @@ class CostLogits:
 
 
 @NECKS.register_module()
-class FrustumToVoxel(nn.Module):
+class FrustumToVoxel(_CudaMirror):
     """Drop-in for the reference ``FrustumToVoxel``
     (necks/feature_transformation.py:12-173): same constructor arguments and
     ``state_dict`` keys (``voxel_convs.<i>.0.conv.weight`` /
@@ -599,6 +667,7 @@ class FrustumToVoxel(nn.Module):
         DepthHead's ``[B, 1, fD, fH, fW]`` tensor like in the reference, or a
         ``CostLogits`` wrapper (fused path)."""
         _check_cuda(stereo_feat, 'stereo_feat')
+        self._forward_only(stereo_feat, cur_sem_feats)
         b, c, d, h, w = stereo_feat.shape
         assert b == len(img_metas)
         logits = sm = samples = preds = None
@@ -658,6 +727,67 @@ class FrustumToVoxel(nn.Module):
         return out
 
 
+class HotPathPipeline:
+    """``DfM.simple_test``'s hot-path segment as one C-ABI call with HOST buffers
+    (detectors/dfm.py:296, :420, :423-425): ``backbone_stereo`` -> ``depth_head``
+    -> ``feature_transformation``.  Pinned host features in, pinned host voxel
+    features + ``depth_preds`` out; nothing else leaves the device.  This is the call
+    a deployment that keeps the 2-D backbone and the BEV head in PyTorch makes once per
+    frame (``bench.py``'s ``e2e`` number times it)."""
+
+    def __init__(self, backbone, depth_head, frustum):
+        self.backbone, self.depth_head, self.frustum = backbone, depth_head, frustum
+        self._out = None
+
+    def prepare(self, feat_h, feat_w, sem_hw):
+        bb, fr = self.backbone, self.frustum
+        L = bb._prepare(feat_h, feat_w)
+        ho = round(feat_h / bb.cost_sample_factor)
+        wo = round(feat_w / bb.cost_sample_factor)
+        f = int(self.depth_head.downsample_factor)
+        fr._ensure_handle(bb.num_planes, ho, wo, sem_hw[0], sem_hw[1], f)
+        fr._sync.sync(fr, lambda k, p, m: capi.check(
+            L.dfm_frustum_set_param(fr._handle, k, p, m),
+            f'dfm_frustum_set_param({k.decode()})'))
+        nz, ny, nx = fr.coordinates_3d.shape[:3]
+        if self._out is None or self._out[0].shape[-3:] != (nz // 4, ny, nx) or \
+                self._out[1].shape[-2:] != (f * ho, f * wo):
+            self._out = (
+                torch.empty((1, fr.out_channels, nz // 4, ny, nx)).pin_memory(),
+                torch.empty((1, 1, f * ho, f * wo)).pin_memory())
+            self._samples = self.depth_head.depth_samples.detach().to(
+                'cpu', torch.float32).contiguous()
+        return L
+
+    def prefetch(self, h_cur, h_prev):
+        """Start copying the NEXT pair (pinned host tensors) while the current one runs."""
+        capi.check(capi.lib().dfm_backbone_prefetch_host(
+            self.backbone._handle, _ptr(h_cur), _ptr(h_prev)),
+            'dfm_backbone_prefetch_host')
+
+    def __call__(self, h_cur, h_prev, h_sem, img_metas, h_cost=None):
+        """h_cur / h_prev [1,C,H,W], h_sem [1,32,H/4,W/4]: CPU float32 tensors (pinned for
+        full PCIe bandwidth).  Returns (voxel_features [1,32,Nz/4,Ny,Nx], depth_preds
+        [1,1,H,W]) as pinned CPU tensors owned by this object (overwritten by the next
+        call)."""
+        for t in (h_cur, h_prev):
+            assert t.device.type == 'cpu' and t.dtype == torch.float32 and t.is_contiguous()
+        _, _, h, w = h_cur.shape
+        L = self.prepare(h, w, tuple(h_sem.shape[-2:]) if h_sem is not None else (1, 1))
+        meta = img_metas[0]
+        geom = geometry_from_meta(meta)
+        P = (ctypes.c_double * 16)(*np.asarray(
+            meta['cam2img'], np.float64).reshape(-1)[:16].tolist())
+        pad = meta['pad_shape']
+        vox, preds = self._out
+        capi.check(L.dfm_pipeline_forward_host(
+            self.backbone._handle, self.frustum._handle, _ptr(h_cur), _ptr(h_prev),
+            _ptr(h_sem), ctypes.byref(geom), P, int(pad[0]), int(pad[1]),
+            _ptr(self._samples), _ptr(vox), _ptr(preds), _ptr(h_cost), _stream()),
+            'dfm_pipeline_forward_host')
+        return vox, preds
+
+
 def aligned_voxel_centers(n_voxels, voxel_range):
     """Per-axis voxel-centre coordinates exactly as
     AlignedAnchor3DRangeGenerator.anchors_single_range computes them
@@ -672,6 +802,24 @@ def aligned_voxel_centers(n_voxels, voxel_range):
     return out
 
 
+def _require_identity_3d_aug(img_meta):
+    """point_sample first undoes the 3-D augmentation recorded in img_meta
+    (apply_3d_transformation(reverse=True), coord_transform.py:9-92).  At test time the
+    keys are absent or identity; the lifting kernel does not implement the reverse
+    transform, so anything else must fail loudly rather than lift with wrong points."""
+    rot = img_meta.get('pcd_rotation')
+    if rot is not None and not np.allclose(np.asarray(rot, dtype=np.float64), np.eye(3)):
+        raise NotImplementedError('multiview_lift: non-identity pcd_rotation')
+    scale = img_meta.get('pcd_scale_factor', 1.0)
+    if not np.isclose(float(scale), 1.0):
+        raise NotImplementedError('multiview_lift: pcd_scale_factor != 1')
+    trans = img_meta.get('pcd_trans')
+    if trans is not None and np.any(np.asarray(trans, dtype=np.float64) != 0):
+        raise NotImplementedError('multiview_lift: non-zero pcd_trans')
+    if img_meta.get('pcd_horizontal_flip', False) or img_meta.get('pcd_vertical_flip', False):
+        raise NotImplementedError('multiview_lift: pcd flip')
+
+
 def multiview_lift(feats, img_meta, n_voxels, voxel_range, num_views,
                    num_frames, temporal_aggregate='mean'):
     """The lifting loop of MultiViewDfM.feature_transformation
@@ -680,6 +828,7 @@ def multiview_lift(feats, img_meta, n_voxels, voxel_range, num_views,
     _check_cuda(feats, 'feats')
     s, c, hf, wf = feats.shape
     assert s == num_views * num_frames
+    _require_identity_3d_aug(img_meta)
     sf = img_meta.get('scale_factor', 1.0)
     sf = np.atleast_1d(np.asarray(sf, dtype=np.float32))
     sx, sy = (float(sf[0]), float(sf[1])) if sf.size >= 2 else (float(sf[0]),) * 2
@@ -712,3 +861,39 @@ def multiview_lift(feats, img_meta, n_voxels, voxel_range, num_views,
         ctypes.c_void_p(zs.data_ptr()), _ptr(out), _stream()),
         'dfm_multiview_lift')
     return out
+
+
+class MultiViewDfMFeatureTransformation:
+    """Method-override mix-in for the reference detector: same signature, same
+    ``img_metas`` keys and same return tuple as
+    ``MultiViewDfM.feature_transformation`` (detectors/multiview_dfm.py:119-268)
+    for the shipped Waymo configs (``valid_sample=True``, no ``backbone_3d``, no
+    ``depth_head``: configs/dfm/multiview-dfm_r101_dcn_2x16_waymoD5-3d-3class_camsync
+    [_10sweeps].py:26-32).  Usage::
+
+        class MultiViewDfMB200(MultiViewDfMFeatureTransformation, MultiViewDfM):
+            pass
+
+    The host object supplies what the reference reads from ``self``: ``n_voxels``,
+    ``voxel_range`` (``anchor_generator['ranges'][0]``), ``temporal_aggregate``,
+    ``valid_sample``, ``neck_3d`` (our ``OutdoorImVoxelNeck`` / ``DfMNeck``)."""
+
+    def feature_transformation(self, batch_feats, img_metas, num_views, num_frames):
+        if getattr(self, 'with_depth_head', False) or getattr(self, 'with_backbone_3d', False):
+            raise NotImplementedError(
+                'the CUDA feature_transformation covers the shipped configs '
+                '(depth_head=None, backbone_3d=None); voxel_sample is not on that path')
+        if not getattr(self, 'valid_sample', True):
+            raise NotImplementedError('valid_sample=False is not implemented')
+        volumes = []
+        for feature, img_meta in zip(batch_feats, img_metas):       # :128
+            meta = dict(img_meta)
+            if 'scale_factor' not in meta:                           # :129-138
+                meta['scale_factor'] = 1.0
+            volumes.append(multiview_lift(
+                feature, meta, list(self.n_voxels), list(self.voxel_range), num_views,
+                num_frames, self.temporal_aggregate))
+        volume_feat = torch.stack(volumes)                           # (B, C, Nx, Ny, Nz), :209
+        if getattr(self, 'with_neck_3d', self.neck_3d is not None):
+            volume_feat = self.neck_3d(volume_feat)[0]               # :263
+        return (volume_feat, )                                       # :265-268

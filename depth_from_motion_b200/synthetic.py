@@ -218,3 +218,50 @@ def make_frustum_case(seed, h, w, num_planes, n_voxels, num_3dconvs=1,
                 coordinates_3d=frustum_coordinates(KITTI_POINT_CLOUD_RANGE,
                                                    n_voxels),
                 depth_cfg=depth_cfg_for(num_planes))
+
+
+# Waymo multi-view workload (configs/dfm/multiview-dfm_r101_dcn_2x16_waymoD5-3d-3class_camsync
+# [_10sweeps].py: input 832x1248 after MultiViewImageResize3D, FPN level-0 features at stride 4,
+# n_voxels [220, 300, 12] over [-35, -75, -2, 75, 75, 4]; detectors/multiview_dfm.py:54-61)
+WAYMO_N_VOXELS = [220, 300, 12]
+WAYMO_RANGE = [-35.0, -75.0, -2.0, 75.0, 75.0, 4.0]
+WAYMO_INPUT_HW = (832, 1248)
+WAYMO_FEAT_HW = (208, 312)
+
+
+def waymo_lidar2img(num_frames, num_views=5, ego_shift=1.0):
+    """Synthetic pinhole rig: cameras yawed over the front half-circle, focal length
+    2055 px * 0.65 (resize), principal point at the image centre; earlier frames are
+    shifted `ego_shift` metres backwards.  [T*Nv, 4, 4] float64."""
+    mats = []
+    for f in range(num_frames):
+        for v in range(num_views):
+            yaw = (v - (num_views - 1) / 2) * 0.7
+            r = np.array([[np.cos(yaw), np.sin(yaw), 0], [-np.sin(yaw), np.cos(yaw), 0],
+                          [0, 0, 1]])
+            # lidar (x fwd, y left, z up) -> camera (x right, y down, z fwd)
+            l2c = np.array([[0, -1, 0], [0, 0, -1], [1, 0, 0]], dtype=np.float64) @ r
+            ext = np.eye(4)
+            ext[:3, :3] = l2c
+            ext[:3, 3] = l2c @ np.array([-ego_shift * f, 0.03 * v, -1.5])
+            k = np.array([[1335.75, 0, 624, 0], [0, 1335.75, 416, 0], [0, 0, 1, 0],
+                          [0, 0, 0, 1]])
+            mats.append(k @ ext)
+    return np.array(mats)
+
+
+def make_waymo_sample(seed, num_frames, num_views=5, channels=64, feat_hw=WAYMO_FEAT_HW,
+                      input_hw=WAYMO_INPUT_HW, flip=False, scale=1.0, crop=(0.0, 0.0)):
+    """One sample of MultiViewDfM.feature_transformation's inputs: [T*Nv, C, Hf, Wf] features
+    and the img_meta keys multiview_dfm.py:139-170 reads."""
+    rng = np.random.RandomState(seed)
+    s = num_frames * num_views
+    feats = torch.from_numpy(
+        rng.standard_normal((s, channels) + tuple(feat_hw)).astype(np.float32))
+    meta = dict(ori_lidar2img=waymo_lidar2img(num_frames, num_views),
+                input_shape=tuple(input_hw),
+                img_shape=[(input_hw[0], input_hw[1], 3)] * s,
+                scale_factor=np.array([scale, scale, scale, scale], dtype=np.float32),
+                img_crop_offset=list(crop), flip=flip, num_views=num_views,
+                num_ref_frames=num_frames - 1)
+    return feats, meta

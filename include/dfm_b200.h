@@ -35,6 +35,8 @@ extern "C" {
 #define DFM_CONV_AUTO 0 /* tcgen05 tensor-core kernels where implemented, SIMT else */
 #define DFM_CONV_SIMT 1 /* fp32 CUDA-core kernels everywhere (bring-up / cross-check) */
 #define DFM_CONV_TC 2   /* tcgen05 only; error if a layer has no tensor-core kernel   */
+#define DFM_CONV_TC_NECK 3 /* dfm_op_conv3d only: force the K-outer tcgen05 kernel of the BEV
+                              necks (64..256 channels, W <= 16, strides (1,1,1) / (1,1,2))  */
 
 /* output-selection flags for the *_host entry points */
 #define DFM_OUT_COST 1   /* gated depth logits           [1,1,D,Ho,Wo] */
@@ -260,6 +262,30 @@ int dfm_frustum_forward(dfm_frustum_t* f, const float* d_stereo_feat, int stereo
                         const float* d_depth_samples, float* d_depth_preds, const float* d_sem,
                         const double* cam2img, int pad_h, int pad_w, float* d_out,
                         void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * The hot-path segment of DfM.simple_test as one call with HOST buffers
+ * (mmdet3d/models/detectors/dfm.py:296 `backbone_stereo(...)`, :420 `depth_head(...)`,
+ * :423-425 `feature_transformation(...)`): (cur, prev) stereo features + cur semantic
+ * features in, what the BEV stage consumes out -- voxel features [out][nz/4][ny][nx] and
+ * DepthHead's depth_preds [fH][fW] (optionally the gated logits [D][Ho][Wo]).  Host->device
+ * copies, the whole path and device->host copies run on `stream`; the call synchronises.
+ * The pair may have been staged with dfm_backbone_prefetch_host.  stereo_feat never leaves
+ * the device and the x4-upsampled DepthHead volumes are never built.  `fr` must have been
+ * created for the backbone's volume shape (num_planes, feat_h = Ho, feat_w = Wo).
+ * h_depth_samples: host [depth_factor * D] (DepthHead.depth_samples).
+ * ---------------------------------------------------------------------------------- */
+int dfm_pipeline_forward_host(dfm_backbone_t* bb, dfm_frustum_t* fr, const float* h_cur,
+                              const float* h_prev, const float* h_sem,
+                              const dfm_geometry_t* geom, const double* cam2img, int pad_h,
+                              int pad_w, const float* h_depth_samples, float* h_voxel,
+                              float* h_depth_preds, float* h_cost, void* stream);
+
+/* Re-entrancy: handles may live on different devices and be driven from different host
+ * threads only if each thread owns its device; per-device scratch (K-slice partial sums,
+ * lifting staging, the host-copy side stream) and the profiling record are shared by all
+ * handles of a device and are NOT locked -- the same one-thread-per-process model as the
+ * reference (tools/slurm_train.sh:15-24, SURVEY.md section 8b "Threading"). */
 
 #ifdef __cplusplus
 }

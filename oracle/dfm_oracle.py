@@ -66,7 +66,7 @@ def points_cam2img(points_3d, proj_mat, with_depth=False):
     d1, d2 = proj_mat.shape[:2]
     assert (d1, d2) in ((3, 3), (3, 4), (4, 4))
     if d1 == 3:
-        expanded = torch.eye(4, dtype=proj_mat.dtype)
+        expanded = torch.eye(4, dtype=proj_mat.dtype, device=proj_mat.device)
         expanded[:d1, :d2] = proj_mat
         proj_mat = expanded
     ones = points_3d.new_ones(list(points_3d.shape[:-1]) + [1])
@@ -85,7 +85,7 @@ def points_img2cam(points, cam2img):
     xys = points[:, :2]
     depths = points[:, 2].view(-1, 1)
     unnormed_xys = torch.cat([xys * depths, depths], dim=1)
-    pad = torch.eye(4, dtype=xys.dtype)
+    pad = torch.eye(4, dtype=xys.dtype, device=xys.device)
     pad[:cam2img.shape[0], :cam2img.shape[1]] = cam2img
     inv_pad = torch.inverse(pad).transpose(0, 1)
     n = unnormed_xys.shape[0]
@@ -100,15 +100,17 @@ def build_dfm_cost(cur_feats, prev_feats, depths, feat_sample_factor,
                    cost_sample_factor, cam2imgs, cur2prevs, img_shape,
                    flip=False, img_crop_offset=(0, 0), img_scale_factor=1.0):
     """dfm_backbone.py:217-314.  Returns [B, 2C, D, Ho, Wo]."""
-    crop = torch.tensor(img_crop_offset)
+    dev = cur_feats.device  # the reference builds everything on the feature's device (:238)
+    crop = torch.tensor(img_crop_offset, device=dev)
+    depths = depths.to(dev)
     batch_size = cur_feats.shape[0]
     h_in, w_in = cur_feats.shape[-2:]
     num_depths = depths.shape[-1]
     h_out = round(h_in / cost_sample_factor)
     w_out = round(w_in / cost_sample_factor)
-    ws = torch.linspace(0, w_out - 1, w_out) * feat_sample_factor * \
+    ws = torch.linspace(0, w_out - 1, w_out, device=dev) * feat_sample_factor * \
         cost_sample_factor                                        # :247-248
-    hs = torch.linspace(0, h_out - 1, h_out) * feat_sample_factor * \
+    hs = torch.linspace(0, h_out - 1, h_out, device=dev) * feat_sample_factor * \
         cost_sample_factor                                        # :249-250
     ds_3d, ys_3d, xs_3d = torch.meshgrid(depths, hs, ws, indexing='ij')
     grid = torch.stack([xs_3d, ys_3d, ds_3d], dim=-1)            # :253
@@ -251,11 +253,12 @@ def dfm_backbone_forward(p, cur_feats, prev_feats, img_metas, depth_cfg,
                          in_channels=32, cost_sample_factor=4,
                          feat_sample_factor=1, q=_ident):
     """DfMBackbone.forward, dfm_backbone.py:143-214."""
+    dev = cur_feats.device
     ori_cam2imgs = torch.as_tensor(
-        np.array([m['ori_cam2img'] for m in img_metas]), dtype=torch.float32)
+        np.array([m['ori_cam2img'] for m in img_metas]), dtype=torch.float32).to(dev)
     cur2prevs = torch.stack([torch.as_tensor(np.asarray(m['cur2prevs']),
                                              dtype=torch.float32)
-                             for m in img_metas])
+                             for m in img_metas]).to(dev)
     cost_raw = build_dfm_cost(
         cur_feats, prev_feats, downsampled_depth(depth_cfg),
         feat_sample_factor, cost_sample_factor, ori_cam2imgs, cur2prevs[0],
@@ -274,7 +277,7 @@ def depth_head_forward(cost, samples, downsample_factor=4):
     vol = F.interpolate(cost, scale_factor=downsample_factor, mode='trilinear',
                         align_corners=True)
     sm = F.softmax(vol, dim=2)
-    preds = torch.sum(sm * samples[None, None, :, None, None], 2)
+    preds = torch.sum(sm * samples.to(vol.device)[None, None, :, None, None], 2)
     return vol, sm, preds
 
 

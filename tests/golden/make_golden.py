@@ -83,6 +83,27 @@ def neck_case(ns):
         print(name, tuple(y.shape), float(y.abs().max()))
 
 
+def neck_multitile_case(ns):
+    """Same two necks on a grid of 3 x 3 tiles (16 x 8 voxels each in the CUDA kernel) with
+    ragged edges, so tile seams, the K-outer group loop across tiles and the stride-(1,1,2)
+    layers on a multi-tile grid are pinned to the reference.  Inputs regenerate from the
+    seed (tests/util.py:make_neck_mt_case); the fixture stores the reference output and a
+    checksum of the input."""
+    from tests.util import make_neck_mt_case
+    for name, make in (('neck_dfm_mt', lambda: ns.DfMNeck(64, 256, num_frames=2)),
+                       ('neck_imvoxel_mt', lambda: ns.OutdoorImVoxelNeck(64, 256))):
+        rng, x = make_neck_mt_case(name)
+        mod = make().eval()
+        sd = syn.make_neck_params(rng, mod.state_dict())
+        mod.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            y = mod(x)[0]
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), y=y.numpy(),
+                            x_sum=np.float64(x.double().sum().item()),
+                            x_abs=np.float64(x.double().abs().sum().item()))
+        print(name, tuple(x.shape), '->', tuple(y.shape), float(y.abs().max()))
+
+
 FRUSTUM_CASE = dict(seed=31, h=32, w=64, num_planes=8, n_voxels=(24, 20, 8))
 
 
@@ -124,9 +145,13 @@ def main():
     if 'frustum' in sys.argv[1:]:
         frustum_case(ns)
         return
+    if 'neck_mt' in sys.argv[1:]:
+        neck_multitile_case(ns)
+        return
     for name, spec in KITTI_CASES.items():
         kitti_case(ns, name, spec)
     neck_case(ns)
+    neck_multitile_case(ns)
     frustum_case(ns)
 
 

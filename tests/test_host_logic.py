@@ -246,3 +246,52 @@ def test_checkpoint_key_plumbing():
     assert all(torch.equal(ft2.state_dict()[k], v) for k, v in ft_sd.items())
     with pytest.raises(KeyError):
         ck.load_hot_path({'state_dict': {'x.y': torch.zeros(1)}}, backbone=bb2)
+
+
+def test_param_sync_hooks_and_guards():
+    """`_version` does not see writes through `.data`; load_state_dict / train() /
+    eval() and mark_dirty() must force a re-upload; unsupported configs fail loudly."""
+    m = modules.DfMBackbone(in_channels=32, depth_cfg=syn.depth_cfg_for(8))
+    uploads = []
+    m._sync.sync(m, lambda k, p, n: uploads.append(k))
+    n0 = len(uploads)
+    assert n0 == 57
+    m._sync.sync(m, lambda k, p, n: uploads.append(k))
+    assert len(uploads) == n0                      # unchanged -> no upload
+    m.dres0.conv.weight.data.fill_(1.0)            # invisible to (data_ptr, _version) ...
+    m._sync.sync(m, lambda k, p, n: uploads.append(k))
+    assert len(uploads) == n0
+    m.sync_params()                                # ... hence the explicit call
+    m._sync.sync(m, lambda k, p, n: uploads.append(k))
+    assert len(uploads) == 2 * n0
+    m.load_state_dict(m.state_dict())
+    m._sync.sync(m, lambda k, p, n: uploads.append(k))
+    assert len(uploads) == 3 * n0
+    m.eval()
+    m._sync.sync(m, lambda k, p, n: uploads.append(k))
+    assert len(uploads) == 4 * n0
+    with torch.no_grad():
+        m.dres1.gn.bias.add_(1.0)                  # bumps _version
+    m._sync.sync(m, lambda k, p, n: uploads.append(k))
+    assert len(uploads) == 5 * n0
+    # content fingerprint (DFM_PARAM_CHECK=1 path)
+    f0 = modules._ParamSync.fingerprint(m)
+    m.dres0.conv.weight.data.mul_(0.5)
+    assert not torch.equal(f0, modules._ParamSync.fingerprint(m))
+    # forward-only guard in training mode
+    m.train()
+    with pytest.raises(RuntimeError, match='forward-only'):
+        m._forward_only(torch.zeros(1))
+    with torch.no_grad():
+        m._forward_only(torch.zeros(1))
+    m.eval()
+    m._forward_only(torch.zeros(1))
+    with pytest.raises(AssertionError):
+        modules.DfMBackbone(in_channels=32, depth_cfg=syn.depth_cfg_for(8),
+                            norm_cfg=dict(type='GN', num_groups=16))
+    meta = dict(pcd_rotation=np.eye(3), pcd_scale_factor=1.0)
+    modules._require_identity_3d_aug(meta)
+    with pytest.raises(NotImplementedError):
+        modules._require_identity_3d_aug(dict(pcd_scale_factor=1.05))
+    with pytest.raises(NotImplementedError):
+        modules._require_identity_3d_aug(dict(pcd_horizontal_flip=True))

@@ -114,6 +114,28 @@ def test_neck_matches_reference_fixture(name):
     assert torch.allclose(y, torch.from_numpy(gold['y']), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize('name', ['neck_dfm_mt', 'neck_imvoxel_mt'])
+def test_neck_multitile_fixture(name):
+    """The multi-tile neck fixtures (37 x 21 x 12 voxels = 3 x 3 tiles of the CUDA kernel,
+    ragged edges): inputs regenerate from the seed (checksums stored), the oracle restatement
+    reproduces the verbatim reference output."""
+    from depth_from_motion_b200 import modules
+    from tests.util import make_neck_mt_case
+    gold = np.load(os.path.join(GOLDEN, name + '.npz'))
+    rng, x = make_neck_mt_case(name)
+    assert float(x.double().sum()) == float(gold['x_sum'])
+    assert float(x.double().abs().sum()) == float(gold['x_abs'])
+    mod = (modules.DfMNeck(64, 256, num_frames=2) if name == 'neck_dfm_mt'
+           else modules.OutdoorImVoxelNeck(64, 256))
+    sd = syn.make_neck_params(rng, mod.state_dict())
+    with torch.no_grad():
+        y = (O.dfm_neck_forward(sd, x, 64) if name == 'neck_dfm_mt'
+             else O.imvoxel_neck_forward(sd, x))[0]
+    ref = torch.from_numpy(gold['y'])
+    assert y.shape == ref.shape == (1, 256, 21, 37)
+    assert torch.allclose(y, ref, rtol=1e-4, atol=1e-4)
+
+
 def test_depth_tables():
     cfg = syn.depth_cfg_for(72)
     d = O.downsampled_depth(cfg)
