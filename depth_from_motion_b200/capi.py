@@ -35,6 +35,10 @@ SYMBOLS = (
     'dfm_neck_forward', 'dfm_frustum_create', 'dfm_frustum_destroy',
     'dfm_frustum_set_param', 'dfm_frustum_missing_params', 'dfm_frustum_forward',
     'dfm_pipeline_forward_host',
+    'dfm_bev_hourglass_create', 'dfm_bev_hourglass_destroy', 'dfm_bev_hourglass_set_param',
+    'dfm_bev_hourglass_missing_params', 'dfm_bev_hourglass_forward',
+    'dfm_anchor_head_create', 'dfm_anchor_head_destroy', 'dfm_anchor_head_set_param',
+    'dfm_anchor_head_missing_params', 'dfm_anchor_head_forward',
 )
 
 
@@ -80,6 +84,18 @@ class FrustumDesc(ctypes.Structure):
                  'depth_factor', 'nx', 'ny', 'nz')] + \
                [('depth_min', c_float), ('depth_max', c_float),
                 ('conv_impl', c_int)]
+
+
+class BevDesc(ctypes.Structure):
+    """``dfm_bev_desc_t``."""
+    _fields_ = [(n, c_int) for n in ('in_channels', 'out_channels', 'ny', 'nx', 'conv_impl')]
+
+
+class AnchorHeadDesc(ctypes.Structure):
+    """``dfm_anchor_head_desc_t``."""
+    _fields_ = [(n, c_int) for n in
+                ('in_channels', 'feat_channels', 'num_convs', 'cls_channels', 'reg_channels',
+                 'dir_channels', 'ny', 'nx', 'conv_impl')]
 
 
 _lib = None
@@ -149,6 +165,16 @@ def lib():
     L.dfm_pipeline_forward_host.argtypes = [vp, vp, vp, vp, vp, POINTER(Geometry),
                                             POINTER(c_double), c_int, c_int, vp, vp, vp,
                                             vp, vp]
+    L.dfm_bev_hourglass_create.argtypes = [POINTER(BevDesc), POINTER(vp)]
+    L.dfm_bev_hourglass_destroy.argtypes = [vp]
+    L.dfm_bev_hourglass_set_param.argtypes = [vp, c_char_p, vp, c_longlong]
+    L.dfm_bev_hourglass_missing_params.argtypes = [vp]
+    L.dfm_bev_hourglass_forward.argtypes = [vp, vp, vp, vp, vp]
+    L.dfm_anchor_head_create.argtypes = [POINTER(AnchorHeadDesc), POINTER(vp)]
+    L.dfm_anchor_head_destroy.argtypes = [vp]
+    L.dfm_anchor_head_set_param.argtypes = [vp, c_char_p, vp, c_longlong]
+    L.dfm_anchor_head_missing_params.argtypes = [vp]
+    L.dfm_anchor_head_forward.argtypes = [vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -257,6 +257,8 @@ int conv_simt_dispatch(const L& ld, const ConvW& w, float* out, const dfm::ConvG
   CASE(64, 32);
   CASE(32, 64);
   CASE(64, 64);
+  CASE(160, 64);
+  CASE(128, 64);
   CASE(64, 128);
   CASE(128, 128);
   CASE(128, 256);
@@ -1287,3 +1289,4 @@ int dfm_depth_head_forward(const float* d_cost, const float* d_depth_samples, in
 #include "neck_api.inc"
 #include "frustum_api.inc"
 #include "pipeline_api.inc"
+#include "bev_api.inc"

@@ -265,3 +265,56 @@ def make_waymo_sample(seed, num_frames, num_views=5, channels=64, feat_hw=WAYMO_
                 img_crop_offset=list(crop), flip=flip, num_views=num_views,
                 num_ref_frames=num_frames - 1)
     return feats, meta
+
+
+def make_bev_params(rng, in_channels=160, c=64):
+    """Random BEVHourglass parameters keyed like the reference state_dict
+    (backbones/bev_hourglass.py:25-32, 53-119; GroupNorm variant of the KITTI config)."""
+    p = {}
+
+    def gn(name, ch):
+        p[name + '.weight'] = (0.5 + rng.random_sample(ch)).astype(np.float32)
+        p[name + '.bias'] = (0.2 * rng.standard_normal(ch)).astype(np.float32)
+
+    p['compress_conv.conv.weight'] = _kaiming(rng, (c, in_channels, 3, 3), in_channels * 9)
+    gn('compress_conv.gn', c)
+    hg = 'bev_hourglass.'
+    for sub, ci, co, seq in (('conv1', c, 2 * c, True), ('conv2', 2 * c, 2 * c, False),
+                             ('conv3', 2 * c, 2 * c, True), ('conv4', 2 * c, 2 * c, True)):
+        pre = f'{hg}{sub}.0' if seq else f'{hg}{sub}'
+        p[pre + '.0.weight'] = _kaiming(rng, (co, ci, 3, 3), ci * 9)
+        gn(pre + '.1', co)
+    p[hg + 'conv5.0.weight'] = _kaiming(rng, (2 * c, 2 * c, 3, 3), 2 * c * 9 / 4)  # (in, out, k, k)
+    gn(hg + 'conv5.1', 2 * c)
+    p[hg + 'conv6.0.weight'] = _kaiming(rng, (2 * c, c, 3, 3), 2 * c * 9 / 4)
+    gn(hg + 'conv6.1', c)
+    return {k: torch.from_numpy(v) for k, v in p.items()}
+
+
+def make_anchor_head_params(rng, c=64, num_convs=2, num_anchors=6, num_classes=3,
+                            box_code_size=7):
+    """Random LIGAAnchor3DHead parameters (dense_heads/liga_anchor3d_head.py:37-75): 6 anchors
+    (3 classes x 2 rotations, KITTI config) -> 18 class / 42 box / 12 direction channels."""
+    p = {}
+    for br in ('cls_convs', 'reg_convs'):
+        for i in range(num_convs):
+            p[f'{br}.{i}.conv.weight'] = _kaiming(rng, (c, c, 3, 3), c * 9)
+            p[f'{br}.{i}.gn.weight'] = (0.5 + rng.random_sample(c)).astype(np.float32)
+            p[f'{br}.{i}.gn.bias'] = (0.2 * rng.standard_normal(c)).astype(np.float32)
+    for name, co, k in (('conv_cls', num_anchors * num_classes, 3),
+                        ('conv_reg', num_anchors * box_code_size, 3),
+                        ('conv_dir_cls', num_anchors * 2, 1)):
+        p[name + '.weight'] = _kaiming(rng, (co, c, k, k), c * k * k, gain=0.7)
+        p[name + '.bias'] = (0.1 * rng.standard_normal(co)).astype(np.float32)
+    return {k: torch.from_numpy(v) for k, v in p.items()}
+
+
+BEV_CASE = dict(seed=91, nz=5, ny=44, nx=36)   # 3 x 5 tiles of the 16 x 8 conv tile, ragged
+
+
+def make_bev_case(seed=91, nz=5, ny=44, nx=36, cv=32):
+    """volume_feat [1, cv, nz, ny, nx] (what FrustumToVoxel returns) + parameters of the 2-D
+    stage; the KITTI config has nz=5, ny=304, nx=288."""
+    rng = np.random.RandomState(seed)
+    vol = torch.from_numpy(rng.standard_normal((1, cv, nz, ny, nx)).astype(np.float32)).relu()
+    return dict(volume=vol, bev=make_bev_params(rng, cv * nz), head=make_anchor_head_params(rng))

@@ -281,6 +281,56 @@ int dfm_pipeline_forward_host(dfm_backbone_t* bb, dfm_frustum_t* fr, const float
                               int pad_w, const float* h_depth_samples, float* h_voxel,
                               float* h_depth_preds, float* h_cost, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * The 2-D BEV stage behind FrustumToVoxel (north_star's "3D box
+ * regressions"): BEVHourglass (mmdet3d/models/backbones/bev_hourglass.py:11-137, GroupNorm
+ * variant of configs/dfm/dfm_r34_1x8_kitti-3d-3class.py:146-150) and LIGAAnchor3DHead's
+ * forward (mmdet3d/models/dense_heads/liga_anchor3d_head.py:37-128).  All tensors NCHW fp32.
+ * ---------------------------------------------------------------------------------- */
+typedef struct dfm_bev_hourglass dfm_bev_hourglass_t;
+typedef struct dfm_bev_desc {
+  int in_channels;  /* 160 = 32 channels x 5 height slices (detectors/dfm.py:427-428) */
+  int out_channels; /* 64                                                            */
+  int ny, nx;       /* BEV grid, both multiples of 4 (304 x 288)                      */
+  int conv_impl;    /* DFM_CONV_*                                                     */
+} dfm_bev_desc_t;
+int dfm_bev_hourglass_create(const dfm_bev_desc_t* desc, dfm_bev_hourglass_t** out);
+int dfm_bev_hourglass_destroy(dfm_bev_hourglass_t* b);
+/* Reference state_dict keys: "compress_conv.conv.weight", "compress_conv.gn.{weight,bias}",
+ * "bev_hourglass.conv1.0.0.weight", "bev_hourglass.conv1.0.1.{weight,bias}",
+ * "bev_hourglass.conv2.0.weight", ..., "bev_hourglass.conv5.0.weight" (ConvTranspose2d layout
+ * in x out), "bev_hourglass.conv6.1.bias". */
+int dfm_bev_hourglass_set_param(dfm_bev_hourglass_t* b, const char* name, const float* h_data,
+                                long long numel);
+int dfm_bev_hourglass_missing_params(const dfm_bev_hourglass_t* b);
+/* BEVHourglass.forward (:39-50): d_x [in][ny][nx] -> d_prehg (optional) and d_out, both
+ * [out][ny][nx] (spatial_features_2d_prehg, spatial_features_2d). */
+int dfm_bev_hourglass_forward(dfm_bev_hourglass_t* b, const float* d_x, float* d_prehg,
+                              float* d_out, void* stream);
+
+typedef struct dfm_anchor_head dfm_anchor_head_t;
+typedef struct dfm_anchor_head_desc {
+  int in_channels, feat_channels; /* 64, 64                                            */
+  int num_convs;                  /* cls_convs / reg_convs depth (2)                   */
+  int cls_channels;               /* num_anchors * num_classes      (18)               */
+  int reg_channels;               /* num_anchors * box_code_size    (42)               */
+  int dir_channels;               /* num_anchors * 2, 0 without direction classifier   */
+  int ny, nx;
+  int conv_impl;
+} dfm_anchor_head_desc_t;
+int dfm_anchor_head_create(const dfm_anchor_head_desc_t* desc, dfm_anchor_head_t** out);
+int dfm_anchor_head_destroy(dfm_anchor_head_t* h);
+/* Keys: "cls_convs.<i>.conv.weight", "cls_convs.<i>.gn.{weight,bias}", "reg_convs.<i>...",
+ * "conv_cls.{weight,bias}", "conv_reg.{weight,bias}", "conv_dir_cls.{weight,bias}". */
+int dfm_anchor_head_set_param(dfm_anchor_head_t* h, const char* name, const float* h_data,
+                              long long numel);
+int dfm_anchor_head_missing_params(const dfm_anchor_head_t* h);
+/* LIGAAnchor3DHead.forward_single (:108-128): d_x [64][ny][nx] -> cls_score
+ * [cls_channels][ny][nx], bbox_pred [reg_channels][ny][nx], dir_cls_preds
+ * [dir_channels][ny][nx]. */
+int dfm_anchor_head_forward(dfm_anchor_head_t* h, const float* d_x, float* d_cls, float* d_bbox,
+                            float* d_dir, void* stream);
+
 /* Re-entrancy: handles may live on different devices and be driven from different host
  * threads only if each thread owns its device; per-device scratch (K-slice partial sums,
  * lifting staging, the host-copy side stream) and the profiling record are shared by all

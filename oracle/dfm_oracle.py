@@ -29,6 +29,10 @@ follows (paths relative to the reference checkout, commit e2321189):
     f1  FrustumToVoxel.forward
                             mmdet3d/models/necks/feature_transformation.py:68-187
                             mmdet3d/models/detectors/dfm.py:174-211 (voxel grid)
+    f3  BEVHourglass.forward + LIGAAnchor3DHead.forward_single (section 8(f) row 3)
+                            mmdet3d/models/backbones/bev_hourglass.py:11-137
+                            mmdet3d/models/dense_heads/liga_anchor3d_head.py:37-128
+                            mmdet3d/models/detectors/dfm.py:426-432
 
 Third-party arithmetic: every number on this path is produced by PyTorch ATen
 ops in the reference (README pins torch 1.9 + mmcv-full 1.6.0, the latter used
@@ -533,6 +537,62 @@ def frustum_to_voxel_forward(p, stereo_feat, stereo_feat_softmax, img_metas,
     for i in range(num_3dconvs):
         voxel = _conv_module(voxel, p, f'voxel_convs.{i}.0')
     return F.avg_pool3d(voxel, (4, 1, 1), stride=(4, 1, 1))
+
+
+# ----------------------------------------------------------------------------
+# f3  BEVHourglass + LIGAAnchor3DHead.forward: the 2-D
+# stage that turns the voxel features into class scores and 3-D box regressions
+# ----------------------------------------------------------------------------
+def _gn2d(x, p, prefix, groups=32):
+    return F.group_norm(x, groups, p[prefix + '.weight'], p[prefix + '.bias'], GN_EPS)
+
+
+def bev_hourglass_forward(p, spatial_features):
+    """BEVHourglass.forward with norm_cfg GN (backbones/bev_hourglass.py:39-50) and
+    hourglass2d.forward (:121-137) with presqu = postsqu = None; convbn = Conv2d(bias=False) +
+    GroupNorm(32) (models/utils/conv_modules.py:6-24).  Returns (prehg, spatial_features_2d)."""
+    x = F.relu(_gn2d(F.conv2d(spatial_features, p['compress_conv.conv.weight'], None, 1, 1),
+                     p, 'compress_conv.gn'))                                   # :40
+    hg = 'bev_hourglass.'
+    out = F.relu(_gn2d(F.conv2d(x, p[hg + 'conv1.0.0.weight'], None, 2, 1),
+                       p, hg + 'conv1.0.1'))                                   # :122
+    pre = F.relu(_gn2d(F.conv2d(out, p[hg + 'conv2.0.weight'], None, 1, 1),
+                       p, hg + 'conv2.1'))                                     # :123-127
+    out = F.relu(_gn2d(F.conv2d(pre, p[hg + 'conv3.0.0.weight'], None, 2, 1),
+                       p, hg + 'conv3.0.1'))                                   # :129
+    out = F.relu(_gn2d(F.conv2d(out, p[hg + 'conv4.0.0.weight'], None, 1, 1),
+                       p, hg + 'conv4.0.1'))                                   # :130
+    post = F.relu(_gn2d(F.conv_transpose2d(out, p[hg + 'conv5.0.weight'], None, 2, 1, 1),
+                        p, hg + 'conv5.1') + pre)                              # :135
+    out = _gn2d(F.conv_transpose2d(post, p[hg + 'conv6.0.weight'], None, 2, 1, 1),
+                p, hg + 'conv6.1')                                             # :137
+    return x, out                                                              # :47-48
+
+
+def liga_anchor3d_head_forward(p, x, num_convs=2):
+    """LIGAAnchor3DHead.forward_single (dense_heads/liga_anchor3d_head.py:108-128) with the
+    layers of _init_layers (:37-75): num_convs x ConvModule(3x3, GN, ReLU) per branch, 3x3
+    conv_cls / conv_reg with bias, 1x1 conv_dir_cls on the CLASSIFICATION features."""
+    cls_feats = reg_feats = x
+    for i in range(num_convs):
+        cls_feats = F.relu(_gn2d(F.conv2d(cls_feats, p[f'cls_convs.{i}.conv.weight'], None, 1, 1),
+                                 p, f'cls_convs.{i}.gn'))
+        reg_feats = F.relu(_gn2d(F.conv2d(reg_feats, p[f'reg_convs.{i}.conv.weight'], None, 1, 1),
+                                 p, f'reg_convs.{i}.gn'))
+    cls_score = F.conv2d(cls_feats, p['conv_cls.weight'], p['conv_cls.bias'], 1, 1)
+    bbox_pred = F.conv2d(reg_feats, p['conv_reg.weight'], p['conv_reg.bias'], 1, 1)
+    dir_cls_preds = F.conv2d(cls_feats, p['conv_dir_cls.weight'], p['conv_dir_cls.bias'])
+    return cls_score, bbox_pred, dir_cls_preds
+
+
+def dfm_bev_stage(p_bev, p_head, volume_feat, num_convs=2):
+    """DfM.simple_test after feature_transformation (detectors/dfm.py:426-432): height
+    compression view, backbone_3d, bbox_head_3d([bev_feat]) -> (cls_score, bbox_pred,
+    dir_cls_preds) of the single level."""
+    _, cv, nz, ny, nx = volume_feat.shape
+    bev_feat = volume_feat.reshape(-1, cv * nz, ny, nx)
+    _, bev = bev_hourglass_forward(p_bev, bev_feat)
+    return liga_anchor3d_head_forward(p_head, bev, num_convs)
 
 
 def tf32_round(x):

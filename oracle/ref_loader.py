@@ -152,6 +152,42 @@ def _exec(modname, relpath):
     return mod
 
 
+def _liga_head_class():
+    """LIGAAnchor3DHead derives from mmdet3d's Anchor3DHead (mmdet / mmcv-ops bases that are
+    not installable here).  Its forward path needs only the constructor attributes below plus
+    two methods, `_init_layers` and `forward_single` (liga_anchor3d_head.py:37-75, 108-128):
+    both are executed VERBATIM from the reference file (ast source segments) on this holder."""
+    import ast
+    rel = 'mmdet3d/models/dense_heads/liga_anchor3d_head.py'
+    src = open(os.path.join(REFERENCE_ROOT, rel)).read()
+    cls = [n for n in ast.parse(src).body
+           if isinstance(n, ast.ClassDef) and n.name == 'LIGAAnchor3DHead'][0]
+    ns = dict(torch=torch, nn=nn, ConvModule=_ConvModule)
+    for node in cls.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ('_init_layers', 'forward_single'):
+            exec(compile(ast.get_source_segment(src, node), rel, 'exec'), ns)
+
+    class LIGAAnchor3DHead(nn.Module):
+        """Attribute holder: what Anchor3DHead.__init__ sets before `_init_layers()`
+        (dense_heads/anchor3d_head.py:73-96)."""
+
+        def __init__(self, num_classes, in_channels, feat_channels, num_anchors,
+                     box_code_size=7, use_direction_classifier=True, num_convs=2,
+                     norm_cfg=None):
+            super().__init__()
+            self.num_classes, self.in_channels = num_classes, in_channels
+            self.feat_channels, self.num_anchors = feat_channels, num_anchors
+            self.box_code_size = box_code_size
+            self.use_direction_classifier = use_direction_classifier
+            self.num_convs, self.norm_cfg = num_convs, norm_cfg
+            self._init_layers()
+
+        _init_layers = ns['_init_layers']
+        forward_single = ns['forward_single']
+
+    return LIGAAnchor3DHead
+
+
 _LOADED = None
 
 
@@ -216,6 +252,7 @@ def load_reference():
                    'mmdet3d/models/utils/conv_modules.py')
         sys.modules['mmdet3d.models.utils'].hourglass = cm.hourglass
         sys.modules['mmdet3d.models.utils'].convbn_3d = cm.convbn_3d
+        sys.modules['mmdet3d.models.utils'].convbn = cm.convbn
 
         bb = _exec('mmdet3d.models.backbones.dfm_backbone',
                    'mmdet3d/models/backbones/dfm_backbone.py')
@@ -228,6 +265,8 @@ def load_reference():
                    'mmdet3d/models/necks/dfm_neck.py')
         ft = _exec('mmdet3d.models.necks.feature_transformation',
                    'mmdet3d/models/necks/feature_transformation.py')
+        bh = _exec('mmdet3d.models.backbones.bev_hourglass',
+                   'mmdet3d/models/backbones/bev_hourglass.py')
 
         ns = types.SimpleNamespace(
             points_cam2img=su.points_cam2img,
@@ -241,6 +280,8 @@ def load_reference():
             ResModule=iv.ResModule,
             DfMNeck=dn.DfMNeck,
             FrustumToVoxel=ft.FrustumToVoxel,
+            BEVHourglass=bh.BEVHourglass,
+            LIGAAnchor3DHead=_liga_head_class(),
             ConvModule=_ConvModule,
         )
         _LOADED = ns

@@ -104,6 +104,29 @@ def neck_multitile_case(ns):
         print(name, tuple(x.shape), '->', tuple(y.shape), float(y.abs().max()))
 
 
+def bev_stage_case(ns):
+    """SURVEY.md section 8(f) row 3 / north_star's "3D box regressions": the reference
+    BEVHourglass (verbatim) + LIGAAnchor3DHead._init_layers / forward_single (verbatim method
+    bodies) on a synthetic voxel feature; inputs regenerate from the seed."""
+    c = syn.make_bev_case(**syn.BEV_CASE)
+    gn = dict(type='GN', num_groups=32, requires_grad=True)
+    bev = ns.BEVHourglass(160, 64, norm_cfg=gn).eval()
+    head = ns.LIGAAnchor3DHead(3, 64, 64, 6, norm_cfg=gn).eval()
+    bev.load_state_dict(c['bev'], strict=True)
+    head.load_state_dict(c['head'], strict=True)
+    v = c['volume']
+    with torch.no_grad():
+        x = v.view(-1, v.shape[1] * v.shape[2], v.shape[3], v.shape[4])   # dfm.py:427-428
+        prehg, feat = bev(x)
+        cls, box, dirc = head.forward_single(feat)
+    np.savez_compressed(os.path.join(HERE, 'bev_stage.npz'), prehg=prehg.numpy(),
+                        bev=feat.numpy(), cls_score=cls.numpy(), bbox_pred=box.numpy(),
+                        dir_cls_preds=dirc.numpy(),
+                        x_sum=np.float64(v.double().sum().item()))
+    print('bev_stage', tuple(cls.shape), tuple(box.shape), tuple(dirc.shape),
+          float(box.abs().max()))
+
+
 FRUSTUM_CASE = dict(seed=31, h=32, w=64, num_planes=8, n_voxels=(24, 20, 8))
 
 
@@ -145,6 +168,9 @@ def main():
     if 'frustum' in sys.argv[1:]:
         frustum_case(ns)
         return
+    if 'bev' in sys.argv[1:]:
+        bev_stage_case(ns)
+        return
     if 'neck_mt' in sys.argv[1:]:
         neck_multitile_case(ns)
         return
@@ -153,6 +179,7 @@ def main():
     neck_case(ns)
     neck_multitile_case(ns)
     frustum_case(ns)
+    bev_stage_case(ns)
 
 
 if __name__ == '__main__':

@@ -190,3 +190,41 @@ def test_voxel_sample_matches_reference_source(flip, aligned):
     assert a.shape == b.shape == (1, 6, 4, 8, 16)
     assert torch.equal(a, b)
     assert float(a.abs().sum()) > 0
+
+
+def test_bev_stage_matches_reference_fixture():
+    """oracle restatement of BEVHourglass + LIGAAnchor3DHead
+    (class scores, 3-D box regressions, direction logits) against the verbatim reference run."""
+    gold = np.load(os.path.join(GOLDEN, 'bev_stage.npz'))
+    c = syn.make_bev_case(**syn.BEV_CASE)
+    assert float(c['volume'].double().sum()) == float(gold['x_sum'])
+    v = c['volume']
+    with torch.no_grad():
+        prehg, bev = O.bev_hourglass_forward(c['bev'], v.reshape(1, -1, v.shape[3], v.shape[4]))
+        outs = O.dfm_bev_stage(c['bev'], c['head'], v)
+    for got, key in ((prehg, 'prehg'), (bev, 'bev'), (outs[0], 'cls_score'),
+                     (outs[1], 'bbox_pred'), (outs[2], 'dir_cls_preds')):
+        ref = torch.from_numpy(gold[key])
+        assert got.shape == ref.shape, key
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5), key
+    assert outs[0].shape[1] == 18 and outs[1].shape[1] == 42 and outs[2].shape[1] == 12
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/mmdet3d'), reason='reference tree not mounted')
+def test_bev_stage_oracle_equals_reference_source():
+    """Bit-for-bit against the reference classes executed in place (only where mounted)."""
+    from oracle.ref_loader import load_reference
+    ns = load_reference()
+    c = syn.make_bev_case(seed=5, nz=5, ny=12, nx=16)
+    gn = dict(type='GN', num_groups=32, requires_grad=True)
+    bev = ns.BEVHourglass(160, 64, norm_cfg=gn).eval()
+    head = ns.LIGAAnchor3DHead(3, 64, 64, 6, norm_cfg=gn).eval()
+    bev.load_state_dict(c['bev'], strict=True)
+    head.load_state_dict(c['head'], strict=True)
+    x = c['volume'].reshape(1, 160, 12, 16)
+    with torch.no_grad():
+        _, feat = bev(x)
+        ref = head.forward_single(feat)
+        got = O.dfm_bev_stage(c['bev'], c['head'], c['volume'])
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
