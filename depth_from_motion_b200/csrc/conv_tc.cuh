@@ -35,6 +35,7 @@
 //     DFM_TC_DEBUG=<bits> disables roles (1 loaders, 2 epilogue, 8 proxy fence, 16 the
 //     loaders' global loads, 32 the loaders' shared-memory stores).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -474,6 +475,7 @@ __device__ __forceinline__ float4 ld_act(const float4* p) {
 
 template <int NT>  // number of input terms (compile-time: sizes the in-flight registers)
 struct SrcLoader8 {
+  static constexpr bool kTma = false;
   Src s;
   int C, H, W;
   // items of a thread in flight at once: at most 12 float4 (48 registers) of raw loads
@@ -524,6 +526,7 @@ struct SrcLoader8 {
 };
 
 struct WarpLoader8 {
+  static constexpr bool kTma = false;
   WarpLoader w;
   static constexpr int BATCH = 1;
   struct Raw {
@@ -568,6 +571,106 @@ struct WarpLoader8 {
     }
   }
 };
+
+// ----------------------------------------------------------------------------------
+// TMA loader (stride-2 convs): the input was written once by presplit_kernel as bf16 hi / lo
+// pairs in the "pre-split" layout [plane][hi|lo][8-channel chunk][y][x][8 x bf16] (16 bytes per
+// (chunk, voxel), the same 4 bytes per value as fp32), viewed by a rank-4 tensor map
+// {8, W, H, planes*2*chunks}.  One elected thread then stages a whole brick with
+// cp.async.bulk.tensor: per (hi|lo, x/y parity class) ONE box of 9 x 17 positions x 2 chunks with
+// element strides (2, 2) -- the parity de-interleave of the stride-2 brick -- and out-of-range
+// halo positions arrive as zeros.  No loader warp touches the data: the fused GroupNorm /
+// ReLU / residual transform and the bf16 split happened once, in the producer pass.
+// (tests/probe/probe_tma.cu pins the box / stride / zero-fill / byte-count semantics.)
+// ----------------------------------------------------------------------------------
+struct TmaLoader8 {
+  static constexpr bool kTma = true;
+  static constexpr int BATCH = 1;
+  CUtensorMap map;
+  int nch_total;  // channels / 8 of the pre-split tensor
+  struct Raw {};
+  __device__ __forceinline__ void issue(int, int, int, int, Raw&) const {}
+  __device__ __forceinline__ void finish(const Raw&, int, float v[8]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+};
+constexpr int TMA_S2_CLS = 17 * 9;                         // rows of one parity class, one chunk
+constexpr int TMA_S2_CLSR = (2 * TMA_S2_CLS + 7) / 8 * 8;  // two chunks, padded to 128 bytes
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c1, int c2,
+                                            int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(map), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
+// producer pass: value = the fused input transform of `ld` (<= 3 terms), split to bf16 hi / lo,
+// written in the pre-split layout.  out: [Z][2][C/8][H][W] uint4.
+template <int NT>
+__global__ void __launch_bounds__(256)
+presplit_kernel(const SrcLoader8<NT> ld, int Z, uint4* __restrict__ out) {
+  const int nch = ld.C >> 3;
+  const long long HW = (long long)ld.H * ld.W;
+  const long long total = (long long)Z * HW * nch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i % nch);
+    const long long v = i / nch;
+    const int z = (int)(v / HW);
+    const long long pos = v - (long long)z * HW;
+    const int y = (int)(pos / ld.W), x = (int)(pos - (long long)y * ld.W);
+    typename SrcLoader8<NT>::Raw r;
+    ld.issue(z, y, x, chunk * 8, r);
+    float val[8];
+    ld.finish(r, chunk * 8, val);
+    uint4* hi = out + ((long long)(z * 2) * nch + chunk) * HW + pos;
+    split_store(val, reinterpret_cast<uint8_t*>(hi), reinterpret_cast<uint8_t*>(hi + nch * HW));
+  }
+}
+inline bool presplit_launch(const Src& s, int C, int Z, int H, int W, uint4* out, cudaStream_t st) {
+  const long long total = (long long)Z * H * W * (C / 8);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+  if (s.n == 1) presplit_kernel<1><<<blocks, 256, 0, st>>>(SrcLoader8<1>{s, C, H, W}, Z, out);
+  else if (s.n == 2) presplit_kernel<2><<<blocks, 256, 0, st>>>(SrcLoader8<2>{s, C, H, W}, Z, out);
+  else presplit_kernel<3><<<blocks, 256, 0, st>>>(SrcLoader8<3>{s, C, H, W}, Z, out);
+  return cudaGetLastError() == cudaSuccess;
+}
+
+// host: tensor map over a pre-split buffer for the stride-2 brick boxes
+inline bool make_presplit_map_s2(CUtensorMap* map, const void* base, int W, int H,
+                                 long long slabs, std::string* err) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                               const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) !=
+            cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+      if (err) *err = "cuTensorMapEncodeTiled is not available from this driver";
+      return false;
+    }
+    encode = (EncodeFn)fn;
+  }
+  const cuuint64_t dims[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)slabs};
+  const cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  const cuuint32_t box[4] = {8, 17, 33, 2};   // un-strided extent: 9 x 17 positions, 2 chunks
+  const cuuint32_t estr[4] = {1, 2, 2, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
 
 struct TcParams {
   const uint8_t* wimg;
@@ -638,14 +741,21 @@ __device__ __forceinline__ bool tc_walk_next(const TcParams& p, TcWalk& w, TcIte
 // ----------------------------------------------------------------------------------
 template <int MODE, int CIN, int NCTA, class Loader>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p,
-                                                                 const Loader ld) {
+                                                                 const __grid_constant__ Loader ld) {
   using M = TcMode<MODE>;
+  constexpr bool TMA = Loader::kTma;
+  static_assert(!TMA || MODE == TC_S2, "the TMA loader serves the stride-2 brick only");
   constexpr int CG = M::CG < CIN ? M::CG : CIN;  // channels per stage
   constexpr int NCH = CG / 8;                    // 16-byte channel chunks per stage
   constexpr int NCG = CIN / CG;                  // pipeline stages per input plane
-  constexpr uint32_t A_LBO = M::ROWS * 16;
-  constexpr uint32_t A_SBO = (MODE == TC_S2 ? 1 : 1) * M::PITCH * 16;
-  constexpr uint32_t A_HL = NCH * M::ROWS * 16;  // hi -> lo array offset in a stage
+  static_assert(!TMA || NCH == 2, "TMA stride-2 stages hold two 8-channel chunks");
+  // stage layout.  Register loaders: [hi|lo][chunk][ROWS rows] with the four x/y parity classes
+  // of a stride-2 brick inside a chunk's rows.  TMA loader: [hi|lo][class][chunk][153 rows], one
+  // TMA box per (hi|lo, class), each block padded to 128 bytes.
+  constexpr uint32_t S2_CLS16 = TMA ? TMA_S2_CLSR : TMA_S2_CLS;  // class stride, 16-byte rows
+  constexpr uint32_t A_LBO = TMA ? TMA_S2_CLS * 16 : M::ROWS * 16;
+  constexpr uint32_t A_SBO = M::PITCH * 16;
+  constexpr uint32_t A_HL = TMA ? 4 * TMA_S2_CLSR * 16 : NCH * M::ROWS * 16;  // hi -> lo offset
   constexpr uint32_t STAGE_BYTES = 2 * A_HL;
   constexpr uint32_t B_SBO = 128;
   constexpr int SLOT_COLS = M::SLOT_BLOCKS * NCTA;
@@ -683,7 +793,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t w_bar = bar0 + 8u * (2 * M::NSTAGE + 2 * TC_NSLOT);
   if (tid == 0) {
     for (int s = 0; s < M::NSTAGE; ++s) {
-      mbar_init(full_a(s), LG_THREADS / 32);  // one arrival per loader warp of the group
+      // one arrival per loader warp of the group; TMA: the issuing thread's expect_tx arrival
+      mbar_init(full_a(s), TMA ? 1 : LG_THREADS / 32);
       mbar_init(empty_a(s), 1);
     }
     for (int s = 0; s < TC_NSLOT; ++s) {
@@ -732,7 +843,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  if (warp >= 4 && warp < MMA_WARP) {
+  if constexpr (TMA) {
+    if (warp == 4 && lane == 0) {
+      // ============================ TMA producer (one thread) ============================
+      constexpr uint32_t STAGE_TX = 8u * 2u * TMA_S2_CLS * 16u;  // 8 boxes of 2 x 153 x 16 bytes
+      uint32_t stage_ctr = 0;
+      TcWalk walk = tc_walk_begin(p);
+      TcItem it;
+      while (tc_walk_next(p, walk, it)) {
+        const int zi0 = max(M::zi_first(it.z_lo), 0);
+        const int zi1 = min(M::zi_last(it.z_hi - 1), p.Di - 1);
+        const int chunk0 = CIN == 16 ? it.split * 2 : 0;
+        for (int zi = zi0; zi <= zi1; ++zi) {
+#pragma unroll 1
+          for (int cg = 0; cg < NCG; ++cg, ++stage_ctr) {
+            const int s = stage_ctr % M::NSTAGE;
+            mbar_wait(empty_a(s), ((stage_ctr / M::NSTAGE) & 1) ^ 1, p.err);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_a(s)),
+                         "r"(STAGE_TX)
+                         : "memory");
+            const uint32_t st_addr = smem_u32(a_s + s * STAGE_BYTES);
+#pragma unroll
+            for (int hl = 0; hl < 2; ++hl) {
+              const int slab = (zi * 2 + hl) * ld.nch_total + chunk0 + cg * NCH;
+#pragma unroll
+              for (int cls = 0; cls < 4; ++cls)  // class = (x parity) * 2 + (y parity)
+                tma_load_4d(st_addr + hl * A_HL + cls * (TMA_S2_CLSR * 16), &ld.map,
+                            2 * it.x0 - 1 + (cls >> 1), 2 * it.y0 - 1 + (cls & 1), slab, full_a(s));
+            }
+          }
+        }
+      }
+    }
+  }
+  if (TMA && warp >= 4 && warp < MMA_WARP) {
+    // (the loader warps have nothing to do: warp 4's lane 0 issued the TMA boxes above)
+  } else if (warp >= 4 && warp < MMA_WARP) {
     // ============================ loaders ============================
     const int lgrp = (warp - 4) & (LGROUPS - 1);
     const int lt = ((warp - 4) / LGROUPS) * 32 + lane;  // thread index inside the group
@@ -945,8 +1091,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                   const int dy = tap / 3, dx = tap % 3;
-                  const uint32_t a16 =
-                      (uint32_t)((((dx & 1) * 2 + (dy & 1)) * 17 + (dy >> 1)) * M::PITCH + (dx >> 1));
+                  const uint32_t a16 = (uint32_t)(((dx & 1) * 2 + (dy & 1)) * S2_CLS16 +
+                                                  (dy >> 1) * M::PITCH + (dx >> 1));
                   const uint64_t dah = pack64(a_lo_stage + a16, a_desc_hi);
                   const uint64_t dal = pack64(a_lo_stage + a16 + A_HL16, a_desc_hi);
                   if (elect_one()) {
@@ -1365,7 +1511,8 @@ bool tc_launch(const Loader& ld, const TcWeights& w, float* out, double* stats,
                const ConvGeom& g, cudaStream_t st, std::string* err, TcOpts opt = TcOpts()) {
   using M = TcMode<MODE>;
   constexpr int CG = M::CG < CIN ? M::CG : CIN;
-  constexpr size_t STAGE_BYTES = (size_t)2 * (CG / 8) * M::ROWS * 16;
+  constexpr size_t STAGE_BYTES = Loader::kTma ? (size_t)2 * 4 * TMA_S2_CLSR * 16
+                                              : (size_t)2 * (CG / 8) * M::ROWS * 16;
   const size_t smem = w.image_bytes + M::NSTAGE * STAGE_BYTES +
                       (2 * M::NSTAGE + 2 * M::NSLOT) * 8 + 16;
   auto kern = conv_tc_kernel<MODE, CIN, NCTA, Loader>;
@@ -1467,9 +1614,15 @@ bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats
     }
     TcOpts o2 = opt;
     o2.slice_stride = V * 64;
-    const bool launched = mode == TC_S2
-                              ? tc_launch<TC_S2, 16, 64, Loader>(ld, w, part, nullptr, g, st, err, o2)
-                              : tc_launch<TC_S1, 16, 64, Loader>(ld, w, part, nullptr, g, st, err, o2);
+    bool launched = false;
+    if constexpr (Loader::kTma) {
+      if (mode == TC_S2) launched = tc_launch<TC_S2, 16, 64, Loader>(ld, w, part, nullptr, g, st, err, o2);
+      else if (err) *err = "conv_tc: the TMA loader serves stride-2 convs only";
+    } else {
+      launched = mode == TC_S2
+                     ? tc_launch<TC_S2, 16, 64, Loader>(ld, w, part, nullptr, g, st, err, o2)
+                     : tc_launch<TC_S1, 16, 64, Loader>(ld, w, part, nullptr, g, st, err, o2);
+    }
     if (!launched) return false;
     const int blocks = (int)std::min<long long>(148 * 8, (V + 15) / 16);
     kslice_reduce_kernel<<<blocks, 256, 0, st>>>(part, w.nsplit, V, (long long)g.Ho * g.Wo, out,
@@ -1480,6 +1633,10 @@ bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats
     }
     return true;
   }
+  if constexpr (Loader::kTma) {
+    if (err) *err = "conv_tc: the TMA loader serves the K-slice stride-2 convs only";
+    return false;
+  } else {
 #define TC_CASE(MD, CI, NC) \
   if (mode == MD && g.Cin == CI) \
     return tc_launch<MD, CI, NC, Loader>(ld, w, out, stats, g, st, err, opt)
@@ -1491,6 +1648,7 @@ bool tc_dispatch(const Loader& ld, const TcWeights& w, float* out, double* stats
 #undef TC_CASE
   if (err) *err = "conv_tc: unsupported (mode, Cin)";
   return false;
+  }
 }
 
 inline bool tc_conv_src(const Src& s, const TcWeights& w, float* out, double* stats,
@@ -1505,6 +1663,20 @@ inline bool tc_conv_src(const Src& s, const TcWeights& w, float* out, double* st
     return tc_dispatch(ld, w, out, stats, g, st, err, opt);
   }
   SrcLoader8<3> ld{s, g.Cin, g.Hi, g.Wi};
+  return tc_dispatch(ld, w, out, stats, g, st, err, opt);
+}
+// stride-2 conv whose input is a pre-split tensor (presplit_kernel): bricks staged by TMA
+inline bool tc_conv_presplit(const uint4* ps, int channels, const TcWeights& w, float* out,
+                             double* stats, const ConvGeom& g, cudaStream_t st, std::string* err,
+                             TcOpts opt = TcOpts()) {
+  if (tc_mode_of(g) != TC_S2 || !w.kslice || channels != g.Cin) {
+    if (err) *err = "conv_tc: the TMA loader serves the K-slice stride-2 convs only";
+    return false;
+  }
+  TmaLoader8 ld;
+  ld.nch_total = channels / 8;
+  if (!make_presplit_map_s2(&ld.map, ps, g.Wi, g.Hi, (long long)g.Di * 2 * ld.nch_total, err))
+    return false;
   return tc_dispatch(ld, w, out, stats, g, st, err, opt);
 }
 inline bool tc_conv_warp(const WarpLoader& wl, const TcWeights& w, float* out, double* stats,

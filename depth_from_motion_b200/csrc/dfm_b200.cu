@@ -17,6 +17,7 @@
 #include "conv_tc_neck.cuh"
 #include "simt_kernels.cuh"
 #include "frustum_kernels.cuh"
+#include "tail_kernels.cuh"
 
 namespace {
 
@@ -269,7 +270,7 @@ int conv_simt_dispatch(const L& ld, const ConvW& w, float* out, const dfm::ConvG
 }
 
 int gn_finalize(Norm& n, long long V, int groups, cudaStream_t st) {
-  dfm::gn_finalize_kernel<<<1, 64, 0, st>>>(n.sums, n.gamma.p, n.beta.p, n.C, groups, (double)V,
+  dfm::gn_finalize_kernel<<<1, 256, 0, st>>>(n.sums, n.gamma.p, n.beta.p, n.C, groups, (double)V,
                                            1e-5f, n.scale.p, n.shift.p);
   LAUNCH_CHECK();
   return DFM_OK;
@@ -337,6 +338,38 @@ int run_conv(const dfm::Src& s, const ConvW& w, float* out, const dfm::ConvGeom&
         o.zw = zw.w;
         return dfm::tc_conv_src(s, w.tc, out, stats, g, st, err, o);
       }, "src", w, out, g, impl, gn, st, zw);
+}
+
+// Stride-2 conv fed by TMA: one producer pass applies the fused input transform of `s` and
+// writes it pre-split (bf16 hi / lo, brick-friendly layout) into `ps`, then the conv stages its
+// bricks with cp.async.bulk.tensor instead of eight loader warps (conv_tc.cuh, TmaLoader8).
+int run_conv_presplit(const dfm::Src& s, DevBuf& ps, const ConvW& w, float* out,
+                      const dfm::ConvGeom& g, cudaStream_t st, Norm* gn, const ZW& zw) {
+  const long long Vin = (long long)g.Di * g.Hi * g.Wi;
+  DFM_TRY(ps.alloc((size_t)Vin * g.Cin));
+  {
+    ProfScope ps_scope("presplit<" + std::to_string(g.Cin) + ">@" + std::to_string(g.Di) + "x" +
+                           std::to_string(g.Hi) + "x" + std::to_string(g.Wi), 0.0, st);
+    if (!dfm::presplit_launch(s, g.Cin, g.Di, g.Hi, g.Wi, reinterpret_cast<uint4*>(ps.p), st))
+      return fail(DFM_ERR_CUDA, "presplit_kernel launch failed");
+    g_launches.fetch_add(1);
+  }
+  const long long V = (long long)(zw.count_planes ? zw.count_planes : g.Do) * g.Ho * g.Wo;
+  if (gn) CU_TRY(cudaMemsetAsync(gn->sums, 0, 2 * gn->C * sizeof(double), st));
+  {
+    std::string err;
+    ProfScope pc(conv_class("conv_tc", g, "tma"), conv_flops(g), st);
+    dfm::TcOpts o;
+    o.zw_lo = zw.lo;
+    o.zw_hi = zw.hi;
+    o.zw = zw.w;
+    if (!dfm::tc_conv_presplit(reinterpret_cast<const uint4*>(ps.p), g.Cin, w.tc, out,
+                               gn ? gn->sums : nullptr, g, st, &err, o))
+      return fail(DFM_ERR_CUDA, err);
+  }
+  g_launches.fetch_add(2);  // conv + slice reduce
+  g_tc_launches.fetch_add(1);
+  return gn ? gn_finalize(*gn, V, 32, st) : DFM_OK;
 }
 
 int run_conv_warp(const dfm::WarpLoader& ld, const ConvW& w, float* out, const dfm::ConvGeom& g,
@@ -444,6 +477,7 @@ int make_warp_geom(const dfm_geometry_t* gm, int Hf, int Wf, int csf, int fsf, d
 struct Tower {
   ConvW dres0, dres1, c1, c2, c3, c4, c5, c6, p0;
   DevBuf p1w;  // [27][32]
+  std::vector<float> p1w_host;  // same, host copy: kernel-parameter weights of logits_conv_kernel
   ConvW p1tc;  // the 32->1 logit conv zero-padded to 32 output channels for the tensor cores
   // z-invariance of the cur-frame half: dres0 split into its cur- and
   // prev-channel halves (stereo); the cur contribution is computed on 5 replicated planes
@@ -452,13 +486,14 @@ struct Tower {
   DevBuf cls5, cls3;
   Norm g0, g1, gc1, gc2, gc3, gc4, gc5, gc6, gp0;
   DevBuf raw0, raw1, b1, b2, b3, b4, b5, b6, cur, p0b, logit;
+  DevBuf ps0, ps2;  // pre-split (bf16 hi / lo) inputs of the two stride-2 convs, read by TMA
 };
 
 struct dfm_backbone {
   dfm_backbone_desc_t d;
   int D, Ho, Wo;
   Tower st, mo;
-  DevBuf cur_nhwc, prev_nhwc, depths, wagg, cost, volume_dbg;
+  DevBuf cur_nhwc, prev_nhwc, depths, wagg, waggT, cost, volume_dbg;
   // NCHW staging of the host-buffer entry point, double-buffered so that the next pair can be
   // copied in (dfm_backbone_prefetch_host) while the current one is being processed
   struct HostStage {
@@ -524,7 +559,7 @@ int tower_alloc(Tower& t, int D, int Ho, int Wo, int cv) {
 
 void tower_release(Tower& t) {
   for (DevBuf* b : {&t.raw0, &t.raw1, &t.b1, &t.b2, &t.b3, &t.b4, &t.b5, &t.b6, &t.cur, &t.p0b,
-                    &t.logit, &t.p1w, &t.cls5, &t.cls3})
+                    &t.logit, &t.p1w, &t.cls5, &t.cls3, &t.ps0, &t.ps2})
     b->release();
   for (Norm* n : {&t.g0, &t.g1, &t.gc1, &t.gc2, &t.gc3, &t.gc4, &t.gc5, &t.gc6, &t.gp0})
     n->release();
@@ -622,6 +657,7 @@ int tower_set_param(Tower& t, bool mono, int cin0, int cv, const std::string& na
     for (int c = 0; c < cv; ++c)
       for (int k = 0; k < 27; ++k) padded[(size_t)c * 27 + k] = h[(size_t)c * 27 + k];
     DFM_TRY(set_conv(t.p1tc, padded.data(), (long long)padded.size(), cv, cv, 0, dfm::TC_S1));
+    t.p1w_host = p;
     return upload(t.p1w, p.data(), p.size());
   }
   *handled = false;
@@ -712,13 +748,27 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
   // cost0 = gn1(raw1) + relu(gn0(raw0)) is never stored: consumers re-evaluate it
   const dfm::Term T1 = term(t.raw1, &t.g1, 0);
   // hourglass (conv_modules.py:129-149)
+  // the stride-2 convs are fed by TMA from a pre-split copy of their input (DFM_NO_TMA=1: the
+  // round-1 register loaders, for A/B runs)
+  static const bool no_tma = getenv("DFM_NO_TMA") != nullptr;
+  auto tma_ok = [&](const ConvW& w) {
+    return impl != DFM_CONV_SIMT && !no_tma && w.tc.ready() && w.tc.kslice &&
+           w.tc.mode == dfm::TC_S2;
+  };
   g = geom_s(D, Ho, Wo, cv, 2 * cv, 2, 2, 2, 1, 1, 1);
-  DFM_TRY(run_conv(src2(T1, T0), t.c1, t.b1.p, g, impl, st, &t.gc1, zw_at(2)));
+  if (tma_ok(t.c1) && dfm::tc_mode_of(g) == dfm::TC_S2)
+    DFM_TRY(run_conv_presplit(src2(T1, T0), t.ps0, t.c1, t.b1.p, g, st, &t.gc1, zw_at(2)));
+  else
+    DFM_TRY(run_conv(src2(T1, T0), t.c1, t.b1.p, g, impl, st, &t.gc1, zw_at(2)));
   const int D2 = g.Do, H2 = g.Ho, W2 = g.Wo;
   g = geom_s(D2, H2, W2, 2 * cv, 2 * cv, 1, 1, 1, 1, 1, 1);
   DFM_TRY(run_conv(src1(term(t.b1, &t.gc1, 1)), t.c2, t.b2.p, g, impl, st, &t.gc2, zw_at(2)));
   g = geom_s(D2, H2, W2, 2 * cv, 2 * cv, 2, 2, 2, 1, 1, 1);
-  DFM_TRY(run_conv(src1(term(t.b2, &t.gc2, 1)), t.c3, t.b3.p, g, impl, st, &t.gc3, zw_at(4)));
+  if (tma_ok(t.c3) && dfm::tc_mode_of(g) == dfm::TC_S2)
+    DFM_TRY(run_conv_presplit(src1(term(t.b2, &t.gc2, 1)), t.ps2, t.c3, t.b3.p, g, st, &t.gc3,
+                              zw_at(4)));
+  else
+    DFM_TRY(run_conv(src1(term(t.b2, &t.gc2, 1)), t.c3, t.b3.p, g, impl, st, &t.gc3, zw_at(4)));
   const int D4 = g.Do, H4 = g.Ho, W4 = g.Wo;
   g = geom_s(D4, H4, W4, 2 * cv, 2 * cv, 1, 1, 1, 1, 1, 1);
   DFM_TRY(run_conv(src1(term(t.b3, &t.gc3, 1)), t.c4, t.b4.p, g, impl, st, &t.gc4, zw_at(4)));
@@ -747,13 +797,23 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
   // depth prediction module (dfm_backbone.py:118-128)
   g = geom_s(D, Ho, Wo, cv, cv, 1, 1, 1, 1, 1, 1);
   DFM_TRY(run_conv(src1(term(t.cur, nullptr, 0)), t.p0, t.p0b.p, g, impl, st, &t.gp0, zw_at(1)));
-  if (impl != DFM_CONV_SIMT && t.p1tc.tc.ready()) {
+  // 32 -> 1 logits conv (dfm_backbone.py:128): HBM-bound, CUDA-core kernel with the per-tap
+  // dot products staged in shared memory (tail_kernels.cuh).  DFM_LOGITS_TC=1 keeps the
+  // round-1 tensor-core variant (N = 96 MMA, 1/32 useful columns) for A/B runs; the fp32
+  // SIMT bring-up path keeps its own independent kernel.
+  static const bool logits_tc = getenv("DFM_LOGITS_TC") != nullptr;
+  const dfm::Src lsrc = src1(term(t.p0b, &t.gp0, 1));
+  if (impl != DFM_CONV_SIMT && !logits_tc && cv == 32 && t.p1w_host.size() == 27u * 32u) {
+    ProfScope ps(conv_class("cout1_logits", g, "src"), 2.0 * V * cv * 27, st);
+    if (!dfm::logits_conv_launch(lsrc, t.p1w_host.data(), t.logit.p, D, Ho, Wo, st))
+      return fail(DFM_ERR_CUDA, "logits_conv_kernel launch failed");
+    g_launches.fetch_add(1);
+  } else if (impl != DFM_CONV_SIMT && t.p1tc.tc.ready()) {
     std::string err;
     ProfScope ps(conv_class("conv_tc_cout1", g, "src"), 2.0 * V * cv * 27, st);
     dfm::TcOpts o1;
     o1.store1 = 1;
-    if (!dfm::tc_conv_src(src1(term(t.p0b, &t.gp0, 1)), t.p1tc.tc, t.logit.p, nullptr, g, st, &err,
-                          o1))
+    if (!dfm::tc_conv_src(lsrc, t.p1tc.tc, t.logit.p, nullptr, g, st, &err, o1))
       return fail(DFM_ERR_CUDA, err);
     g_launches.fetch_add(1);
     g_tc_launches.fetch_add(1);
@@ -761,7 +821,7 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
     const long long threads = V * 8;
     ProfScope ps(conv_class("conv_simt_cout1", g, "src"), 2.0 * V * cv * 27, st);
     dfm::conv3d_c32_to_1_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-        src1(term(t.p0b, &t.gp0, 1)), t.p1w.p, t.logit.p, D, Ho, Wo);
+        lsrc, t.p1w.p, t.logit.p, D, Ho, Wo);
     LAUNCH_CHECK();
   }
   return DFM_OK;
@@ -905,7 +965,7 @@ int dfm_backbone_destroy(dfm_backbone_t* bb) {
   if (!bb) return DFM_OK;
   tower_release(bb->st);
   tower_release(bb->mo);
-  for (DevBuf* b : {&bb->cur_nhwc, &bb->prev_nhwc, &bb->depths, &bb->wagg, &bb->cost,
+  for (DevBuf* b : {&bb->cur_nhwc, &bb->prev_nhwc, &bb->depths, &bb->wagg, &bb->waggT, &bb->cost,
                     &bb->volume_dbg, &bb->stage[0].cur, &bb->stage[0].prev, &bb->stage[1].cur,
                     &bb->stage[1].prev, &bb->out_st, &bb->out_mo, &bb->pipe_sem, &bb->pipe_vox,
                     &bb->pipe_preds, &bb->pipe_samples})
@@ -925,6 +985,13 @@ int dfm_backbone_set_param(dfm_backbone_t* bb, const char* name, const float* h_
     if (numel != (long long)bb->D * 2 * bb->D)
       return fail(DFM_ERR_INVALID, "aggregate_cost.weight: expected (D, 2D, 1, 1)");
     CU_TRY(cudaMemcpy(bb->wagg.p, h_data, numel * sizeof(float), cudaMemcpyHostToDevice));
+    {  // transposed, padded copy [2D][gate_row_pitch(D)] for the persistent gate kernel
+      const int D = bb->D, pitch = dfm::gate_row_pitch(D);
+      std::vector<float> wt((size_t)2 * D * pitch, 0.f);
+      for (int d = 0; d < D; ++d)
+        for (int j = 0; j < 2 * D; ++j) wt[(size_t)j * pitch + d] = h_data[(size_t)d * 2 * D + j];
+      DFM_TRY(upload(bb->waggT, wt.data(), wt.size()));
+    }
     bb->missing.erase(n);
     return DFM_OK;
   }
@@ -1002,11 +1069,28 @@ int backbone_forward_impl(dfm_backbone_t* bb, const float* d_cur, const float* d
   DFM_TRY(tower_forward(bb, bb->st, false, wl, d_stereo, st, nullptr));
   // mono/stereo gate (dfm_backbone.py:130-141)
   const int HWo = bb->Ho * bb->Wo;
-  const size_t smem = (size_t)2 * bb->D * 32 * sizeof(float);
-  if (smem > 48 * 1024)
-    CU_TRY(cudaFuncSetAttribute(dfm::gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-  {
+  const size_t gsm = dfm::gate_smem_bytes(bb->D);
+  if (bb->D <= 256 && gsm <= 200 * 1024 && getenv("DFM_GATE_V1") == nullptr) {
+    // weights resident in shared memory, one persistent block per SM
+    bool& attr_done = dfm::per_device<bool, 8>();
+    size_t& attr_sz = dfm::per_device<size_t, 9>();
+    if (!attr_done || attr_sz < gsm) {
+      CU_TRY(cudaFuncSetAttribute(dfm::gate_persistent_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+      attr_done = true;
+      attr_sz = gsm;
+    }
+    const int ng = (bb->D + dfm::GT_PG - 1) / dfm::GT_PG;
+    const int grid = std::min((HWo + 31) / 32, dfm::tc_sm_count());
+    ProfScope ps("gate", 0.0, st);
+    dfm::gate_persistent_kernel<<<grid, 32 * ng, gsm, st>>>(bb->st.logit.p, bb->mo.logit.p,
+                                                            bb->waggT.p, bb->cost.p, bb->D, HWo,
+                                                            ze_mono);
+  } else {
+    const size_t smem = (size_t)2 * bb->D * 32 * sizeof(float);
+    if (smem > 48 * 1024)
+      CU_TRY(cudaFuncSetAttribute(dfm::gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
     ProfScope ps("gate", 0.0, st);
     dfm::gate_kernel<<<(HWo + 31) / 32, 128, smem, st>>>(bb->st.logit.p, bb->mo.logit.p,
                                                          bb->wagg.p, bb->cost.p, bb->D, HWo, ze_mono);
@@ -1015,6 +1099,37 @@ int backbone_forward_impl(dfm_backbone_t* bb, const float* d_cur, const float* d
   if (d_cost)
     CU_TRY(cudaMemcpyAsync(d_cost, bb->cost.p, (size_t)bb->D * HWo * sizeof(float),
                            cudaMemcpyDeviceToDevice, st));
+  return DFM_OK;
+}
+}  // namespace
+
+namespace {
+// DepthHead.forward kernel selection: four x pixels per thread (16-byte stores) whenever the
+// output width allows it, else the one-pixel-per-thread kernel
+int launch_depth_head(const float* d_cost, const float* d_samples, int D, int Ho, int Wo,
+                      int factor, float* d_volume, float* d_softmax, float* d_preds,
+                      float2* d_norm, const char* tag, cudaStream_t st) {
+  ProfScope ps(tag, 0.0, st);
+  static const bool v1 = getenv("DFM_DEPTH_HEAD_V1") != nullptr;
+  const size_t sm4 = dfm::dh4_smem_bytes(D, factor);
+  if ((Wo * factor) % 4 == 0 && sm4 <= 160 * 1024 && !v1) {
+    size_t& attr_sz = dfm::per_device<size_t, 10>();
+    if (attr_sz < sm4) {
+      CU_TRY(cudaFuncSetAttribute(dfm::depth_head4_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
+      attr_sz = sm4;
+    }
+    dim3 grid((Wo * factor + dfm::DH4_PX - 1) / dfm::DH4_PX, Ho * factor), block(32, dfm::DH_ZS);
+    dfm::depth_head4_kernel<<<grid, block, sm4, st>>>(d_cost, d_samples, D, Ho, Wo, factor,
+                                                      d_volume, d_softmax, d_preds, d_norm);
+  } else {
+    if (dfm::dh_smem_bytes(D, factor) > 32768)
+      return fail(DFM_ERR_INVALID, "DepthHead: too many depth planes for the staged columns");
+    dim3 grid((Wo * factor + 31) / 32, Ho * factor), block(32, dfm::DH_ZS);
+    dfm::depth_head_kernel<<<grid, block, dfm::dh_smem_bytes(D, factor), st>>>(
+        d_cost, d_samples, D, Ho, Wo, factor, d_volume, d_softmax, d_preds, d_norm);
+  }
+  LAUNCH_CHECK();
   return DFM_OK;
 }
 }  // namespace
@@ -1272,15 +1387,8 @@ int dfm_depth_head_forward(const float* d_cost, const float* d_depth_samples, in
   if (D < 1 || Ho < 1 || Wo < 1 || factor < 1) return fail(DFM_ERR_INVALID, "bad shape");
   if ((long long)D * factor > dfm::DH_MAXBINS)
     return fail(DFM_ERR_INVALID, "DepthHead: more than 1024 depth bins");
-  if (dfm::dh_smem_bytes(D, factor) > 32768)
-    return fail(DFM_ERR_INVALID, "DepthHead: too many depth planes for the staged columns");
-  dim3 grid((Wo * factor + 31) / 32, Ho * factor), block(32, dfm::DH_ZS);
-  {
-    ProfScope ps("depth_head", 0.0, (cudaStream_t)stream);
-    dfm::depth_head_kernel<<<grid, block, dfm::dh_smem_bytes(D, factor), (cudaStream_t)stream>>>(
-        d_cost, d_depth_samples, D, Ho, Wo, factor, d_volume, d_softmax, d_preds);
-  }
-  LAUNCH_CHECK();
+  DFM_TRY(launch_depth_head(d_cost, d_depth_samples, D, Ho, Wo, factor, d_volume, d_softmax,
+                            d_preds, nullptr, "depth_head", (cudaStream_t)stream));
   return DFM_OK;
 }
 

@@ -1,0 +1,444 @@
+// HBM-bound tail of the KITTI path, second generation (round 2):
+//   * logits_conv_kernel  -- the 32 -> 1 channel 3x3x3 conv of build_depth_pred_module
+//     (dfm_backbone.py:128) as a CUDA-core kernel.  The op reads V*32 floats and writes V
+//     (0.43 GB -> ~0.07 ms at the copy bandwidth); on the tensor-core conv it ran as an N = 96
+//     MMA with 1/32 useful columns (0.58 ms per frame).  Formulation: per INPUT voxel, the 27
+//     per-tap dot products q_t = <x, w_t> (864 FMAs whose weight operands come straight from
+//     the constant bank: the weights are a __grid_constant__ kernel parameter and every index
+//     is a compile-time constant, so there is no load instruction per weight), staged in
+//     shared memory; per OUTPUT voxel, out(o) = sum_t q_t(o + off_t) is 27 shared-memory reads.
+//     A block owns a 26 x 16 (x, y) output tile (28 x 18 halo = 504 positions, two per thread)
+//     and marches along z with three running accumulators per output pixel.
+//   * depth_head4_kernel  -- DepthHead.forward with four consecutive x pixels per thread so the
+//     two [4D,4H,4W] volumes are written with 16-byte stores, 512 contiguous bytes per warp
+//     and depth bin.
+//   * gate_persistent_kernel -- the mono/stereo gate with the 1x1 conv weights resident in
+//     shared memory (transposed), one persistent block per SM.
+#pragma once
+#include "conv_tc.cuh"
+#include "simt_kernels.cuh"
+
+namespace dfm {
+
+constexpr int LC_TX = 26, LC_TY = 16;                 // output tile
+constexpr int LC_PX = LC_TX + 2, LC_PY = LC_TY + 2;   // input halo
+constexpr int LC_NPOS = LC_PX * LC_PY;                // 504
+constexpr int LC_THREADS = 256;
+constexpr int LC_ZCHUNK = 8;                          // output planes per block
+
+struct LogitsConvParams {
+  float w[27 * 32];   // [tap = kz*9 + ky*3 + kx][channel]
+  Term t;             // single input term (GroupNorm affine + ReLU folded into the load)
+  int D, H, W;
+  int tiles_x, tiles_y, zchunks;
+};
+
+__global__ void __launch_bounds__(LC_THREADS, 2)
+logits_conv_kernel(const __grid_constant__ LogitsConvParams p, float* __restrict__ out) {
+  extern __shared__ float lc_q[];   // [27][LC_NPOS]
+  float (*q)[LC_NPOS] = reinterpret_cast<float (*)[LC_NPOS]>(lc_q);
+  __shared__ float4 aff[16];        // scale[32] | shift[32] of the input term
+  const int tid = threadIdx.x;
+  if (tid < 64) {
+    float v = tid < 32 ? 1.f : 0.f;
+    if (p.t.scale) v = tid < 32 ? __ldg(p.t.scale + tid) : __ldg(p.t.shift + tid - 32);
+    reinterpret_cast<float*>(aff)[tid] = v;
+  }
+  const long long plane = (long long)p.H * p.W;
+  const int nitems = p.tiles_x * p.tiles_y * p.zchunks;
+  // output pixels of this thread inside a tile: tile-linear indices tid and tid + 256
+  int oy[2], ox[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = tid + k * LC_THREADS;
+    oy[k] = i / LC_TX;
+    ox[k] = i % LC_TX;
+  }
+  // input positions of this thread inside the halo
+  int py[2], pxx[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int pos = tid + k * LC_THREADS;
+    py[k] = pos / LC_PX;
+    pxx[k] = pos % LC_PX;
+  }
+  __syncthreads();
+
+  // persistent: items (tile, z chunk) are dealt round-robin; consecutive items of a block are
+  // far apart, consecutive blocks work on neighbouring tiles of the same planes (L2 halo reuse)
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    int b = item;
+    const int tx_i = b % p.tiles_x;
+    b /= p.tiles_x;
+    const int ty_i = b % p.tiles_y;
+    const int zc = b / p.tiles_y;
+    const int x0 = tx_i * LC_TX, y0 = ty_i * LC_TY;
+    const int z_lo = zc * LC_ZCHUNK, z_hi = min(p.D, z_lo + LC_ZCHUNK);
+    bool olive[2], inb[2];
+    long long goff[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      olive[k] = tid + k * LC_THREADS < LC_TX * LC_TY && y0 + oy[k] < p.H && x0 + ox[k] < p.W;
+      const int gy = y0 - 1 + py[k], gx = x0 - 1 + pxx[k];
+      inb[k] = tid + k * LC_THREADS < LC_NPOS && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+      goff[k] = ((long long)gy * p.W + gx) * 32;
+    }
+    float accA[2] = {0.f, 0.f}, accB[2] = {0.f, 0.f};  // output planes zi-1 and zi
+    const int zi0 = max(z_lo - 1, 0), zi1 = min(z_hi, p.D - 1);
+    // raw channels of position 0 of the first plane; every later load is issued one position
+    // ahead of its use so its latency hides behind 864 FMAs
+    float4 nxt[8];
+    auto issue = [&](int zi, int k) {
+      if (inb[k]) {
+        const float4* src = reinterpret_cast<const float4*>(
+            p.t.x + (long long)term_plane(p.t, zi) * plane * 32 + goff[k]);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) nxt[v] = __ldg(src + v);
+      }
+    };
+    issue(zi0, 0);
+    for (int zi = zi0; zi <= zi1; ++zi) {
+      // ---- phase 1: q_t of this input plane's halo positions ----
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int pos = tid + k * LC_THREADS;
+        float x[32];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          x[4 * v] = nxt[v].x; x[4 * v + 1] = nxt[v].y; x[4 * v + 2] = nxt[v].z; x[4 * v + 3] = nxt[v].w;
+        }
+        const bool have = inb[k];
+        // prefetch: the other position of this plane, or position 0 of the next plane
+        if (k == 0) issue(zi, 1);
+        else if (zi < zi1) issue(zi + 1, 0);
+        if (pos < LC_NPOS) {
+          if (!have) {
+#pragma unroll
+            for (int t = 0; t < 27; ++t) q[t][pos] = 0.f;
+          } else {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const float4 s4 = aff[v], h4 = aff[8 + v];
+              x[4 * v] = fmaf(x[4 * v], s4.x, h4.x);
+              x[4 * v + 1] = fmaf(x[4 * v + 1], s4.y, h4.y);
+              x[4 * v + 2] = fmaf(x[4 * v + 2], s4.z, h4.z);
+              x[4 * v + 3] = fmaf(x[4 * v + 3], s4.w, h4.w);
+            }
+            if (p.t.relu) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) x[c] = fmaxf(x[c], 0.f);
+            }
+#pragma unroll
+            for (int t = 0; t < 27; ++t) {
+              float a0 = 0.f, a1 = 0.f;   // two chains per tap
+#pragma unroll
+              for (int c = 0; c < 32; c += 2) {
+                a0 = fmaf(x[c], p.w[t * 32 + c], a0);
+                a1 = fmaf(x[c + 1], p.w[t * 32 + c + 1], a1);
+              }
+              q[t][pos] = a0 + a1;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // ---- phase 2: gather.  Input plane zi feeds output planes zi-1 (kz = 2), zi (kz = 1)
+      // and zi+1 (kz = 0); out(zi-1) is complete after this plane.
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (!olive[k]) continue;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int pos = (oy[k] + ky) * LC_PX + ox[k] + kx;
+            s0 += q[0 * 9 + ky * 3 + kx][pos];
+            s1 += q[1 * 9 + ky * 3 + kx][pos];
+            s2 += q[2 * 9 + ky * 3 + kx][pos];
+          }
+        const int zo = zi - 1;
+        if (zo >= z_lo && zo < z_hi)
+          out[(long long)zo * plane + (long long)(y0 + oy[k]) * p.W + x0 + ox[k]] = accA[k] + s2;
+        accA[k] = accB[k] + s1;
+        accB[k] = s0;
+      }
+      __syncthreads();
+    }
+    // the last output plane of the chunk when it is the volume's last plane (no input plane
+    // z_hi exists to flush it)
+    if (z_hi == p.D) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (olive[k])
+          out[(long long)(p.D - 1) * plane + (long long)(y0 + oy[k]) * p.W + x0 + ox[k]] = accA[k];
+    }
+  }
+}
+
+inline bool logits_conv_launch(const Src& s, const float* h_w /*[27][32] host*/, float* out,
+                               int D, int H, int W, cudaStream_t st) {
+  if (s.n != 1 || s.outer_relu) return false;
+  LogitsConvParams p;
+  memcpy(p.w, h_w, sizeof(p.w));
+  p.t = s.t[0];
+  p.D = D; p.H = H; p.W = W;
+  p.tiles_x = (W + LC_TX - 1) / LC_TX;
+  p.tiles_y = (H + LC_TY - 1) / LC_TY;
+  p.zchunks = (D + LC_ZCHUNK - 1) / LC_ZCHUNK;
+  const long long blocks = (long long)p.tiles_x * p.tiles_y * p.zchunks;
+  if (blocks > 0x7fffffffLL) return false;
+  constexpr size_t smem = sizeof(float) * 27 * LC_NPOS;
+  bool& attr_done = per_device<bool, 7>();
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(logits_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+      return false;
+    attr_done = true;
+  }
+  const int grid = (int)std::min<long long>(blocks, 2LL * tc_sm_count());
+  logits_conv_kernel<<<grid, LC_THREADS, smem, st>>>(p, out);
+  return cudaGetLastError() == cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------
+// DepthHead.forward, four x pixels per thread (requires (Wo * f) % 4 == 0)
+// ---------------------------------------------------------------------------------
+constexpr int DH4_PX = 128;   // output pixels along x per block
+__host__ __device__ inline int dh4_ncols(int f) { return DH4_PX / f + 3; }
+inline size_t dh4_smem_bytes(int D, int f) { return (size_t)D * 2 * dh4_ncols(f) * sizeof(float); }
+
+__global__ void __launch_bounds__(32 * DH_ZS)
+depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ samples, int D,
+                   int Ho, int Wo, int f, float* __restrict__ vol, float* __restrict__ sm,
+                   float* __restrict__ preds, float2* __restrict__ norm) {
+  extern __shared__ float dh_cols[];                 // [D][2][nc]
+  __shared__ float red[3][DH_ZS][DH4_PX];
+  __shared__ int tab_z0[DH_MAXBINS];
+  __shared__ float tab_l1[DH_MAXBINS], tab_s[DH_MAXBINS];
+  const int OW = Wo * f, OH = Ho * f, OD = D * f;
+  const int tx = threadIdx.x, seg = threadIdx.y;
+  const float sz = OD > 1 ? (float)(D - 1) / (OD - 1) : 0.f;
+  for (int k = seg * 32 + tx; k < OD; k += 32 * DH_ZS) {
+    const float fz = sz * k;
+    const int z0 = (int)fz;
+    tab_z0[k] = z0;
+    tab_l1[k] = fz - z0;
+    tab_s[k] = samples ? __ldg(samples + k) : 0.f;
+  }
+  const int Xb = blockIdx.x * DH4_PX;
+  const int X0 = Xb + 4 * tx;                        // first of this thread's four pixels
+  const bool live = X0 < OW;                          // OW % 4 == 0: all four or none
+  const int Y = blockIdx.y;
+  const float sx = OW > 1 ? (float)(Wo - 1) / (OW - 1) : 0.f;
+  const float sy = OH > 1 ? (float)(Ho - 1) / (OH - 1) : 0.f;
+  const float fy = sy * Y;
+  const int y0 = (int)fy;
+  const int y1 = y0 + (y0 < Ho - 1 ? 1 : 0);
+  const float ly1 = fy - y0, ly0 = 1.f - ly1;
+  const long long plane = (long long)Ho * Wo;
+  const long long oplane = (long long)OH * OW;
+  const int nc = dh4_ncols(f);
+  const int xb = (int)(sx * Xb);                      // first low-res column of the block
+  for (int i = seg * 32 + tx; i < D * 2 * nc; i += 32 * DH_ZS) {
+    const int z = i / (2 * nc), rc = i - z * 2 * nc;
+    const int r = rc >= nc ? 1 : 0, c = rc - r * nc;
+    dh_cols[i] = __ldg(cost + z * plane + (r ? y1 : y0) * Wo + min(xb + c, Wo - 1));
+  }
+  int c0[4], c1[4];
+  float wx0[4], wx1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int X = min(X0 + j, OW - 1);
+    const float fx = sx * X;
+    const int x0 = (int)fx;
+    const int x1 = x0 + (x0 < Wo - 1 ? 1 : 0);
+    wx1[j] = fx - x0;
+    wx0[j] = 1.f - wx1[j];
+    c0[j] = x0 - xb;
+    c1[j] = x1 - xb;
+  }
+  __syncthreads();
+  // same association as ATen upsample_trilinear3d: h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)
+  auto col = [&](int z, int j) {
+    const float* pz = dh_cols + z * 2 * nc;
+    return ly0 * (wx0[j] * pz[c0[j]] + wx1[j] * pz[c1[j]]) +
+           ly1 * (wx0[j] * pz[nc + c0[j]] + wx1[j] * pz[nc + c1[j]]);
+  };
+  float m[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float mm = -INFINITY;
+    for (int z = seg * D / DH_ZS; z < (seg + 1) * D / DH_ZS; ++z) mm = fmaxf(mm, col(z, j));
+    red[0][seg][4 * tx + j] = mm;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m[j] = red[0][0][4 * tx + j];
+#pragma unroll
+    for (int i = 1; i < DH_ZS; ++i) m[j] = fmaxf(m[j], red[0][i][4 * tx + j]);
+  }
+  const int k_lo = seg * OD / DH_ZS, k_hi = (seg + 1) * OD / DH_ZS;
+  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, esum[4] = {0.f, 0.f, 0.f, 0.f};
+  float b0[4], b1[4];
+  int zc = -1;
+  for (int k = k_lo; k < k_hi; ++k) {
+    const int z0 = tab_z0[k];
+    const float lz1 = tab_l1[k], s = tab_s[k];
+    if (z0 != zc) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        b0[j] = (z0 == zc + 1 && zc >= 0) ? b1[j] : col(z0, j);
+        b1[j] = z0 < D - 1 ? col(z0 + 1, j) : b0[j];
+      }
+      zc = z0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v = (1.f - lz1) * b0[j] + lz1 * b1[j];
+      const float e = __expf(v - m[j]);
+      ssum[j] += e;
+      esum[j] = fmaf(e, s, esum[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[1][seg][4 * tx + j] = ssum[j];
+    red[2][seg][4 * tx + j] = esum[j];
+  }
+  __syncthreads();
+  float inv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = 0.f, e = 0.f;
+#pragma unroll
+    for (int i = 0; i < DH_ZS; ++i) {
+      a += red[1][i][4 * tx + j];
+      e += red[2][i][4 * tx + j];
+    }
+    ssum[j] = a;
+    esum[j] = e;
+    inv[j] = 1.f / a;
+  }
+  if (!live) return;
+  const long long opix = (long long)Y * OW + X0;
+  if (seg == 0) {
+    if (preds)
+      *reinterpret_cast<float4*>(preds + opix) =
+          make_float4(esum[0] / ssum[0], esum[1] / ssum[1], esum[2] / ssum[2], esum[3] / ssum[3]);
+    if (norm) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) norm[opix + j] = make_float2(m[j], inv[j]);
+    }
+  }
+  if (!sm && !vol) return;
+  zc = -1;
+  for (int k = k_lo; k < k_hi; ++k) {
+    const int z0 = tab_z0[k];
+    const float lz1 = tab_l1[k];
+    if (z0 != zc) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        b0[j] = (z0 == zc + 1 && zc >= 0) ? b1[j] : col(z0, j);
+        b1[j] = z0 < D - 1 ? col(z0 + 1, j) : b0[j];
+      }
+      zc = z0;
+    }
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (1.f - lz1) * b0[j] + lz1 * b1[j];
+    if (vol)
+      __stcs(reinterpret_cast<float4*>(vol + k * oplane + opix), make_float4(v[0], v[1], v[2], v[3]));
+    if (sm)
+      __stcs(reinterpret_cast<float4*>(sm + k * oplane + opix),
+             make_float4(__expf(v[0] - m[0]) * inv[0], __expf(v[1] - m[1]) * inv[1],
+                         __expf(v[2] - m[2]) * inv[2], __expf(v[3] - m[3]) * inv[3]));
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// mono/stereo gate (dfm_backbone.py:135-141), persistent: the (D x 2D) 1x1-conv weights live
+// in shared memory, transposed to [2D][DG*16] so the 16 weights of a thread's plane group for
+// one input plane j are four broadcast 16-byte reads.
+// ---------------------------------------------------------------------------------
+constexpr int GT_PG = 16;   // output planes per thread
+__host__ __device__ inline int gate_row_pitch(int D) { return (D + GT_PG - 1) / GT_PG * GT_PG; }
+inline size_t gate_smem_bytes(int D) {
+  return ((size_t)2 * D * gate_row_pitch(D) + (size_t)2 * D * 32) * sizeof(float);
+}
+// wT: the 1x1 conv weight transposed and padded on the host, [2D][gate_row_pitch(D)]
+__global__ void __launch_bounds__(512)
+gate_persistent_kernel(const float* __restrict__ ls, const float* __restrict__ lm,
+                       const float* __restrict__ wT_g, float* __restrict__ cost, int D, int HW,
+                       ZExpand zm) {
+  extern __shared__ float gsm[];
+  const int ng = (D + GT_PG - 1) / GT_PG, DP = ng * GT_PG;
+  float* wT = gsm;                          // [2D][DP]
+  float* cat = gsm + (size_t)2 * D * DP;    // [2D][32]
+  const int nthreads = blockDim.x;          // 32 * ng
+  {
+    const float4* src = reinterpret_cast<const float4*>(wT_g);
+    float4* dst = reinterpret_cast<float4*>(wT);
+    for (int i = threadIdx.x; i < 2 * D * DP / 4; i += nthreads) dst[i] = __ldg(src + i);
+  }
+  const int px = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int ntiles = (HW + 31) / 32;
+  constexpr int MAXJ = 32;                  // planes of the cat column a thread stages (2D / ng)
+  const int nj = (2 * D - g + ng - 1) / ng; // j = g, g + ng, ...
+  float stage[MAXJ];
+  auto fetch = [&](int tile) {
+    const int p = tile * 32 + px;
+#pragma unroll
+    for (int q = 0; q < MAXJ; ++q) {
+      const int j = g + q * ng;
+      float v = 0.f;
+      if (q < nj && p < HW)
+        v = j < D ? __ldg(ls + (long long)j * HW + p)
+                  : __ldg(lm + (long long)zexpand(zm, j - D) * HW + p);
+      stage[q] = v;
+    }
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) fetch(tile);
+  for (; tile < ntiles; tile += gridDim.x) {
+    const int p = tile * 32 + px;
+    __syncthreads();   // previous tile's cat fully consumed (and wT written, first time)
+#pragma unroll
+    for (int q = 0; q < MAXJ; ++q)
+      if (q < nj) cat[(g + q * ng) * 32 + px] = stage[q];
+    __syncthreads();
+    // the next tile's column is fetched while this one is being reduced
+    if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
+    float a[GT_PG];
+#pragma unroll
+    for (int k = 0; k < GT_PG; ++k) a[k] = 0.f;
+    const float4* wrow = reinterpret_cast<const float4*>(wT + g * GT_PG);
+#pragma unroll 4
+    for (int j = 0; j < 2 * D; ++j) {
+      const float c = cat[j * 32 + px];
+      const float4* w4 = wrow + (size_t)j * (DP / 4);
+#pragma unroll
+      for (int q = 0; q < GT_PG / 4; ++q) {
+        const float4 w = w4[q];
+        a[4 * q] = fmaf(w.x, c, a[4 * q]);
+        a[4 * q + 1] = fmaf(w.y, c, a[4 * q + 1]);
+        a[4 * q + 2] = fmaf(w.z, c, a[4 * q + 2]);
+        a[4 * q + 3] = fmaf(w.w, c, a[4 * q + 3]);
+      }
+    }
+    if (p < HW) {
+#pragma unroll
+      for (int k = 0; k < GT_PG; ++k) {
+        const int d = g * GT_PG + k;
+        if (d < D) {
+          const float wgt = 1.f / (1.f + __expf(-a[k]));
+          const float sv = cat[d * 32 + px], mv = cat[(D + d) * 32 + px];
+          cost[(long long)d * HW + p] = wgt * sv + (1.f - wgt) * mv;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace dfm

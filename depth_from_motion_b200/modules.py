@@ -788,6 +788,193 @@ class HotPathPipeline:
         return vox, preds
 
 
+class _ConvGN2d(nn.Module):
+    """Parameter layout of mmcv ConvModule(Conv2d 3x3, norm=GN): .conv / .gn."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 3, 1, 1, bias=False)
+        self.gn = nn.GroupNorm(32, cout)
+
+
+def _convbn2d(cin, cout, stride):
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, stride, 1, bias=False),
+                         nn.GroupNorm(32, cout))
+
+
+class _Hourglass2d(nn.Module):
+    """Parameter layout of hourglass2d (backbones/bev_hourglass.py:53-119, gn=True)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Sequential(_convbn2d(c, 2 * c, 2), nn.ReLU(True))
+        self.conv2 = _convbn2d(2 * c, 2 * c, 1)
+        self.conv3 = nn.Sequential(_convbn2d(2 * c, 2 * c, 2), nn.ReLU(True))
+        self.conv4 = nn.Sequential(_convbn2d(2 * c, 2 * c, 1), nn.ReLU(True))
+        self.conv5 = nn.Sequential(
+            nn.ConvTranspose2d(2 * c, 2 * c, 3, padding=1, output_padding=1, stride=2,
+                               bias=False), nn.GroupNorm(32, 2 * c))
+        self.conv6 = nn.Sequential(
+            nn.ConvTranspose2d(2 * c, c, 3, padding=1, output_padding=1, stride=2,
+                               bias=False), nn.GroupNorm(32, c))
+
+
+class _HandleMirror(_CudaMirror):
+    """create / destroy / parameter-sync plumbing shared by the 2-D BEV mirrors."""
+    _destroy = None
+
+    def release(self):
+        if getattr(self, '_handle', None) is not None:
+            getattr(capi.lib(), self._destroy)(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def init_weights(self):
+        pass
+
+
+@BACKBONES.register_module()
+class BEVHourglass(_HandleMirror):
+    """Drop-in for the reference ``BEVHourglass`` forward with GroupNorm
+    (backbones/bev_hourglass.py:11-137; ``backbone_3d`` of
+    configs/dfm/dfm_r34_1x8_kitti-3d-3class.py:146-150).  The SyncBN variant is the frozen
+    LiDAR teacher's (config :30-36, training only) and is not mirrored."""
+    _destroy = 'dfm_bev_hourglass_destroy'
+
+    def __init__(self, in_channels, out_channels, norm_cfg=None, output_prehg_feat=True,
+                 conv_impl='auto'):
+        super().__init__()
+        assert norm_cfg is not None and norm_cfg.get('type') == 'GN' and \
+            norm_cfg.get('num_groups', 32) == 32, 'only the GroupNorm(32) variant is implemented'
+        self.out_channels = out_channels
+        self.norm_cfg = norm_cfg
+        self.output_prehg_feat = output_prehg_feat
+        self.in_channels = in_channels
+        self.conv_impl = conv_impl
+        self.compress_conv = _ConvGN2d(in_channels, out_channels)
+        self.bev_hourglass = _Hourglass2d(out_channels)
+        self.num_bev_features = out_channels
+        self._handle = None
+        self._key = None
+
+    def forward(self, spatial_features):
+        _check_cuda(spatial_features, 'spatial_features')
+        self._forward_only(spatial_features)
+        b, c, ny, nx = spatial_features.shape
+        assert c == self.in_channels
+        L = capi.lib()
+        key = (ny, nx, self.conv_impl)
+        if self._handle is None or key != self._key:
+            self.release()
+            desc = capi.BevDesc(self.in_channels, self.out_channels, ny, nx,
+                                _IMPL[self.conv_impl])
+            hd = ctypes.c_void_p()
+            capi.check(L.dfm_bev_hourglass_create(ctypes.byref(desc), ctypes.byref(hd)),
+                       'dfm_bev_hourglass_create')
+            self._handle, self._key = hd, key
+            self._sync = _ParamSync()
+        self._sync.sync(self, lambda k, p, m: capi.check(
+            L.dfm_bev_hourglass_set_param(self._handle, k, p, m),
+            f'dfm_bev_hourglass_set_param({k.decode()})'))
+        x = spatial_features.contiguous()
+        out = torch.empty((b, self.out_channels, ny, nx), device=x.device)
+        pre = torch.empty_like(out) if self.output_prehg_feat else None
+        for i in range(b):
+            capi.check(L.dfm_bev_hourglass_forward(
+                self._handle, _ptr(x[i]), _ptr(pre[i]) if pre is not None else None,
+                _ptr(out[i]), _stream()), 'dfm_bev_hourglass_forward')
+        return (pre, out) if self.output_prehg_feat else out   # bev_hourglass.py:46-50
+
+
+@HEADS.register_module()
+class LIGAAnchor3DHead(_HandleMirror):
+    """Forward of the reference ``LIGAAnchor3DHead`` (dense_heads/liga_anchor3d_head.py:
+    12-128): ``forward(feats) -> ([cls_score], [bbox_pred], [dir_cls_preds])``.  Anchor
+    generation, target assignment, losses and ``get_bboxes`` (NMS) stay with the reference's
+    PyTorch code (heads only consume the hot path's output); the
+    constructor keeps their arguments so the config block builds unchanged."""
+    _destroy = 'dfm_anchor_head_destroy'
+
+    def __init__(self, num_classes, in_channels, feat_channels=256, num_convs=2,
+                 norm_cfg=None, use_direction_classifier=True,
+                 anchor_generator=dict(type='Anchor3DRangeGenerator',
+                                       sizes=[[3.9, 1.6, 1.56]], rotations=[0, 1.57]),
+                 bbox_coder=dict(type='DeltaXYZWLHRBBoxCoder'), normalizer_clamp_value=10,
+                 reduce_avg_factor=True, train_cfg=None, test_cfg=None, conv_impl='auto',
+                 **kwargs):
+        super().__init__()
+        assert norm_cfg is not None and norm_cfg.get('type') == 'GN' and \
+            norm_cfg.get('num_groups', 32) == 32, 'only the GroupNorm(32) variant is implemented'
+        self.num_classes, self.in_channels = num_classes, in_channels
+        self.feat_channels, self.num_convs = feat_channels, num_convs
+        self.norm_cfg = norm_cfg
+        self.use_direction_classifier = use_direction_classifier
+        self.normalizer_clamp_value = normalizer_clamp_value
+        self.reduce_avg_factor = reduce_avg_factor
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.extra_cfg = dict(anchor_generator=anchor_generator, bbox_coder=bbox_coder, **kwargs)
+        # Anchor3DRangeGenerator.num_base_anchors (core/anchor/anchor_3d_generator.py:78-82)
+        sizes = np.asarray(anchor_generator.get('sizes', [[3.9, 1.6, 1.56]])).reshape(-1, 3)
+        self.num_anchors = len(anchor_generator.get('rotations', [0, 1.5707963])) * len(sizes)
+        self.box_code_size = int(bbox_coder.get('code_size', 7))   # DeltaXYZWLHRBBoxCoder
+        self.conv_impl = conv_impl
+        # _init_layers (:37-75)
+        self.cls_convs = nn.Sequential(*[_ConvGN2d(in_channels if i == 0 else feat_channels,
+                                                   feat_channels) for i in range(num_convs)])
+        self.reg_convs = nn.Sequential(*[_ConvGN2d(in_channels if i == 0 else feat_channels,
+                                                   feat_channels) for i in range(num_convs)])
+        self.cls_out_channels = self.num_anchors * num_classes
+        self.conv_cls = nn.Conv2d(feat_channels, self.cls_out_channels, 3, 1, 1)
+        self.conv_reg = nn.Conv2d(feat_channels, self.num_anchors * self.box_code_size, 3, 1, 1)
+        if use_direction_classifier:
+            self.conv_dir_cls = nn.Conv2d(feat_channels, self.num_anchors * 2, 1)
+        self._handle = None
+        self._key = None
+
+    def forward(self, feats):
+        if not isinstance(feats, list):                      # :104-105
+            feats = [feats]
+        outs = [self.forward_single(x) for x in feats]       # multi_apply
+        return tuple(map(list, zip(*outs)))
+
+    def forward_single(self, x):
+        _check_cuda(x, 'x')
+        self._forward_only(x)
+        b, c, ny, nx = x.shape
+        assert c == self.in_channels
+        L = capi.lib()
+        nd = self.num_anchors * 2 if self.use_direction_classifier else 0
+        key = (ny, nx, self.conv_impl)
+        if self._handle is None or key != self._key:
+            self.release()
+            desc = capi.AnchorHeadDesc(
+                self.in_channels, self.feat_channels, self.num_convs, self.cls_out_channels,
+                self.num_anchors * self.box_code_size, nd, ny, nx, _IMPL[self.conv_impl])
+            hd = ctypes.c_void_p()
+            capi.check(L.dfm_anchor_head_create(ctypes.byref(desc), ctypes.byref(hd)),
+                       'dfm_anchor_head_create')
+            self._handle, self._key = hd, key
+            self._sync = _ParamSync()
+        self._sync.sync(self, lambda k, p, m: capi.check(
+            L.dfm_anchor_head_set_param(self._handle, k, p, m),
+            f'dfm_anchor_head_set_param({k.decode()})'))
+        x = x.contiguous()
+        cls = torch.empty((b, self.cls_out_channels, ny, nx), device=x.device)
+        box = torch.empty((b, self.num_anchors * self.box_code_size, ny, nx), device=x.device)
+        dirc = torch.empty((b, nd, ny, nx), device=x.device) if nd else None
+        for i in range(b):
+            capi.check(L.dfm_anchor_head_forward(
+                self._handle, _ptr(x[i]), _ptr(cls[i]), _ptr(box[i]),
+                _ptr(dirc[i]) if dirc is not None else None, _stream()),
+                'dfm_anchor_head_forward')
+        return cls, box, dirc
+
+
 def aligned_voxel_centers(n_voxels, voxel_range):
     """Per-axis voxel-centre coordinates exactly as
     AlignedAnchor3DRangeGenerator.anchors_single_range computes them

@@ -136,6 +136,11 @@ def register_into_mmdet():
                                  module=modules.DfMBackbone)
     MM_HEADS.register_module(name='DepthHead', force=True,
                              module=modules.DepthHead)
+    # (LIGAAnchor3DHead is NOT forced into mmdet's registry: the mirror implements forward
+    # only, the detector needs the reference class's loss / get_bboxes; BEVHourglass's
+    # forward is the whole module)
+    MM_BACKBONES.register_module(name='BEVHourglassB200', force=True,
+                                 module=modules.BEVHourglass)
     try:
         from mmdet3d.models.builder import NECKS as MM3D_NECKS
         MM3D_NECKS.register_module(name='DfMNeck', force=True,

@@ -164,6 +164,15 @@ def _ident(x):
     return x
 
 
+def _q(q, t, layer, kind):
+    """Operand-rounding hook of the precision study (tools/precision_study.py): `q` is either
+    a one-argument function applied to every conv operand, or an object with a
+    ``round(tensor, layer, kind)`` method (kind 'x' = activation, 'w' = weight) that can treat
+    each of the 22 conv layers differently.  Identity by default."""
+    r = getattr(q, 'round', None)
+    return r(t, layer, kind) if r is not None else q(t)
+
+
 def _gn(x, p, prefix, groups=32):
     return F.group_norm(x, groups, p[prefix + '.weight'], p[prefix + '.bias'],
                         GN_EPS)
@@ -172,7 +181,7 @@ def _gn(x, p, prefix, groups=32):
 def _conv_module(x, p, name, act=True, q=_ident):
     """mmcv ConvModule(conv3d k3 s1 p1, bias=False) -> GN(32) -> [ReLU];
     dfm_backbone.py:50-66, 118-127."""
-    y = F.conv3d(q(x), q(p[name + '.conv.weight']), None, 1, 1)
+    y = F.conv3d(_q(q, x, name, 'x'), _q(q, p[name + '.conv.weight'], name, 'w'), None, 1, 1)
     y = _gn(y, p, name + '.gn')
     return F.relu(y) if act else y
 
@@ -180,16 +189,21 @@ def _conv_module(x, p, name, act=True, q=_ident):
 def hourglass(x, p, name, q=_ident):
     """conv_modules.py:129-149 with presqu = postsqu = None (dfm_backbone.py:181)."""
     def cb(t, sub, stride):  # convbn_3d, conv_modules.py:27-43
-        y = F.conv3d(q(t), q(p[f'{name}.{sub}.0.weight']), None, stride, 1)
+        ln = f'{name}.{sub}'
+        y = F.conv3d(_q(q, t, ln, 'x'), _q(q, p[f'{name}.{sub}.0.weight'], ln, 'w'), None,
+                     stride, 1)
         return _gn(y, p, f'{name}.{sub}.1')
 
     def cb_seq(t, sub, stride):  # nn.Sequential(convbn_3d, ReLU)
-        y = F.conv3d(q(t), q(p[f'{name}.{sub}.0.0.weight']), None, stride, 1)
+        ln = f'{name}.{sub}'
+        y = F.conv3d(_q(q, t, ln, 'x'), _q(q, p[f'{name}.{sub}.0.0.weight'], ln, 'w'), None,
+                     stride, 1)
         return F.relu(_gn(y, p, f'{name}.{sub}.0.1'))
 
     def deconv(t, sub):  # ConvTranspose3d k3 p1 op1 s2 + GN, conv_modules.py:104-127
-        y = F.conv_transpose3d(q(t), q(p[f'{name}.{sub}.0.weight']), None, 2,
-                               1, 1)
+        ln = f'{name}.{sub}'
+        y = F.conv_transpose3d(_q(q, t, ln, 'x'), _q(q, p[f'{name}.{sub}.0.weight'], ln, 'w'),
+                               None, 2, 1, 1)
         return _gn(y, p, f'{name}.{sub}.1')
 
     out = cb_seq(x, 'conv1', 2)              # :131
@@ -213,7 +227,8 @@ def _tower(x, p, sfx, q=_ident):
 def _pred(x, p, name, q=_ident):
     """build_depth_pred_module, dfm_backbone.py:118-128."""
     y = _conv_module(x, p, name + '.0', True, q)
-    return F.conv3d(q(y), q(p[name + '.1.weight']), None, 1, 1)
+    return F.conv3d(_q(q, y, name + '.1', 'x'), _q(q, p[name + '.1.weight'], name + '.1', 'w'),
+                    None, 1, 1)
 
 
 def mono_stereo_aggregate(stereo_cost, mono_cost, p, q=_ident):
@@ -593,6 +608,11 @@ def dfm_bev_stage(p_bev, p_head, volume_feat, num_convs=2):
     bev_feat = volume_feat.reshape(-1, cv * nz, ny, nx)
     _, bev = bev_hourglass_forward(p_bev, bev_feat)
     return liga_anchor3d_head_forward(p_head, bev, num_convs)
+
+
+def bf16_round(x):
+    """Round-to-nearest-even to bf16 precision, kept in fp32 (precision study only)."""
+    return x.to(torch.bfloat16).to(torch.float32)
 
 
 def tf32_round(x):

@@ -48,6 +48,21 @@ def reference_function(rel_path, name, namespace):
     raise KeyError(name)
 
 
+def reference_class(rel_path, name, namespace):
+    """Executes ONE top-level class of a reference file verbatim (decorators dropped) in
+    ``namespace``: for classes whose module cannot be imported without mmcv/mmdet."""
+    import ast
+    src = open(os.path.join(REFERENCE_ROOT, rel_path)).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == name:
+            node.decorator_list = []
+            mod = ast.Module(body=[node], type_ignores=[])
+            ns = dict(namespace)
+            exec(compile(mod, rel_path, 'exec'), ns)
+            return ns[name]
+    raise KeyError(name)
+
+
 def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, 'mmdet3d'))
 

@@ -819,3 +819,110 @@ def test_multiview_feature_transformation_mixin_vs_oracle(t, agg, neck):
         e = rel_err(out[0][b], ref[0])
         print('feature_transformation', neck, b, e)
         assert e < TOL
+
+
+# ---------------------------------------------------------------------------
+# 2-D BEV stage: BEVHourglass + LIGAAnchor3DHead and the
+# north_star's "3D box regressions match the reference"
+# ---------------------------------------------------------------------------
+def _bev_modules(c, impl='auto'):
+    gn = dict(type='GN', num_groups=32, requires_grad=True)
+    bev = modules.BEVHourglass(c['volume'].shape[1] * c['volume'].shape[2], 64, norm_cfg=gn,
+                               conv_impl=impl)
+    bev.load_state_dict(c['bev'], strict=True)
+    head = modules.LIGAAnchor3DHead(
+        num_classes=3, in_channels=64, feat_channels=64, num_convs=2, norm_cfg=gn,
+        use_direction_classifier=True,
+        anchor_generator=dict(type='Anchor3DRangeGenerator',
+                              ranges=[[2, -30.4, -1.78, 59.6, 30.4, -1.78]] * 3,
+                              sizes=[[3.9, 1.6, 1.56], [0.8, 0.6, 1.73], [1.76, 0.6, 1.73]],
+                              rotations=[0, 1.57], reshape_out=False),
+        bbox_coder=dict(type='DeltaXYZWLHRBBoxCoder'), conv_impl=impl)
+    head.load_state_dict(c['head'], strict=True)
+    return bev.cuda().eval(), head.cuda().eval()
+
+
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+def test_bev_stage_matches_reference_fixture(impl):
+    """CUDA BEVHourglass + LIGAAnchor3DHead against the verbatim reference run
+    (tests/golden/bev_stage.npz, 44 x 36 cells = 3 x 5 conv tiles with ragged edges)."""
+    gold = np.load(os.path.join(GOLDEN, 'bev_stage.npz'))
+    c = syn.make_bev_case(**syn.BEV_CASE)
+    bev, head = _bev_modules(c, impl)
+    v = c['volume'].cuda()
+    x = v.view(1, -1, v.shape[3], v.shape[4])              # detectors/dfm.py:427-428
+    _, tc0 = capi.launch_counters()
+    prehg, feat = bev(x)                                   # :429
+    cls, box, dirc = head([feat])                          # :432
+    capi.sync_check()
+    _, tc1 = capi.launch_counters()
+    assert (tc1 - tc0 > 0) == (impl == 'auto')
+    assert isinstance(cls, list) and len(cls) == 1
+    for got, key in ((prehg, 'prehg'), (feat, 'bev'), (cls[0], 'cls_score'),
+                     (box[0], 'bbox_pred'), (dirc[0], 'dir_cls_preds')):
+        ref = torch.from_numpy(gold[key])
+        e = rel_err(got, ref)
+        print('bev stage', impl, key, e, 'worst element / tol', assert_close(got, ref, key))
+        assert e < TOL, (key, e)
+
+
+def test_bev_stage_full_size_vs_torch_gpu():
+    """KITTI size (160 channels, 304 x 288 cells): the CUDA stage against the same reference
+    ops run by PyTorch on the GPU with TF32 off."""
+    c = syn.make_bev_case(seed=93, nz=5, ny=304, nx=288)
+    bev, head = _bev_modules(c)
+    v = c['volume'].cuda()
+    x = v.view(1, 160, 304, 288)
+    _, feat = bev(x)
+    cls, box, dirc = head.forward_single(feat)
+    capi.sync_check()
+    pb = {k: t.cuda() for k, t in c['bev'].items()}
+    ph = {k: t.cuda() for k, t in c['head'].items()}
+    with torch.no_grad():
+        _, rfeat = O.bev_hourglass_forward(pb, x)
+        rcls, rbox, rdir = O.liga_anchor3d_head_forward(ph, rfeat)
+    for got, ref, key in ((feat, rfeat, 'bev'), (cls, rcls, 'cls_score'),
+                          (box, rbox, 'bbox_pred'), (dirc, rdir, 'dir_cls_preds')):
+        e = rel_err(got, ref)
+        print('bev stage 304x288', key, e, 'worst element / tol', assert_close(got, ref, key))
+        assert e < TOL, (key, e)
+
+
+def test_box_regression_parity_end_to_end():
+    """north_star: "depth logits and 3D box regressions match the reference PyTorch path on
+    identical inputs within 1e-3".  All-CUDA DfM.simple_test segment (detectors/dfm.py:416-432:
+    DfMBackbone -> DepthHead/FrustumToVoxel -> height compression -> BEVHourglass ->
+    LIGAAnchor3DHead) against the all-oracle pipeline on the same pair."""
+    h, w, d = 64, 128, 16
+    cur, prev, metas, params = syn.make_kitti_pair(23, h, w, d)
+    cfg = syn.depth_cfg_for(d)
+    fc = syn.make_frustum_case(24, h, w, d, (32, 28, 20))
+    metas = copy.deepcopy(metas)
+    metas[0]['cam2img'] = fc['metas'][0]['cam2img']
+    bc = syn.make_bev_case(seed=25, nz=5, ny=28, nx=32)
+    # ---- oracle ----
+    with torch.no_grad():
+        rcost, rstereo, _ = O.dfm_backbone_forward(params, cur, prev, metas, cfg)
+        _, sm, rpreds = O.depth_head_forward(rcost, O.depth_samples(cfg), 4)
+        rvol = O.frustum_to_voxel_forward(fc['params'], rstereo, sm, metas, fc['sem'],
+                                          fc['coordinates_3d'], cfg)
+        rcls, rbox, rdir = O.dfm_bev_stage(bc['bev'], bc['head'], rvol)
+    assert float((rvol != 0).float().mean()) > 0.2
+    # ---- CUDA ----
+    bb = _backbone(params, cfg, 'auto')
+    fr = _frustum_module(fc)
+    bev, head = _bev_modules(bc)
+    with torch.no_grad():
+        cost, stereo, _ = bb(cur.cuda(), prev.cuda(), copy.deepcopy(metas))
+        lg = modules.CostLogits(cost, depth_samples=O.depth_samples(cfg))
+        vol = fr(stereo, lg, metas, fc['sem'].cuda())
+        _, nz, ny, nx = vol.shape[1:]
+        _, feat = bev(vol.view(1, -1, ny, nx))
+        cls, box, dirc = head([feat])
+    capi.sync_check()
+    for got, ref, key in ((cost, rcost, 'depth logits'), (lg.depth_preds, rpreds, 'depth_preds'),
+                          (vol, rvol, 'voxel features'), (cls[0], rcls, 'cls_score'),
+                          (box[0], rbox, 'bbox_pred'), (dirc[0], rdir, 'dir_cls_preds')):
+        e = rel_err(got, ref)
+        print('end to end', key, e, 'worst element / tol', assert_close(got, ref, key))
+        assert e < TOL, (key, e)

@@ -111,6 +111,11 @@ def test_reference_configs_parse_and_build_hot_path(cfg_name):
         nvox = [round((vc['point_cloud_range'][3 + a] - vc['point_cloud_range'][a]) /
                       vc['voxel_size'][a]) for a in range(3)]
         assert nvox == [288, 304, 20]
+        b3 = pkg.build_backbone(dict(model['backbone_3d']))       # BEVHourglass, GN variant
+        assert isinstance(b3, modules.BEVHourglass) and b3.in_channels == 160
+        hd = pkg.build_head(dict(model['bbox_head_3d']))
+        assert isinstance(hd, modules.LIGAAnchor3DHead)
+        assert (hd.num_anchors, hd.cls_out_channels) == (6, 18)
     else:
         n = pkg.build_neck(dict(model['neck_3d']))
         assert isinstance(n, (modules.DfMNeck, modules.OutdoorImVoxelNeck))
@@ -295,3 +300,32 @@ def test_param_sync_hooks_and_guards():
         modules._require_identity_3d_aug(dict(pcd_scale_factor=1.05))
     with pytest.raises(NotImplementedError):
         modules._require_identity_3d_aug(dict(pcd_horizontal_flip=True))
+
+
+def test_bev_stage_state_dict_contract():
+    """BEVHourglass / LIGAAnchor3DHead mirrors take the reference state_dict keys (the same
+    dicts load strict=True into the verbatim reference classes in tests/golden/make_golden.py)
+    and build from the KITTI config block through the registry."""
+    gn = dict(type='GN', num_groups=32, requires_grad=True)
+    c = syn.make_bev_case(seed=1, nz=5, ny=8, nx=8)
+    bev = pkg.build_backbone(dict(type='BEVHourglass', in_channels=160, out_channels=64,
+                                  norm_cfg=gn))
+    bev.load_state_dict(c['bev'], strict=True)
+    head = registry.HEADS.build(dict(
+        type='LIGAAnchor3DHead', num_classes=3, in_channels=64, feat_channels=64, num_convs=2,
+        use_direction_classifier=True, diff_rad_by_sin=True, dir_offset=0.7854,
+        anchor_generator=dict(type='Anchor3DRangeGenerator',
+                              ranges=[[2, -30.4, -1.78, 59.6, 30.4, -1.78]] * 3,
+                              sizes=[[3.9, 1.6, 1.56], [0.8, 0.6, 1.73], [1.76, 0.6, 1.73]],
+                              rotations=[0, 1.57], reshape_out=False),
+        assign_per_class=True, bbox_coder=dict(type='DeltaXYZWLHRBBoxCoder'),
+        loss_cls=dict(type='FocalLoss'), loss_bbox=dict(type='SmoothL1Loss'),
+        loss_dir=dict(type='CrossEntropyLoss'), loss_iou=dict(type='IOU3DLoss'), norm_cfg=gn))
+    head.load_state_dict(c['head'], strict=True)
+    assert head.num_anchors == 6 and head.box_code_size == 7
+    assert head.conv_cls.out_channels == 18 and head.conv_reg.out_channels == 42
+    assert head.conv_dir_cls.out_channels == 12
+    with pytest.raises(AssertionError):   # the SyncBN (LiDAR teacher) variant is not mirrored
+        modules.BEVHourglass(160, 64, norm_cfg=dict(type='SyncBN'))
+    with pytest.raises(RuntimeError):     # no CPU path
+        bev(torch.zeros(1, 160, 8, 8))
