@@ -34,11 +34,13 @@ SYMBOLS = (
     'dfm_neck_destroy', 'dfm_neck_set_param', 'dfm_neck_missing_params',
     'dfm_neck_forward', 'dfm_frustum_create', 'dfm_frustum_destroy',
     'dfm_frustum_set_param', 'dfm_frustum_missing_params', 'dfm_frustum_forward',
-    'dfm_pipeline_forward_host',
+    'dfm_pipeline_forward_host', 'dfm_pipeline_submit_host', 'dfm_pipeline_wait',
     'dfm_bev_hourglass_create', 'dfm_bev_hourglass_destroy', 'dfm_bev_hourglass_set_param',
     'dfm_bev_hourglass_missing_params', 'dfm_bev_hourglass_forward',
     'dfm_anchor_head_create', 'dfm_anchor_head_destroy', 'dfm_anchor_head_set_param',
-    'dfm_anchor_head_missing_params', 'dfm_anchor_head_forward',
+    'dfm_anchor_head_missing_params', 'dfm_anchor_head_forward', 'dfm_voxel_sample',
+    'dfm_backbone_forward_cl', 'dfm_stereo_tail_create', 'dfm_stereo_tail_destroy',
+    'dfm_stereo_tail_set_param', 'dfm_stereo_tail_missing_params', 'dfm_stereo_tail_forward',
 )
 
 
@@ -96,6 +98,16 @@ class AnchorHeadDesc(ctypes.Structure):
     _fields_ = [(n, c_int) for n in
                 ('in_channels', 'feat_channels', 'num_convs', 'cls_channels', 'reg_channels',
                  'dir_channels', 'ny', 'nx', 'conv_impl')]
+
+
+class VoxelSampleDesc(ctypes.Structure):
+    """``dfm_voxel_sample_desc_t``."""
+    _fields_ = [('channels', c_int), ('nx', c_int), ('ny', c_int), ('nz', c_int),
+                ('voxel_range', c_float * 6), ('voxel_size', c_float * 3),
+                ('num_depths', c_int), ('out_h', c_int), ('out_w', c_int),
+                ('downsample_factor', c_int), ('scale_x', c_float), ('scale_y', c_float),
+                ('crop_x', c_float), ('crop_y', c_float), ('flip', c_int), ('img_w', c_int),
+                ('aligned', c_int)]
 
 
 _lib = None
@@ -165,6 +177,9 @@ def lib():
     L.dfm_pipeline_forward_host.argtypes = [vp, vp, vp, vp, vp, POINTER(Geometry),
                                             POINTER(c_double), c_int, c_int, vp, vp, vp,
                                             vp, vp]
+    L.dfm_pipeline_submit_host.argtypes = [vp, vp, vp, vp, vp, POINTER(Geometry),
+                                           POINTER(c_double), c_int, c_int, vp, vp, vp, vp]
+    L.dfm_pipeline_wait.argtypes = [vp]
     L.dfm_bev_hourglass_create.argtypes = [POINTER(BevDesc), POINTER(vp)]
     L.dfm_bev_hourglass_destroy.argtypes = [vp]
     L.dfm_bev_hourglass_set_param.argtypes = [vp, c_char_p, vp, c_longlong]
@@ -175,6 +190,13 @@ def lib():
     L.dfm_anchor_head_set_param.argtypes = [vp, c_char_p, vp, c_longlong]
     L.dfm_anchor_head_missing_params.argtypes = [vp]
     L.dfm_anchor_head_forward.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.dfm_backbone_forward_cl.argtypes = [vp, vp, vp, POINTER(Geometry), vp, vp, vp, vp]
+    L.dfm_stereo_tail_create.argtypes = [c_int, c_int, c_int, POINTER(vp)]
+    L.dfm_stereo_tail_destroy.argtypes = [vp]
+    L.dfm_stereo_tail_set_param.argtypes = [vp, c_char_p, vp, c_longlong]
+    L.dfm_stereo_tail_missing_params.argtypes = [vp]
+    L.dfm_stereo_tail_forward.argtypes = [vp, vp, vp, vp, vp]
+    L.dfm_voxel_sample.argtypes = [POINTER(VoxelSampleDesc), vp, vp, POINTER(c_double), vp, vp]
     _lib = L
     return L
 

@@ -574,12 +574,11 @@ struct WarpLoader8 {
 
 // ----------------------------------------------------------------------------------
 // TMA loader (stride-2 convs): the input was written once by presplit_kernel as bf16 hi / lo
-// pairs in the "pre-split" layout [plane][hi|lo][8-channel chunk][y][x][8 x bf16] (16 bytes per
-// (chunk, voxel), the same 4 bytes per value as fp32), viewed by a rank-4 tensor map
-// {8, W, H, planes*2*chunks}.  One elected thread then stages a whole brick with
-// cp.async.bulk.tensor: per (hi|lo, x/y parity class) ONE box of 9 x 17 positions x 2 chunks with
-// element strides (2, 2) -- the parity de-interleave of the stride-2 brick -- and out-of-range
-// halo positions arrive as zeros.  No loader warp touches the data: the fused GroupNorm /
+// pairs in the parity-planar "pre-split" layout (see presplit_kernel; 16 bytes per (chunk,
+// voxel), the same 4 bytes per value as fp32), viewed by a rank-4 tensor map
+// {8, W/2, H/2, planes*2*4*chunks}.  One elected thread then stages a whole brick with
+// cp.async.bulk.tensor: per (hi|lo, x/y parity class) ONE dense box of 9 x 17 positions x 2
+// chunks, and out-of-range halo positions arrive as zeros.  No loader warp touches the data: the fused GroupNorm /
 // ReLU / residual transform and the bf16 split happened once, in the producer pass.
 // (tests/probe/probe_tma.cu pins the box / stride / zero-fill / byte-count semantics.)
 // ----------------------------------------------------------------------------------
@@ -608,38 +607,72 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 }
 
 // producer pass: value = the fused input transform of `ld` (<= 3 terms), split to bf16 hi / lo,
-// written in the pre-split layout.  out: [Z][2][C/8][H][W] uint4.
+// written in the pre-split layout of a stride-2 consumer: x / y PARITY-PLANAR,
+//   [plane z][hi|lo][y parity][x parity][8-channel chunk][H/2][W/2] x 16 bytes,
+// so every parity class of a stride-2 brick is a DENSE 2-D box for TMA (a strided box --
+// elementStrides 2 -- moves one 16-byte element per request and ran at ~2.5 cycles per element).
+// A warp transforms a run of 64 consecutive x of one row (coalesced 32-byte reads), stages the
+// split values in shared memory and writes 512-byte runs per (hi|lo, x parity, chunk).
+constexpr int PS_XRUN = 64, PS_WARPS = 4, PS_SEG = 33;  // 33: shared-memory segment pitch
+inline size_t presplit_smem_bytes(int C) { return (size_t)PS_WARPS * 4 * (C / 8) * PS_SEG * 16; }
 template <int NT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * PS_WARPS)
 presplit_kernel(const SrcLoader8<NT> ld, int Z, uint4* __restrict__ out) {
-  const int nch = ld.C >> 3;
-  const long long HW = (long long)ld.H * ld.W;
-  const long long total = (long long)Z * HW * nch;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int chunk = (int)(i % nch);
-    const long long v = i / nch;
-    const int z = (int)(v / HW);
-    const long long pos = v - (long long)z * HW;
-    const int y = (int)(pos / ld.W), x = (int)(pos - (long long)y * ld.W);
-    typename SrcLoader8<NT>::Raw r;
-    ld.issue(z, y, x, chunk * 8, r);
-    float val[8];
-    ld.finish(r, chunk * 8, val);
-    uint4* hi = out + ((long long)(z * 2) * nch + chunk) * HW + pos;
-    split_store(val, reinterpret_cast<uint8_t*>(hi), reinterpret_cast<uint8_t*>(hi + nch * HW));
+  extern __shared__ uint4 ps_sm[];
+  const int nch = ld.C >> 3, W = ld.W, H = ld.H, W2 = W >> 1, H2 = H >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint4* sm = ps_sm + (size_t)warp * 4 * nch * PS_SEG;   // [hi|lo][x parity][chunk][33]
+  const int runs_per_row = (W + PS_XRUN - 1) / PS_XRUN;
+  const long long nruns = (long long)Z * H * runs_per_row;
+  for (long long r = (long long)blockIdx.x * PS_WARPS + warp; r < nruns;
+       r += (long long)gridDim.x * PS_WARPS) {
+    const int run = (int)(r % runs_per_row);
+    const long long zy = r / runs_per_row;
+    const int y = (int)(zy % H), z = (int)(zy / H);
+    const int xb = run * PS_XRUN;
+#pragma unroll 4
+    for (int i = lane; i < PS_XRUN * nch; i += 32) {
+      const int xl = i / nch, chunk = i - xl * nch, x = xb + xl;
+      if (x < W) {
+        typename SrcLoader8<NT>::Raw raw;
+        ld.issue(z, y, x, chunk * 8, raw);
+        float val[8];
+        ld.finish(raw, chunk * 8, val);
+        uint4* hi = sm + ((xl & 1) * nch + chunk) * PS_SEG + (xl >> 1);
+        split_store(val, reinterpret_cast<uint8_t*>(hi),
+                    reinterpret_cast<uint8_t*>(hi + 2 * nch * PS_SEG));
+      }
+    }
+    __syncwarp();
+    const int py = y & 1, y2 = y >> 1, x2 = (xb >> 1) + lane;
+    for (int seg = 0; seg < 4 * nch; ++seg) {
+      const int chunk = seg % nch, px = (seg / nch) & 1, hl = seg / (2 * nch);
+      if (2 * x2 + px < W)
+        out[((((long long)(z * 2 + hl) * 4 + py * 2 + px) * nch + chunk) * H2 + y2) * W2 + x2] =
+            sm[seg * PS_SEG + lane];
+    }
+    __syncwarp();
   }
 }
 inline bool presplit_launch(const Src& s, int C, int Z, int H, int W, uint4* out, cudaStream_t st) {
-  const long long total = (long long)Z * H * W * (C / 8);
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-  if (s.n == 1) presplit_kernel<1><<<blocks, 256, 0, st>>>(SrcLoader8<1>{s, C, H, W}, Z, out);
-  else if (s.n == 2) presplit_kernel<2><<<blocks, 256, 0, st>>>(SrcLoader8<2>{s, C, H, W}, Z, out);
-  else presplit_kernel<3><<<blocks, 256, 0, st>>>(SrcLoader8<3>{s, C, H, W}, Z, out);
-  return cudaGetLastError() == cudaSuccess;
+  if ((H | W) & 1) return false;
+  const size_t smem = presplit_smem_bytes(C);
+  const long long nruns = (long long)Z * H * ((W + PS_XRUN - 1) / PS_XRUN);
+  const int blocks = (int)std::min<long long>((nruns + PS_WARPS - 1) / PS_WARPS, 148LL * 12);
+  auto go = [&](auto kern, auto ld) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return false;
+    kern<<<blocks, 32 * PS_WARPS, smem, st>>>(ld, Z, out);
+    return cudaGetLastError() == cudaSuccess;
+  };
+  if (s.n == 1) return go(presplit_kernel<1>, SrcLoader8<1>{s, C, H, W});
+  if (s.n == 2) return go(presplit_kernel<2>, SrcLoader8<2>{s, C, H, W});
+  return go(presplit_kernel<3>, SrcLoader8<3>{s, C, H, W});
 }
 
-// host: tensor map over a pre-split buffer for the stride-2 brick boxes
+// host: tensor map over a pre-split buffer: rank 4 {8 bf16, W/2, H/2, planes*2*4*chunks}, box =
+// one parity class of a stride-2 brick (9 x 17 positions) for two adjacent chunks
 inline bool make_presplit_map_s2(CUtensorMap* map, const void* base, int W, int H,
                                  long long slabs, std::string* err) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -657,10 +690,11 @@ inline bool make_presplit_map_s2(CUtensorMap* map, const void* base, int W, int 
     }
     encode = (EncodeFn)fn;
   }
-  const cuuint64_t dims[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)slabs};
-  const cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-  const cuuint32_t box[4] = {8, 17, 33, 2};   // un-strided extent: 9 x 17 positions, 2 chunks
-  const cuuint32_t estr[4] = {1, 2, 2, 1};
+  const int W2 = W / 2, H2 = H / 2;
+  const cuuint64_t dims[4] = {8, (cuuint64_t)W2, (cuuint64_t)H2, (cuuint64_t)slabs};
+  const cuuint64_t strides[3] = {16, (cuuint64_t)W2 * 16, (cuuint64_t)H2 * W2 * 16};
+  const cuuint32_t box[4] = {8, 9, 17, 2};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims,
                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -865,11 +899,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t st_addr = smem_u32(a_s + s * STAGE_BYTES);
 #pragma unroll
             for (int hl = 0; hl < 2; ++hl) {
-              const int slab = (zi * 2 + hl) * ld.nch_total + chunk0 + cg * NCH;
 #pragma unroll
-              for (int cls = 0; cls < 4; ++cls)  // class = (x parity) * 2 + (y parity)
+              for (int cls = 0; cls < 4; ++cls) {
+                // brick class = (brick x parity) * 2 + (brick y parity).  Brick position bx
+                // is input x = 2*x0 - 1 + bx: brick parity 0 holds the ODD input columns
+                // x0-1, x0, ... (half index), brick parity 1 the EVEN ones x0, x0+1, ...
+                const int bxp = cls >> 1, byp = cls & 1;
+                const int cls_in = (1 - byp) * 2 + (1 - bxp);
+                const int slab = ((zi * 2 + hl) * 4 + cls_in) * ld.nch_total + chunk0 + cg * NCH;
                 tma_load_4d(st_addr + hl * A_HL + cls * (TMA_S2_CLSR * 16), &ld.map,
-                            2 * it.x0 - 1 + (cls >> 1), 2 * it.y0 - 1 + (cls & 1), slab, full_a(s));
+                            it.x0 - 1 + bxp, it.y0 - 1 + byp, slab, full_a(s));
+              }
             }
           }
         }
@@ -1675,7 +1715,7 @@ inline bool tc_conv_presplit(const uint4* ps, int channels, const TcWeights& w, 
   }
   TmaLoader8 ld;
   ld.nch_total = channels / 8;
-  if (!make_presplit_map_s2(&ld.map, ps, g.Wi, g.Hi, (long long)g.Di * 2 * ld.nch_total, err))
+  if (!make_presplit_map_s2(&ld.map, ps, g.Wi, g.Hi, (long long)g.Di * 2 * 4 * ld.nch_total, err))
     return false;
   return tc_dispatch(ld, w, out, stats, g, st, err, opt);
 }

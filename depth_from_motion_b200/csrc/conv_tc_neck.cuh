@@ -96,6 +96,9 @@ struct NeckParams {
   int Nx, Ny, Zi, Zo, Cin, Cout;
   int zmode;
   int tiles_x, tiles_y, nsplit, ncg, n_items;
+  int ntiles;   // tiles_x * tiles_y
+  int tpi;      // tiles per item: their accumulators (Zo * 32 columns each) share the 512 TMEM
+                // columns, so one 110 KB weight image serves tpi tiles before it is replaced
   int* err;
 };
 
@@ -235,8 +238,8 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
     const int chunk = lt & 3;
     uint32_t stage_ctr = 0, w_ctr = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int tile = item / p.nsplit;
-      const int y0 = (tile % p.tiles_x) * NK_BX, x0 = (tile / p.tiles_x) * NK_BY;
+      const int tile0 = (item / p.nsplit) * p.tpi;
+      const int nt = min(p.tpi, p.ntiles - tile0);
       for (int cg = 0; cg < p.ncg; ++cg, ++w_ctr) {
         // this group's weight image (all loader threads), once the previous group's MMAs retired
         mbar_wait(w_empty, (w_ctr & 1) ^ 1, p.err);
@@ -249,46 +252,50 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(w_full);
         }
-        for (int iz = 0; iz < p.Zi; ++iz, ++stage_ctr) {
-          if ((int)(stage_ctr & 1) != lgrp) continue;
-          const int s = stage_ctr % NK_NSTAGE;
-          mbar_wait(empty_a(s), ((stage_ctr / NK_NSTAGE) & 1) ^ 1, p.err);
-          uint8_t* st = a_s + s * NK_STAGE_BYTES;
-          const int c0 = cg * 32 + chunk * 8;
+        for (int t = 0; t < nt; ++t) {
+          const int tile = tile0 + t;
+          const int y0 = (tile % p.tiles_x) * NK_BX, x0 = (tile / p.tiles_x) * NK_BY;
+          for (int iz = 0; iz < p.Zi; ++iz, ++stage_ctr) {
+            if ((int)(stage_ctr & 1) != lgrp) continue;
+            const int s = stage_ctr % NK_NSTAGE;
+            mbar_wait(empty_a(s), ((stage_ctr / NK_NSTAGE) & 1) ^ 1, p.err);
+            uint8_t* st = a_s + s * NK_STAGE_BYTES;
+            const int c0 = cg * 32 + chunk * 8;
 #pragma unroll
-          for (int k0 = 0; k0 < NITEM; k0 += LB) {
-            typename NeckLoader<NT>::Raw raw[LB];
-            bool inb[LB], live[LB];
-            int soff[LB];
+            for (int k0 = 0; k0 < NITEM; k0 += LB) {
+              typename NeckLoader<NT>::Raw raw[LB];
+              bool inb[LB], live[LB];
+              int soff[LB];
 #pragma unroll
-            for (int b = 0; b < LB; ++b) {
-              const int i = lt + (k0 + b) * LG_THREADS;
-              live[b] = (k0 + b) < NITEM && i < NPOS * 4;
-              const int pos = i >> 2;
-              const int bx = pos % NK_PX, by = pos / NK_PX;
-              const int gy = y0 - 1 + bx, gx = x0 - 1 + by;
-              inb[b] = live[b] && gx >= 0 && gx < p.Nx && gy >= 0 && gy < p.Ny;
-              soff[b] = (chunk * NK_ROWS + pos) * 16;
-              if (inb[b])
-                NeckLoader<NT>::issue(p, ((long long)gx * p.Ny + gy) * p.Zi + iz, c0, raw[b]);
-            }
+              for (int b = 0; b < LB; ++b) {
+                const int i = lt + (k0 + b) * LG_THREADS;
+                live[b] = (k0 + b) < NITEM && i < NPOS * 4;
+                const int pos = i >> 2;
+                const int bx = pos % NK_PX, by = pos / NK_PX;
+                const int gy = y0 - 1 + bx, gx = x0 - 1 + by;
+                inb[b] = live[b] && gx >= 0 && gx < p.Nx && gy >= 0 && gy < p.Ny;
+                soff[b] = (chunk * NK_ROWS + pos) * 16;
+                if (inb[b])
+                  NeckLoader<NT>::issue(p, ((long long)gx * p.Ny + gy) * p.Zi + iz, c0, raw[b]);
+              }
 #pragma unroll
-            for (int b = 0; b < LB; ++b) {
-              if (live[b]) {
-                float v[8];
-                if (inb[b]) {
-                  NeckLoader<NT>::finish(p, raw[b], c0, v);
-                } else {
+              for (int b = 0; b < LB; ++b) {
+                if (live[b]) {
+                  float v[8];
+                  if (inb[b]) {
+                    NeckLoader<NT>::finish(p, raw[b], c0, v);
+                  } else {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                  }
+                  split_store(v, st + soff[b], st + A_HL + soff[b]);
                 }
-                split_store(v, st + soff[b], st + A_HL + soff[b]);
               }
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a(s));
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_a(s));
         }
       }
     }
@@ -303,48 +310,52 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
       // the previous item's accumulators must have been drained (and re-zeroed)
       mbar_wait(acc_empty, (item_ctr & 1) ^ 1, p.err);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int tile0 = (item / p.nsplit) * p.tpi;
+      const int nt = min(p.tpi, p.ntiles - tile0);
       for (int cg = 0; cg < p.ncg; ++cg, ++w_ctr) {
         mbar_wait(w_full, w_ctr & 1, p.err);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int iz = 0; iz < p.Zi; ++iz, ++stage_ctr) {
-          const int s = stage_ctr % NK_NSTAGE;
-          mbar_wait(full_a(s), (stage_ctr / NK_NSTAGE) & 1, p.err);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          int n0, nblk, zo0;
-          nk_plane_map(p.zmode, iz, p.Zo, n0, nblk, zo0);
-          const uint32_t d0 = tmem_u + (uint32_t)zo0 * NK_NCTA;
-          const uint32_t idesc = idesc_bf16(nblk * NK_NCTA);
-          const uint32_t a_lo_stage = (((a_base + s * NK_STAGE_BYTES) >> 4) & 0x3FFF) | (A_LBO16 << 16);
-          const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFF) + (uint32_t)n0 + (B_LBO16 << 16);
-          uint64_t da[2][2], db[2][2];
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            da[ks][0] = pack64(a_lo_stage + 2 * ks * A_LBO16, a_desc_hi);
-            da[ks][1] = pack64(a_lo_stage + 2 * ks * A_LBO16 + A_HL16, a_desc_hi);
-            db[ks][0] = pack64(b_lo0 + 2 * ks * B_LBO16, b_desc_hi);
-            db[ks][1] = pack64(b_lo0 + 2 * ks * B_LBO16 + w_hi16, b_desc_hi);
-          }
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            if (elect_one()) {
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                umma_bf16(d0, da[ks][0], db[ks][0], idesc, 1u);
-                umma_bf16(d0, da[ks][1], db[ks][0], idesc, 1u);
-                umma_bf16(d0, da[ks][0], db[ks][1], idesc, 1u);
-              }
-            }
-            const uint32_t ainc = (tap == 2 || tap == 5) ? (uint32_t)(NK_PX - 2) : 1u;
+        for (int t = 0; t < nt; ++t) {
+          for (int iz = 0; iz < p.Zi; ++iz, ++stage_ctr) {
+            const int s = stage_ctr % NK_NSTAGE;
+            mbar_wait(full_a(s), (stage_ctr / NK_NSTAGE) & 1, p.err);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int n0, nblk, zo0;
+            nk_plane_map(p.zmode, iz, p.Zo, n0, nblk, zo0);
+            const uint32_t d0 = tmem_u + (uint32_t)(t * p.Zo + zo0) * NK_NCTA;
+            const uint32_t idesc = idesc_bf16(nblk * NK_NCTA);
+            const uint32_t a_lo_stage = (((a_base + s * NK_STAGE_BYTES) >> 4) & 0x3FFF) | (A_LBO16 << 16);
+            const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFF) + (uint32_t)n0 + (B_LBO16 << 16);
+            uint64_t da[2][2], db[2][2];
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              desc_add(da[ks][0], ainc);
-              desc_add(da[ks][1], ainc);
-              desc_add(db[ks][0], NK_TAP16);
-              desc_add(db[ks][1], NK_TAP16);
+              da[ks][0] = pack64(a_lo_stage + 2 * ks * A_LBO16, a_desc_hi);
+              da[ks][1] = pack64(a_lo_stage + 2 * ks * A_LBO16 + A_HL16, a_desc_hi);
+              db[ks][0] = pack64(b_lo0 + 2 * ks * B_LBO16, b_desc_hi);
+              db[ks][1] = pack64(b_lo0 + 2 * ks * B_LBO16 + w_hi16, b_desc_hi);
             }
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  umma_bf16(d0, da[ks][0], db[ks][0], idesc, 1u);
+                  umma_bf16(d0, da[ks][1], db[ks][0], idesc, 1u);
+                  umma_bf16(d0, da[ks][0], db[ks][1], idesc, 1u);
+                }
+              }
+              const uint32_t ainc = (tap == 2 || tap == 5) ? (uint32_t)(NK_PX - 2) : 1u;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                desc_add(da[ks][0], ainc);
+                desc_add(da[ks][1], ainc);
+                desc_add(db[ks][0], NK_TAP16);
+                desc_add(db[ks][1], NK_TAP16);
+              }
+            }
+            if (elect_one()) umma_commit(empty_a(s));
+            __syncwarp();
           }
-          if (elect_one()) umma_commit(empty_a(s));
-          __syncwarp();
         }
         if (elect_one()) umma_commit(w_empty);  // weights may be replaced once these retire
         __syncwarp();
@@ -357,24 +368,29 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
     const int m = warp * 32 + lane;
     uint32_t item_ctr = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_ctr) {
-      const int tile = item / p.nsplit;
-      const int y = (tile % p.tiles_x) * NK_BX + (m & 7), x = (tile / p.tiles_x) * NK_BY + (m >> 3);
-      const bool ok = x < p.Nx && y < p.Ny;
+      const int tile0 = (item / p.nsplit) * p.tpi;
+      const int nt = min(p.tpi, p.ntiles - tile0);
       mbar_wait(acc_full, item_ctr & 1, p.err);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int zo = 0; zo < p.Zo; ++zo) {
-        uint32_t r[NK_NCTA];
-        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)zo * NK_NCTA;
-        tmem_ld<NK_NCTA>(ta, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tmem_zero<NK_NCTA>(ta);
-        if (ok) {
-          float4* dst = reinterpret_cast<float4*>(
-              p.out + (((long long)x * p.Ny + y) * p.Zo + zo) * p.Cout + split * NK_NCTA);
+      for (int t = 0; t < nt; ++t) {
+        const int tile = tile0 + t;
+        const int y = (tile % p.tiles_x) * NK_BX + (m & 7), x = (tile / p.tiles_x) * NK_BY + (m >> 3);
+        const bool ok = x < p.Nx && y < p.Ny;
+        for (int zo = 0; zo < p.Zo; ++zo) {
+          uint32_t r[NK_NCTA];
+          const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                              (uint32_t)(t * p.Zo + zo) * NK_NCTA;
+          tmem_ld<NK_NCTA>(ta, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tmem_zero<NK_NCTA>(ta);
+          if (ok) {
+            float4* dst = reinterpret_cast<float4*>(
+                p.out + (((long long)x * p.Ny + y) * p.Zo + zo) * p.Cout + split * NK_NCTA);
 #pragma unroll
-          for (int q = 0; q < NK_NCTA / 4; ++q)
-            dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                 __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            for (int q = 0; q < NK_NCTA / 4; ++q)
+              dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+          }
         }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -405,7 +421,18 @@ inline bool neck_tc_conv(const Src& s, const NeckTcWeights& w, float* out, const
   p.tiles_y = (g.Di + NK_BY - 1) / NK_BY;   // along Nx
   p.nsplit = g.Cout / 32;
   p.ncg = g.Cin / 32;
-  p.n_items = p.tiles_x * p.tiles_y * p.nsplit;
+  p.ntiles = p.tiles_x * p.tiles_y;
+  // tiles per item: as many as the 512 TMEM columns hold (Zo * 32 columns per tile), but not so
+  // many that the persistent grid runs short of items
+  const int tpi_env = getenv("DFM_NECK_TPI") ? atoi(getenv("DFM_NECK_TPI")) : 0;  // tests / A-B runs
+  {
+    const int cap = std::max(1, 512 / (g.Wo * NK_NCTA));
+    const int sms0 = tc_sm_count();
+    int tpi = std::min(cap, std::max(1, p.ntiles * p.nsplit / (2 * sms0)));
+    if (tpi_env > 0) tpi = std::min(cap, tpi_env);
+    p.tpi = std::max(1, tpi);
+  }
+  p.n_items = (p.ntiles + p.tpi - 1) / p.tpi * p.nsplit;
   p.err = tc_err_flag().get();
   const int sms = tc_sm_count();
   int grid = std::max(p.nsplit, sms / p.nsplit * p.nsplit);

@@ -502,6 +502,8 @@ struct dfm_backbone {
     const float* h_prev = nullptr;
     bool pending = false;      // holds a prefetched pair that no forward has consumed yet
     cudaEvent_t ready = nullptr;
+    cudaEvent_t consumed = nullptr;  // recorded after the last kernel that reads this slot
+                                     // (asynchronous pipeline: a later prefetch waits for it)
     unsigned long long tick = 0;
   } stage[2];
   unsigned long long stage_tick = 0;
@@ -764,7 +766,10 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
   g = geom_s(D2, H2, W2, 2 * cv, 2 * cv, 1, 1, 1, 1, 1, 1);
   DFM_TRY(run_conv(src1(term(t.b1, &t.gc1, 1)), t.c2, t.b2.p, g, impl, st, &t.gc2, zw_at(2)));
   g = geom_s(D2, H2, W2, 2 * cv, 2 * cv, 2, 2, 2, 1, 1, 1);
-  if (tma_ok(t.c3) && dfm::tc_mode_of(g) == dfm::TC_S2)
+  // (conv3, half resolution: measured neutral-to-worse with TMA -- 0.106 + 0.100 ms producer vs
+  // 0.149 ms with register loaders -- so it is opt-in)
+  static const bool tma_c3 = getenv("DFM_TMA_CONV3") != nullptr;
+  if (tma_c3 && tma_ok(t.c3) && dfm::tc_mode_of(g) == dfm::TC_S2)
     DFM_TRY(run_conv_presplit(src1(term(t.b2, &t.gc2, 1)), t.ps2, t.c3, t.b3.p, g, st, &t.gc3,
                               zw_at(4)));
   else
@@ -961,8 +966,10 @@ int dfm_backbone_create(const dfm_backbone_desc_t* desc, dfm_backbone_t** out) {
   return DFM_OK;
 }
 
+void pipeline_forget(const dfm_backbone* bb);  // pipeline_api.inc
 int dfm_backbone_destroy(dfm_backbone_t* bb) {
   if (!bb) return DFM_OK;
+  pipeline_forget(bb);
   tower_release(bb->st);
   tower_release(bb->mo);
   for (DevBuf* b : {&bb->cur_nhwc, &bb->prev_nhwc, &bb->depths, &bb->wagg, &bb->waggT, &bb->cost,
@@ -970,8 +977,10 @@ int dfm_backbone_destroy(dfm_backbone_t* bb) {
                     &bb->stage[1].prev, &bb->out_st, &bb->out_mo, &bb->pipe_sem, &bb->pipe_vox,
                     &bb->pipe_preds, &bb->pipe_samples})
     b->release();
-  for (auto& hs : bb->stage)
+  for (auto& hs : bb->stage) {
     if (hs.ready) cudaEventDestroy(hs.ready);
+    if (hs.consumed) cudaEventDestroy(hs.consumed);
+  }
   delete bb;
   return DFM_OK;
 }
@@ -1034,7 +1043,8 @@ namespace {
 // the cur-frame features)
 int backbone_forward_impl(dfm_backbone_t* bb, const float* d_cur, const float* d_prev,
                           const dfm_geometry_t* geom, float* d_cost, float* d_stereo,
-                          float* d_mono, void* stream, cudaEvent_t prev_ready) {
+                          float* d_mono, void* stream, cudaEvent_t prev_ready,
+                          bool channels_last = false) {
   if (!bb || !d_cur || !d_prev || !geom) return fail(DFM_ERR_INVALID, "null argument");
   if (dfm::tc_consume_error())
     return fail(DFM_ERR_CUDA, "an earlier tensor-core conv kernel timed out on an mbarrier "
@@ -1047,13 +1057,13 @@ int backbone_forward_impl(dfm_backbone_t* bb, const float* d_cur, const float* d
   ProfScope ps_all("backbone_forward_total", 0.0, st);
   const int C = bb->d.in_channels;
   const long long HW = (long long)bb->d.feat_h * bb->d.feat_w;
-  {
+  if (!channels_last) {
     ProfScope ps("nchw_to_nhwc_cur", 0.0, st);
     DFM_TRY(to_nhwc(d_cur, bb->cur_nhwc.p, C, HW, st));
   }
   dfm::WarpLoader wl{};
-  wl.cur = bb->cur_nhwc.p;
-  wl.prev = bb->prev_nhwc.p;
+  wl.cur = channels_last ? d_cur : bb->cur_nhwc.p;
+  wl.prev = channels_last ? d_prev : bb->prev_nhwc.p;
   wl.depths = bb->depths.p;
   wl.C = C;
   wl.first = 0;
@@ -1062,7 +1072,7 @@ int backbone_forward_impl(dfm_backbone_t* bb, const float* d_cur, const float* d
   dfm::ZExpand ze_mono{bb->D, bb->D, 0, 0};
   DFM_TRY(tower_forward(bb, bb->mo, true, wl, d_mono, st, &ze_mono));
   if (prev_ready) CU_TRY(cudaStreamWaitEvent(st, prev_ready, 0));
-  {
+  if (!channels_last) {
     ProfScope ps("nchw_to_nhwc_prev", 0.0, st);
     DFM_TRY(to_nhwc(d_prev, bb->prev_nhwc.p, C, HW, st));
   }
@@ -1142,6 +1152,13 @@ int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_
   return backbone_forward_impl(bb, d_cur, d_prev, geom, d_cost, d_stereo, d_mono, stream, nullptr);
 }
 
+int dfm_backbone_forward_cl(dfm_backbone_t* bb, const float* d_cur_cl, const float* d_prev_cl,
+                            const dfm_geometry_t* geom, float* d_cost, float* d_stereo,
+                            float* d_mono, void* stream) {
+  return backbone_forward_impl(bb, d_cur_cl, d_prev_cl, geom, d_cost, d_stereo, d_mono, stream,
+                               nullptr, true);
+}
+
 const float* dfm_backbone_cost_device(const dfm_backbone_t* bb) { return bb ? bb->cost.p : nullptr; }
 const float* dfm_backbone_stereo_feat_device(const dfm_backbone_t* bb) {
   return bb ? bb->st.cur.p : nullptr;
@@ -1169,6 +1186,7 @@ int stage_alloc(dfm_backbone::HostStage& hs, size_t nfeat) {
   DFM_TRY(hs.cur.alloc(nfeat));
   DFM_TRY(hs.prev.alloc(nfeat));
   if (!hs.ready) CU_TRY(cudaEventCreateWithFlags(&hs.ready, cudaEventDisableTiming));
+  if (!hs.consumed) CU_TRY(cudaEventCreateWithFlags(&hs.consumed, cudaEventDisableTiming));
   return DFM_OK;
 }
 }  // namespace
@@ -1178,7 +1196,8 @@ namespace {
 // dfm_backbone_prefetch_host, else a fresh copy whose prev half rides the side stream
 // underneath the mono tower (*prev_ready is the event to wait for before reading d_prev).
 int stage_host_pair(dfm_backbone_t* bb, const float* h_cur, const float* h_prev, cudaStream_t st,
-                    float** d_cur_out, float** d_prev_out, cudaEvent_t* prev_ready) {
+                    float** d_cur_out, float** d_prev_out, cudaEvent_t* prev_ready,
+                    int* slot_out = nullptr) {
   const size_t nfeat = (size_t)bb->d.in_channels * bb->d.feat_h * bb->d.feat_w;
   HostCopyCtx* cx = nullptr;
   DFM_TRY(host_copy_ctx(&cx));
@@ -1196,6 +1215,7 @@ int stage_host_pair(dfm_backbone_t* bb, const float* h_cur, const float* h_prev,
     d_cur = hs.cur.p;
     d_prev = hs.prev.p;
     CU_TRY(cudaStreamWaitEvent(st, hs.ready, 0));
+    if (slot_out) *slot_out = hit;
   } else {
     const int slot = !bb->stage[0].pending ? 0 : !bb->stage[1].pending ? 1
                      : (bb->stage[0].tick <= bb->stage[1].tick ? 0 : 1);
@@ -1211,6 +1231,7 @@ int stage_host_pair(dfm_backbone_t* bb, const float* h_cur, const float* h_prev,
     CU_TRY(cudaMemcpyAsync(d_prev, h_prev, nfeat * 4, cudaMemcpyHostToDevice, cx->stream));
     CU_TRY(cudaEventRecord(cx->prev_done, cx->stream));
     *prev_ready = cx->prev_done;
+    if (slot_out) *slot_out = slot;
   }
   *d_cur_out = d_cur;
   *d_prev_out = d_prev;
@@ -1230,7 +1251,9 @@ int dfm_backbone_prefetch_host(dfm_backbone_t* bb, const float* h_cur, const flo
              : (bb->stage[0].tick <= bb->stage[1].tick ? 0 : 1);
   dfm_backbone::HostStage& hs = bb->stage[slot];
   DFM_TRY(stage_alloc(hs, nfeat));
-  // forward_host synchronises before it returns, so nothing on the device still reads this slot
+  // the synchronous entry points return after the device is done with this slot; the
+  // asynchronous pipeline records `consumed` after the last kernel that reads it
+  CU_TRY(cudaStreamWaitEvent(cx->stream, hs.consumed, 0));
   CU_TRY(cudaMemcpyAsync(hs.cur.p, h_cur, nfeat * 4, cudaMemcpyHostToDevice, cx->stream));
   CU_TRY(cudaMemcpyAsync(hs.prev.p, h_prev, nfeat * 4, cudaMemcpyHostToDevice, cx->stream));
   CU_TRY(cudaEventRecord(hs.ready, cx->stream));
@@ -1398,3 +1421,5 @@ int dfm_depth_head_forward(const float* d_cost, const float* d_depth_samples, in
 #include "frustum_api.inc"
 #include "pipeline_api.inc"
 #include "bev_api.inc"
+#include "voxel_sample_api.inc"
+#include "stereo_tail_api.inc"

@@ -3,10 +3,9 @@
 //     (dfm_backbone.py:128) as a CUDA-core kernel.  The op reads V*32 floats and writes V
 //     (0.43 GB -> ~0.07 ms at the copy bandwidth); on the tensor-core conv it ran as an N = 96
 //     MMA with 1/32 useful columns (0.58 ms per frame).  Formulation: per INPUT voxel, the 27
-//     per-tap dot products q_t = <x, w_t> (864 FMAs whose weight operands come straight from
-//     the constant bank: the weights are a __grid_constant__ kernel parameter and every index
-//     is a compile-time constant, so there is no load instruction per weight), staged in
-//     shared memory; per OUTPUT voxel, out(o) = sum_t q_t(o + off_t) is 27 shared-memory reads.
+//     per-tap dot products q_t = <x, w_t> (864 FMAs whose weight operands come from the
+//     constant bank: the weights are a __grid_constant__ kernel parameter and every index is a
+//     compile-time constant), staged in shared memory; per OUTPUT voxel, out(o) = sum_t q_t(o + off_t) is 27 shared-memory reads.
 //     A block owns a 26 x 16 (x, y) output tile (28 x 18 halo = 504 positions, two per thread)
 //     and marches along z with three running accumulators per output pixel.
 //   * depth_head4_kernel  -- DepthHead.forward with four consecutive x pixels per thread so the
@@ -33,146 +32,113 @@ struct LogitsConvParams {
   int tiles_x, tiles_y, zchunks;
 };
 
-__global__ void __launch_bounds__(LC_THREADS, 2)
+// Variants measured on B200 (profiles/r02_tail_kernels.md): this one (weights from the constant
+// bank, one position at a time) 0.31 + 0.14 ms for the two towers; a persistent grid with
+// software-prefetched positions 0.39 + 0.16; packed fma.rn.f32x2 with shared-memory weights
+// 0.40 + 0.18 (FFMA2 halves the issue slots but not the FMA-pipe cycles, and the weight reads
+// move to the LSU).  ncu: FMA pipe 39 % active, top stalls long-scoreboard (the 128-byte row
+// of a position) and the two barriers per plane.
+__global__ void __launch_bounds__(LC_THREADS)
 logits_conv_kernel(const __grid_constant__ LogitsConvParams p, float* __restrict__ out) {
   extern __shared__ float lc_q[];   // [27][LC_NPOS]
   float (*q)[LC_NPOS] = reinterpret_cast<float (*)[LC_NPOS]>(lc_q);
-  __shared__ float4 aff[16];        // scale[32] | shift[32] of the input term
   const int tid = threadIdx.x;
-  if (tid < 64) {
-    float v = tid < 32 ? 1.f : 0.f;
-    if (p.t.scale) v = tid < 32 ? __ldg(p.t.scale + tid) : __ldg(p.t.shift + tid - 32);
-    reinterpret_cast<float*>(aff)[tid] = v;
-  }
+  int b = blockIdx.x;
+  const int tx_i = b % p.tiles_x;
+  b /= p.tiles_x;
+  const int ty_i = b % p.tiles_y;
+  const int zc = b / p.tiles_y;
+  const int x0 = tx_i * LC_TX, y0 = ty_i * LC_TY;
+  const int z_lo = zc * LC_ZCHUNK, z_hi = min(p.D, z_lo + LC_ZCHUNK);
   const long long plane = (long long)p.H * p.W;
-  const int nitems = p.tiles_x * p.tiles_y * p.zchunks;
-  // output pixels of this thread inside a tile: tile-linear indices tid and tid + 256
+
+  // per-channel affine of the input term, in registers (32 + 32)
+  float sc[32], sh[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    sc[c] = p.t.scale ? __ldg(p.t.scale + c) : 1.f;
+    sh[c] = p.t.scale ? __ldg(p.t.shift + c) : 0.f;
+  }
+  // the (up to) two output pixels of this thread: tile-linear indices tid and tid + 256
   int oy[2], ox[2];
+  bool olive[2];
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const int i = tid + k * LC_THREADS;
     oy[k] = i / LC_TX;
     ox[k] = i % LC_TX;
+    olive[k] = i < LC_TX * LC_TY && y0 + oy[k] < p.H && x0 + ox[k] < p.W;
   }
-  // input positions of this thread inside the halo
-  int py[2], pxx[2];
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int pos = tid + k * LC_THREADS;
-    py[k] = pos / LC_PX;
-    pxx[k] = pos % LC_PX;
-  }
-  __syncthreads();
+  float accA[2] = {0.f, 0.f}, accB[2] = {0.f, 0.f};  // output planes zi-1 and zi
 
-  // persistent: items (tile, z chunk) are dealt round-robin; consecutive items of a block are
-  // far apart, consecutive blocks work on neighbouring tiles of the same planes (L2 halo reuse)
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    int b = item;
-    const int tx_i = b % p.tiles_x;
-    b /= p.tiles_x;
-    const int ty_i = b % p.tiles_y;
-    const int zc = b / p.tiles_y;
-    const int x0 = tx_i * LC_TX, y0 = ty_i * LC_TY;
-    const int z_lo = zc * LC_ZCHUNK, z_hi = min(p.D, z_lo + LC_ZCHUNK);
-    bool olive[2], inb[2];
-    long long goff[2];
+  for (int zi = max(z_lo - 1, 0); zi <= min(z_hi, p.D - 1); ++zi) {
+    // ---- phase 1: q_t of this input plane's halo positions ----
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+      const int pos = tid + k * LC_THREADS;
+      if (pos >= LC_NPOS) break;
+      const int py = pos / LC_PX, px = pos % LC_PX;
+      const int gy = y0 - 1 + py, gx = x0 - 1 + px;
+      if (gy < 0 || gy >= p.H || gx < 0 || gx >= p.W) {
+#pragma unroll
+        for (int t = 0; t < 27; ++t) q[t][pos] = 0.f;
+        continue;
+      }
+      const float4* src = reinterpret_cast<const float4*>(
+          p.t.x + ((long long)term_plane(p.t, zi) * plane + (long long)gy * p.W + gx) * 32);
+      float x[32];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const float4 a = __ldg(src + v);
+        x[4 * v] = a.x; x[4 * v + 1] = a.y; x[4 * v + 2] = a.z; x[4 * v + 3] = a.w;
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        x[c] = fmaf(x[c], sc[c], sh[c]);
+        if (p.t.relu) x[c] = fmaxf(x[c], 0.f);
+      }
+#pragma unroll
+      for (int t = 0; t < 27; ++t) {
+        float a0 = 0.f, a1 = 0.f;   // two chains per tap
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          a0 = fmaf(x[c], p.w[t * 32 + c], a0);
+          a1 = fmaf(x[c + 1], p.w[t * 32 + c + 1], a1);
+        }
+        q[t][pos] = a0 + a1;
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: gather.  Input plane zi feeds output planes zi-1 (kz = 2), zi (kz = 1)
+    // and zi+1 (kz = 0); out(zi-1) is complete after this plane.
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      olive[k] = tid + k * LC_THREADS < LC_TX * LC_TY && y0 + oy[k] < p.H && x0 + ox[k] < p.W;
-      const int gy = y0 - 1 + py[k], gx = x0 - 1 + pxx[k];
-      inb[k] = tid + k * LC_THREADS < LC_NPOS && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-      goff[k] = ((long long)gy * p.W + gx) * 32;
-    }
-    float accA[2] = {0.f, 0.f}, accB[2] = {0.f, 0.f};  // output planes zi-1 and zi
-    const int zi0 = max(z_lo - 1, 0), zi1 = min(z_hi, p.D - 1);
-    // raw channels of position 0 of the first plane; every later load is issued one position
-    // ahead of its use so its latency hides behind 864 FMAs
-    float4 nxt[8];
-    auto issue = [&](int zi, int k) {
-      if (inb[k]) {
-        const float4* src = reinterpret_cast<const float4*>(
-            p.t.x + (long long)term_plane(p.t, zi) * plane * 32 + goff[k]);
+      if (!olive[k]) continue;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int v = 0; v < 8; ++v) nxt[v] = __ldg(src + v);
-      }
-    };
-    issue(zi0, 0);
-    for (int zi = zi0; zi <= zi1; ++zi) {
-      // ---- phase 1: q_t of this input plane's halo positions ----
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int pos = tid + k * LC_THREADS;
-        float x[32];
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          x[4 * v] = nxt[v].x; x[4 * v + 1] = nxt[v].y; x[4 * v + 2] = nxt[v].z; x[4 * v + 3] = nxt[v].w;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int pos = (oy[k] + ky) * LC_PX + ox[k] + kx;
+          s0 += q[0 * 9 + ky * 3 + kx][pos];
+          s1 += q[1 * 9 + ky * 3 + kx][pos];
+          s2 += q[2 * 9 + ky * 3 + kx][pos];
         }
-        const bool have = inb[k];
-        // prefetch: the other position of this plane, or position 0 of the next plane
-        if (k == 0) issue(zi, 1);
-        else if (zi < zi1) issue(zi + 1, 0);
-        if (pos < LC_NPOS) {
-          if (!have) {
-#pragma unroll
-            for (int t = 0; t < 27; ++t) q[t][pos] = 0.f;
-          } else {
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              const float4 s4 = aff[v], h4 = aff[8 + v];
-              x[4 * v] = fmaf(x[4 * v], s4.x, h4.x);
-              x[4 * v + 1] = fmaf(x[4 * v + 1], s4.y, h4.y);
-              x[4 * v + 2] = fmaf(x[4 * v + 2], s4.z, h4.z);
-              x[4 * v + 3] = fmaf(x[4 * v + 3], s4.w, h4.w);
-            }
-            if (p.t.relu) {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) x[c] = fmaxf(x[c], 0.f);
-            }
-#pragma unroll
-            for (int t = 0; t < 27; ++t) {
-              float a0 = 0.f, a1 = 0.f;   // two chains per tap
-#pragma unroll
-              for (int c = 0; c < 32; c += 2) {
-                a0 = fmaf(x[c], p.w[t * 32 + c], a0);
-                a1 = fmaf(x[c + 1], p.w[t * 32 + c + 1], a1);
-              }
-              q[t][pos] = a0 + a1;
-            }
-          }
-        }
-      }
-      __syncthreads();
-      // ---- phase 2: gather.  Input plane zi feeds output planes zi-1 (kz = 2), zi (kz = 1)
-      // and zi+1 (kz = 0); out(zi-1) is complete after this plane.
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (!olive[k]) continue;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int pos = (oy[k] + ky) * LC_PX + ox[k] + kx;
-            s0 += q[0 * 9 + ky * 3 + kx][pos];
-            s1 += q[1 * 9 + ky * 3 + kx][pos];
-            s2 += q[2 * 9 + ky * 3 + kx][pos];
-          }
-        const int zo = zi - 1;
-        if (zo >= z_lo && zo < z_hi)
-          out[(long long)zo * plane + (long long)(y0 + oy[k]) * p.W + x0 + ox[k]] = accA[k] + s2;
-        accA[k] = accB[k] + s1;
-        accB[k] = s0;
-      }
-      __syncthreads();
+      const int zo = zi - 1;
+      if (zo >= z_lo && zo < z_hi)
+        out[(long long)zo * plane + (long long)(y0 + oy[k]) * p.W + x0 + ox[k]] = accA[k] + s2;
+      accA[k] = accB[k] + s1;
+      accB[k] = s0;
     }
-    // the last output plane of the chunk when it is the volume's last plane (no input plane
-    // z_hi exists to flush it)
-    if (z_hi == p.D) {
+    __syncthreads();
+  }
+  // the last output plane of the chunk when it is the volume's last plane (no input plane
+  // z_hi exists to flush it)
+  if (z_hi == p.D) {
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
-        if (olive[k])
-          out[(long long)(p.D - 1) * plane + (long long)(y0 + oy[k]) * p.W + x0 + ox[k]] = accA[k];
-    }
+    for (int k = 0; k < 2; ++k)
+      if (olive[k])
+        out[(long long)(p.D - 1) * plane + (long long)(y0 + oy[k]) * p.W + x0 + ox[k]] = accA[k];
   }
 }
 
@@ -196,35 +162,43 @@ inline bool logits_conv_launch(const Src& s, const float* h_w /*[27][32] host*/,
       return false;
     attr_done = true;
   }
-  const int grid = (int)std::min<long long>(blocks, 2LL * tc_sm_count());
-  logits_conv_kernel<<<grid, LC_THREADS, smem, st>>>(p, out);
+  logits_conv_kernel<<<(unsigned)blocks, LC_THREADS, smem, st>>>(p, out);
   return cudaGetLastError() == cudaSuccess;
 }
 
 // ---------------------------------------------------------------------------------
-// DepthHead.forward, four x pixels per thread (requires (Wo * f) % 4 == 0)
+// DepthHead.forward, four x pixels per thread (requires (Wo * f) % 4 == 0).
+// Structure chosen from the ncu profile of the first version (issue-bound at 120 instructions
+// per 4-pixel depth bin): the two low-res rows a block interpolates between are blended ONCE
+// while staging (R[z][c] = ly0*row0 + ly1*row1), the depth loop walks low-res intervals with
+// the carried pair (b0, b1) and an inner loop over the bins of the interval, all per-bin
+// constants come from shared-memory tables.  ~38 instructions per 4-pixel bin and pass.
 // ---------------------------------------------------------------------------------
 constexpr int DH4_PX = 128;   // output pixels along x per block
 __host__ __device__ inline int dh4_ncols(int f) { return DH4_PX / f + 3; }
-inline size_t dh4_smem_bytes(int D, int f) { return (size_t)D * 2 * dh4_ncols(f) * sizeof(float); }
+inline size_t dh4_smem_bytes(int D, int f) { return (size_t)D * dh4_ncols(f) * sizeof(float); }
 
 __global__ void __launch_bounds__(32 * DH_ZS)
 depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ samples, int D,
                    int Ho, int Wo, int f, float* __restrict__ vol, float* __restrict__ sm,
                    float* __restrict__ preds, float2* __restrict__ norm) {
-  extern __shared__ float dh_cols[];                 // [D][2][nc]
+  extern __shared__ float dh_rows[];                 // [D][nc]: y-blended low-res rows
   __shared__ float red[3][DH_ZS][DH4_PX];
-  __shared__ int tab_z0[DH_MAXBINS];
-  __shared__ float tab_l1[DH_MAXBINS], tab_s[DH_MAXBINS];
+  __shared__ float tab_l0[DH_MAXBINS], tab_l1[DH_MAXBINS], tab_s[DH_MAXBINS];
+  __shared__ int tab_k0[DH_MAXBINS + 2];             // first bin of low-res interval z
   const int OW = Wo * f, OH = Ho * f, OD = D * f;
-  const int tx = threadIdx.x, seg = threadIdx.y;
+  const int tx = threadIdx.x, seg = threadIdx.y, tid = seg * 32 + tx;
   const float sz = OD > 1 ? (float)(D - 1) / (OD - 1) : 0.f;
-  for (int k = seg * 32 + tx; k < OD; k += 32 * DH_ZS) {
-    const float fz = sz * k;
-    const int z0 = (int)fz;
-    tab_z0[k] = z0;
-    tab_l1[k] = fz - z0;
+  for (int z = tid; z <= D; z += 32 * DH_ZS) tab_k0[z] = OD;
+  __syncthreads();
+  for (int k = tid; k < OD; k += 32 * DH_ZS) {
+    const float fz = sz * k;       // ATen: area_pixel_compute_source_index, align_corners
+    const int z0 = min((int)fz, D - 1);
+    const float l1 = fz - z0;
+    tab_l1[k] = l1;
+    tab_l0[k] = 1.f - l1;
     tab_s[k] = samples ? __ldg(samples + k) : 0.f;
+    atomicMin(&tab_k0[z0], k);
   }
   const int Xb = blockIdx.x * DH4_PX;
   const int X0 = Xb + 4 * tx;                        // first of this thread's four pixels
@@ -240,10 +214,11 @@ depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ sam
   const long long oplane = (long long)OH * OW;
   const int nc = dh4_ncols(f);
   const int xb = (int)(sx * Xb);                      // first low-res column of the block
-  for (int i = seg * 32 + tx; i < D * 2 * nc; i += 32 * DH_ZS) {
-    const int z = i / (2 * nc), rc = i - z * 2 * nc;
-    const int r = rc >= nc ? 1 : 0, c = rc - r * nc;
-    dh_cols[i] = __ldg(cost + z * plane + (r ? y1 : y0) * Wo + min(xb + c, Wo - 1));
+  for (int i = tid; i < D * nc; i += 32 * DH_ZS) {
+    const int z = i / nc, c = i - z * nc;
+    const int xc = min(xb + c, Wo - 1);
+    dh_rows[i] = ly0 * __ldg(cost + z * plane + y0 * Wo + xc) +
+                 ly1 * __ldg(cost + z * plane + y1 * Wo + xc);
   }
   int c0[4], c1[4];
   float wx0[4], wx1[4];
@@ -259,17 +234,23 @@ depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ sam
     c1[j] = x1 - xb;
   }
   __syncthreads();
-  // same association as ATen upsample_trilinear3d: h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)
+  // an interval without bins (fp32 rounding can leave the last one empty) starts where the
+  // next one does
+  if (tid == 0)
+    for (int z = D - 1; z >= 0; --z) tab_k0[z] = min(tab_k0[z], tab_k0[z + 1]);
+  __syncthreads();
   auto col = [&](int z, int j) {
-    const float* pz = dh_cols + z * 2 * nc;
-    return ly0 * (wx0[j] * pz[c0[j]] + wx1[j] * pz[c1[j]]) +
-           ly1 * (wx0[j] * pz[nc + c0[j]] + wx1[j] * pz[nc + c1[j]]);
+    const float* pz = dh_rows + z * nc;
+    return wx0[j] * pz[c0[j]] + wx1[j] * pz[c1[j]];
   };
+  // this thread's share of the depth axis: low-res planes [zA, zB) for the maximum, the bins of
+  // the intervals [zA, zB) for the sums and the writes
+  const int zA = seg * D / DH_ZS, zB = (seg + 1) * D / DH_ZS;
   float m[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float mm = -INFINITY;
-    for (int z = seg * D / DH_ZS; z < (seg + 1) * D / DH_ZS; ++z) mm = fmaxf(mm, col(z, j));
+    for (int z = zA; z < zB; ++z) mm = fmaxf(mm, col(z, j));
     red[0][seg][4 * tx + j] = mm;
   }
   __syncthreads();
@@ -279,27 +260,26 @@ depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ sam
 #pragma unroll
     for (int i = 1; i < DH_ZS; ++i) m[j] = fmaxf(m[j], red[0][i][4 * tx + j]);
   }
-  const int k_lo = seg * OD / DH_ZS, k_hi = (seg + 1) * OD / DH_ZS;
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, esum[4] = {0.f, 0.f, 0.f, 0.f};
   float b0[4], b1[4];
-  int zc = -1;
-  for (int k = k_lo; k < k_hi; ++k) {
-    const int z0 = tab_z0[k];
-    const float lz1 = tab_l1[k], s = tab_s[k];
-    if (z0 != zc) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        b0[j] = (z0 == zc + 1 && zc >= 0) ? b1[j] : col(z0, j);
-        b1[j] = z0 < D - 1 ? col(z0 + 1, j) : b0[j];
-      }
-      zc = z0;
-    }
+  for (int j = 0; j < 4; ++j) b1[j] = col(zA, j);
+  for (int z = zA; z < zB; ++z) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float v = (1.f - lz1) * b0[j] + lz1 * b1[j];
-      const float e = __expf(v - m[j]);
-      ssum[j] += e;
-      esum[j] = fmaf(e, s, esum[j]);
+      b0[j] = b1[j];
+      b1[j] = z < D - 1 ? col(z + 1, j) : b0[j];
+    }
+    const int ke = tab_k0[z + 1];
+    for (int k = tab_k0[z]; k < ke; ++k) {
+      const float l0 = tab_l0[k], l1 = tab_l1[k], s = tab_s[k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = l0 * b0[j] + l1 * b1[j];
+        const float e = __expf(v - m[j]);
+        ssum[j] += e;
+        esum[j] = fmaf(e, s, esum[j]);
+      }
     }
   }
 #pragma unroll
@@ -333,27 +313,28 @@ depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ sam
     }
   }
   if (!sm && !vol) return;
-  zc = -1;
-  for (int k = k_lo; k < k_hi; ++k) {
-    const int z0 = tab_z0[k];
-    const float lz1 = tab_l1[k];
-    if (z0 != zc) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        b0[j] = (z0 == zc + 1 && zc >= 0) ? b1[j] : col(z0, j);
-        b1[j] = z0 < D - 1 ? col(z0 + 1, j) : b0[j];
-      }
-      zc = z0;
+  for (int j = 0; j < 4; ++j) b1[j] = col(zA, j);
+  for (int z = zA; z < zB; ++z) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      b0[j] = b1[j];
+      b1[j] = z < D - 1 ? col(z + 1, j) : b0[j];
     }
-    float v[4];
+    const int ke = tab_k0[z + 1];
+    for (int k = tab_k0[z]; k < ke; ++k) {
+      const float l0 = tab_l0[k], l1 = tab_l1[k];
+      float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = (1.f - lz1) * b0[j] + lz1 * b1[j];
-    if (vol)
-      __stcs(reinterpret_cast<float4*>(vol + k * oplane + opix), make_float4(v[0], v[1], v[2], v[3]));
-    if (sm)
-      __stcs(reinterpret_cast<float4*>(sm + k * oplane + opix),
-             make_float4(__expf(v[0] - m[0]) * inv[0], __expf(v[1] - m[1]) * inv[1],
-                         __expf(v[2] - m[2]) * inv[2], __expf(v[3] - m[3]) * inv[3]));
+      for (int j = 0; j < 4; ++j) v[j] = l0 * b0[j] + l1 * b1[j];
+      if (vol)
+        __stcs(reinterpret_cast<float4*>(vol + k * oplane + opix),
+               make_float4(v[0], v[1], v[2], v[3]));
+      if (sm)
+        __stcs(reinterpret_cast<float4*>(sm + k * oplane + opix),
+               make_float4(__expf(v[0] - m[0]) * inv[0], __expf(v[1] - m[1]) * inv[1],
+                           __expf(v[2] - m[2]) * inv[2], __expf(v[3] - m[3]) * inv[3]));
+    }
   }
 }
 

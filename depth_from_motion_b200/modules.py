@@ -319,9 +319,18 @@ class DfMBackbone(_CudaMirror):
         stereo = torch.empty((1, self.cv_channels, d, ho, wo), device=dev,
                              dtype=torch.float32)
         mono = torch.empty_like(stereo)
-        capi.check(L.dfm_backbone_forward(
-            self._handle, _ptr(cur), _ptr(prev), ctypes.byref(geom), _ptr(cost),
-            _ptr(stereo), _ptr(mono), _stream()), 'dfm_backbone_forward')
+        # stereo features that came out of our SPPUNetNeckTail carry a channels-last twin:
+        # the plane-sweep loader reads it directly, no NCHW -> NHWC transposes
+        cl_c = getattr(cur_stereo_feats, '_dfm_cl', None)
+        cl_p = getattr(prev_stereo_feats, '_dfm_cl', None)
+        if cl_c is not None and cl_p is not None and cl_c.shape == (h, w, c) == cl_p.shape:
+            capi.check(L.dfm_backbone_forward_cl(
+                self._handle, _ptr(cl_c), _ptr(cl_p), ctypes.byref(geom), _ptr(cost),
+                _ptr(stereo), _ptr(mono), _stream()), 'dfm_backbone_forward_cl')
+        else:
+            capi.check(L.dfm_backbone_forward(
+                self._handle, _ptr(cur), _ptr(prev), ctypes.byref(geom), _ptr(cost),
+                _ptr(stereo), _ptr(mono), _stream()), 'dfm_backbone_forward')
         # the handle keeps a channels-last copy of stereo_feat until the next forward;
         # FrustumToVoxel reads it instead of transposing `stereo` again
         self._generation = getattr(self, '_generation', 0) + 1
@@ -737,7 +746,9 @@ class HotPathPipeline:
 
     def __init__(self, backbone, depth_head, frustum):
         self.backbone, self.depth_head, self.frustum = backbone, depth_head, frustum
-        self._out = None
+        self._outs = None
+        self._slot = 0
+        self._inflight = []
 
     def prepare(self, feat_h, feat_w, sem_hw):
         bb, fr = self.backbone, self.frustum
@@ -750,14 +761,18 @@ class HotPathPipeline:
             L.dfm_frustum_set_param(fr._handle, k, p, m),
             f'dfm_frustum_set_param({k.decode()})'))
         nz, ny, nx = fr.coordinates_3d.shape[:3]
-        if self._out is None or self._out[0].shape[-3:] != (nz // 4, ny, nx) or \
-                self._out[1].shape[-2:] != (f * ho, f * wo):
-            self._out = (
-                torch.empty((1, fr.out_channels, nz // 4, ny, nx)).pin_memory(),
-                torch.empty((1, 1, f * ho, f * wo)).pin_memory())
+        if self._outs is None or self._outs[0][0].shape[-3:] != (nz // 4, ny, nx) or \
+                self._outs[0][1].shape[-2:] != (f * ho, f * wo):
+            # two pinned output sets: frame i's results are read while frame i+1 is in flight
+            self._outs = [(torch.empty((1, fr.out_channels, nz // 4, ny, nx)).pin_memory(),
+                           torch.empty((1, 1, f * ho, f * wo)).pin_memory()) for _ in range(2)]
             self._samples = self.depth_head.depth_samples.detach().to(
                 'cpu', torch.float32).contiguous()
         return L
+
+    @property
+    def _out(self):
+        return self._outs[0]
 
     def prefetch(self, h_cur, h_prev):
         """Start copying the NEXT pair (pinned host tensors) while the current one runs."""
@@ -765,11 +780,7 @@ class HotPathPipeline:
             self.backbone._handle, _ptr(h_cur), _ptr(h_prev)),
             'dfm_backbone_prefetch_host')
 
-    def __call__(self, h_cur, h_prev, h_sem, img_metas, h_cost=None):
-        """h_cur / h_prev [1,C,H,W], h_sem [1,32,H/4,W/4]: CPU float32 tensors (pinned for
-        full PCIe bandwidth).  Returns (voxel_features [1,32,Nz/4,Ny,Nx], depth_preds
-        [1,1,H,W]) as pinned CPU tensors owned by this object (overwritten by the next
-        call)."""
+    def _args(self, h_cur, h_prev, h_sem, img_metas):
         for t in (h_cur, h_prev):
             assert t.device.type == 'cpu' and t.dtype == torch.float32 and t.is_contiguous()
         _, _, h, w = h_cur.shape
@@ -779,12 +790,39 @@ class HotPathPipeline:
         P = (ctypes.c_double * 16)(*np.asarray(
             meta['cam2img'], np.float64).reshape(-1)[:16].tolist())
         pad = meta['pad_shape']
-        vox, preds = self._out
+        return L, geom, P, int(pad[0]), int(pad[1])
+
+    def __call__(self, h_cur, h_prev, h_sem, img_metas, h_cost=None):
+        """Synchronous call.  h_cur / h_prev [1,C,H,W], h_sem [1,32,H/4,W/4]: CPU float32
+        tensors (pinned for full PCIe bandwidth).  Returns (voxel_features [1,32,Nz/4,Ny,Nx],
+        depth_preds [1,1,H,W]) as pinned CPU tensors owned by this object (overwritten by a
+        later call)."""
+        L, geom, P, ph, pw = self._args(h_cur, h_prev, h_sem, img_metas)
+        self._inflight = []
+        vox, preds = self._outs[self._slot]
+        self._slot ^= 1
         capi.check(L.dfm_pipeline_forward_host(
             self.backbone._handle, self.frustum._handle, _ptr(h_cur), _ptr(h_prev),
-            _ptr(h_sem), ctypes.byref(geom), P, int(pad[0]), int(pad[1]),
-            _ptr(self._samples), _ptr(vox), _ptr(preds), _ptr(h_cost), _stream()),
-            'dfm_pipeline_forward_host')
+            _ptr(h_sem), ctypes.byref(geom), P, ph, pw, _ptr(self._samples), _ptr(vox),
+            _ptr(preds), _ptr(h_cost), _stream()), 'dfm_pipeline_forward_host')
+        return vox, preds
+
+    def submit(self, h_cur, h_prev, h_sem, img_metas):
+        """Asynchronous call: enqueue one frame and return at once (at most two in flight).
+        ``wait()`` returns the outputs of the oldest submitted frame; the device->host copy of
+        frame i overlaps the compute of frame i+1."""
+        L, geom, P, ph, pw = self._args(h_cur, h_prev, h_sem, img_metas)
+        vox, preds = self._outs[self._slot]
+        capi.check(L.dfm_pipeline_submit_host(
+            self.backbone._handle, self.frustum._handle, _ptr(h_cur), _ptr(h_prev),
+            _ptr(h_sem), ctypes.byref(geom), P, ph, pw, _ptr(self._samples), _ptr(vox),
+            _ptr(preds), _stream()), 'dfm_pipeline_submit_host')
+        self._slot ^= 1
+        self._inflight.append((vox, preds, h_cur, h_prev, h_sem))
+
+    def wait(self):
+        capi.check(capi.lib().dfm_pipeline_wait(self.backbone._handle), 'dfm_pipeline_wait')
+        vox, preds = self._inflight.pop(0)[:2]
         return vox, preds
 
 
@@ -836,6 +874,59 @@ class _HandleMirror(_CudaMirror):
 
     def init_weights(self):
         pass
+
+
+@NECKS.register_module()
+class SPPUNetNeckTail(_HandleMirror):
+    """The last two layers of the reference ``SPPUNetNeck`` (necks/spp_unet_neck.py:60-75
+    ``lastconv``, applied at :110) on CUDA: 3x3 conv + GroupNorm(32) + ReLU + 1x1 conv on the
+    full-resolution up-convolved feature.  ``state_dict`` keys are the reference's
+    (``lastconv.0.conv.weight``, ``lastconv.0.gn.*``, ``lastconv.1.weight``), so
+    ``load_state_dict(neck.state_dict(), strict=False)`` of a reference neck fills it.  The
+    returned ``[B, 32, H, W]`` tensor carries a channels-last twin that our ``DfMBackbone``
+    consumes directly.  Patch: ``neck.lastconv = SPPUNetNeckTail(...)`` (it is called with the
+    same single tensor argument as the ``nn.Sequential`` it replaces)."""
+    _destroy = 'dfm_stereo_tail_destroy'
+
+    def __init__(self, stereo_channels=(32, 32), in_channels=32,
+                 norm_cfg=dict(type='GN', num_groups=32, requires_grad=True), conv_impl='auto'):
+        super().__init__()
+        assert tuple(stereo_channels) == (32, 32) and in_channels == 32
+        assert norm_cfg.get('type') == 'GN' and norm_cfg.get('num_groups', 32) == 32
+        self.conv_impl = conv_impl
+        self.lastconv = nn.Sequential(_ConvGN2d(32, 32), nn.Conv2d(32, 32, 1, bias=False))
+        self._handle = None
+        self._key = None
+
+    def forward(self, x):
+        _check_cuda(x, 'x')
+        self._forward_only(x)
+        b, c, h, w = x.shape
+        assert c == 32
+        L = capi.lib()
+        key = (h, w, self.conv_impl)
+        if self._handle is None or key != self._key:
+            self.release()
+            hd = ctypes.c_void_p()
+            capi.check(L.dfm_stereo_tail_create(h, w, _IMPL[self.conv_impl], ctypes.byref(hd)),
+                       'dfm_stereo_tail_create')
+            self._handle, self._key = hd, key
+            self._sync = _ParamSync()
+        self._sync.sync(self, lambda k, p, m: capi.check(
+            L.dfm_stereo_tail_set_param(self._handle, k, p, m),
+            f'dfm_stereo_tail_set_param({k.decode()})'))
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        twins = []
+        for i in range(b):
+            cl = torch.empty((h, w, c), device=x.device)
+            capi.check(L.dfm_stereo_tail_forward(self._handle, _ptr(x[i]), _ptr(cl),
+                                                 _ptr(out[i]), _stream()),
+                       'dfm_stereo_tail_forward')
+            twins.append(cl)
+        if b == 1:
+            out._dfm_cl = twins[0]
+        return out
 
 
 @BACKBONES.register_module()
@@ -1047,6 +1138,51 @@ def multiview_lift(feats, img_meta, n_voxels, voxel_range, num_views,
         ctypes.c_void_p(xs.data_ptr()), ctypes.c_void_p(ys.data_ptr()),
         ctypes.c_void_p(zs.data_ptr()), _ptr(out), _stream()),
         'dfm_multiview_lift')
+    return out
+
+
+def voxel_sample(voxel_features, voxel_range, voxel_size, depth_samples, proj_mat,
+                 downsample_factor, img_scale_factor, img_crop_offset, img_flip,
+                 img_pad_shape, img_shape, aligned=True, padding_mode='zeros',
+                 align_corners=True):
+    """Same signature as the reference ``voxel_sample``
+    (fusion_layers/point_fusion.py:324-339): [1, C, Nx, Ny, Nz] CUDA voxel features ->
+    [1, C, D, H, W] frustum features (D = len(depth_samples[::downsample_factor]))."""
+    _check_cuda(voxel_features, 'voxel_features')
+    if padding_mode != 'zeros' or not align_corners:
+        raise NotImplementedError("voxel_sample: only padding_mode='zeros', "
+                                  'align_corners=True (the reference defaults)')
+    n, c, nx, ny, nz = voxel_features.shape
+    assert n == 1
+    h, w = img_pad_shape[:2]
+    ho, wo = round(h / downsample_factor), round(w / downsample_factor)
+    depths = torch.as_tensor(depth_samples, dtype=torch.float32).detach().cpu()[
+        ::downsample_factor].contiguous()
+    sf = np.atleast_1d(np.asarray(
+        img_scale_factor.detach().cpu() if isinstance(img_scale_factor, torch.Tensor)
+        else img_scale_factor, dtype=np.float32))
+    crop = np.atleast_1d(np.asarray(
+        img_crop_offset.detach().cpu() if isinstance(img_crop_offset, torch.Tensor)
+        else img_crop_offset, dtype=np.float32))
+    desc = capi.VoxelSampleDesc()
+    desc.channels, desc.nx, desc.ny, desc.nz = c, nx, ny, nz
+    desc.voxel_range[:] = [float(v) for v in voxel_range]
+    desc.voxel_size[:] = [float(v) for v in voxel_size]
+    desc.num_depths, desc.out_h, desc.out_w = depths.numel(), ho, wo
+    desc.downsample_factor = int(downsample_factor)
+    desc.scale_x, desc.scale_y = float(sf[0]), float(sf[-1] if sf.size > 1 else sf[0])
+    desc.crop_x, desc.crop_y = float(crop[0]), float(crop[-1] if crop.size > 1 else crop[0])
+    desc.flip, desc.img_w = int(bool(img_flip)), int(img_shape[1])
+    desc.aligned = int(bool(aligned))
+    pm = np.asarray(proj_mat.detach().cpu() if isinstance(proj_mat, torch.Tensor) else proj_mat,
+                    dtype=np.float64)
+    pad = np.eye(4)
+    pad[:pm.shape[0], :pm.shape[1]] = pm
+    P = (ctypes.c_double * 16)(*pad.reshape(-1).tolist())
+    out = torch.empty((1, c, depths.numel(), ho, wo), device=voxel_features.device)
+    capi.check(capi.lib().dfm_voxel_sample(
+        ctypes.byref(desc), _ptr(voxel_features.contiguous()),
+        ctypes.c_void_p(depths.data_ptr()), P, _ptr(out), _stream()), 'dfm_voxel_sample')
     return out
 
 

@@ -98,6 +98,11 @@ long long dfm_backbone_workspace_bytes(const dfm_backbone_t* bb);
 int dfm_backbone_forward(dfm_backbone_t* bb, const float* d_cur, const float* d_prev,
                          const dfm_geometry_t* geom, float* d_cost, float* d_stereo,
                          float* d_mono, void* stream);
+/* Same call for stereo features that are already channels-last [H][W][C] (what
+ * dfm_stereo_tail_forward emits): skips the two NCHW -> NHWC transposes. */
+int dfm_backbone_forward_cl(dfm_backbone_t* bb, const float* d_cur_cl, const float* d_prev_cl,
+                            const dfm_geometry_t* geom, float* d_cost, float* d_stereo,
+                            float* d_mono, void* stream);
 /* Same call with HOST buffers: copies the two feature maps host->device, runs the
  * path, copies the outputs selected by out_flags (DFM_OUT_*) device->host, and
  * synchronises.  Buffers should be page-locked for full PCIe bandwidth. */
@@ -330,6 +335,58 @@ int dfm_anchor_head_missing_params(const dfm_anchor_head_t* h);
  * [dir_channels][ny][nx]. */
 int dfm_anchor_head_forward(dfm_anchor_head_t* h, const float* d_x, float* d_cls, float* d_bbox,
                             float* d_dir, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * voxel_sample (mmdet3d/models/fusion_layers/point_fusion.py:324-410): frustum-from-voxel
+ * resampling for an optional depth head of MultiViewDfM (detectors/multiview_dfm.py:220-256;
+ * no shipped config enables it).  d_voxel [C][Nx][Ny][Nz] -> d_out [C][num_depths][out_h][out_w],
+ * out_h/out_w = round(img_pad_shape / downsample_factor); h_depths: host [num_depths] =
+ * depth_samples[::downsample_factor]; h_proj: 16 doubles, the (lidar/cam)2img matrix.
+ * grid_sample semantics: zeros padding, align_corners=True, trilinear (aligned) or nearest.
+ * ---------------------------------------------------------------------------------- */
+typedef struct dfm_voxel_sample_desc {
+  int channels, nx, ny, nz;
+  float voxel_range[6];
+  float voxel_size[3];
+  int num_depths, out_h, out_w, downsample_factor;
+  float scale_x, scale_y;  /* img_scale_factor */
+  float crop_x, crop_y;    /* img_crop_offset  */
+  int flip, img_w;         /* img_flip, img_shape[1] */
+  int aligned;             /* 1: trilinear, 0: nearest */
+} dfm_voxel_sample_desc_t;
+int dfm_voxel_sample(const dfm_voxel_sample_desc_t* desc, const float* d_voxel,
+                     const float* h_depths, const double* h_proj, float* d_out, void* stream);
+
+/* Asynchronous form of the same call: submit enqueues the host->device copies, the path and
+ * the device->host copies of the outputs (those on a side stream, so they overlap the NEXT
+ * frame's compute) and returns at once; dfm_pipeline_wait blocks until the outputs of the
+ * oldest submitted frame are in host memory and reports asynchronous failures.  At most two
+ * frames may be in flight; host input buffers must stay unchanged until the wait for their
+ * frame returns, output buffers must not be read before it. */
+int dfm_pipeline_submit_host(dfm_backbone_t* bb, dfm_frustum_t* fr, const float* h_cur,
+                             const float* h_prev, const float* h_sem,
+                             const dfm_geometry_t* geom, const double* cam2img, int pad_h,
+                             int pad_w, const float* h_depth_samples, float* h_voxel,
+                             float* h_depth_preds, void* stream);
+int dfm_pipeline_wait(dfm_backbone_t* bb);
+
+/* ------------------------------------------------------------------------------------
+ * The tail of SPPUNetNeck (mmdet3d/models/necks/spp_unet_neck.py:60-75 `lastconv`, applied at
+ * :110): Conv2d 3x3 (32->32) + GroupNorm(32) + ReLU + Conv2d 1x1
+ * (32->32, no bias) producing the full-resolution stereo feature that build_dfm_cost samples.
+ * d_x [32][H][W] (the up-convolved feature, NCHW) -> d_out_cl [H][W][32] channels-last (feed it
+ * to dfm_backbone_forward_cl) and / or d_out_nchw [32][H][W] (the reference's return value).
+ * Keys: "lastconv.0.conv.weight" (32,32,3,3), "lastconv.0.gn.weight", "lastconv.0.gn.bias",
+ * "lastconv.1.weight" (32,32,1,1).
+ * ---------------------------------------------------------------------------------- */
+typedef struct dfm_stereo_tail dfm_stereo_tail_t;
+int dfm_stereo_tail_create(int H, int W, int conv_impl, dfm_stereo_tail_t** out);
+int dfm_stereo_tail_destroy(dfm_stereo_tail_t* t);
+int dfm_stereo_tail_set_param(dfm_stereo_tail_t* t, const char* name, const float* h_data,
+                              long long numel);
+int dfm_stereo_tail_missing_params(const dfm_stereo_tail_t* t);
+int dfm_stereo_tail_forward(dfm_stereo_tail_t* t, const float* d_x, float* d_out_cl,
+                            float* d_out_nchw, void* stream);
 
 /* Re-entrancy: handles may live on different devices and be driven from different host
  * threads only if each thread owns its device; per-device scratch (K-slice partial sums,

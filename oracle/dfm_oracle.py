@@ -29,6 +29,8 @@ follows (paths relative to the reference checkout, commit e2321189):
     f1  FrustumToVoxel.forward
                             mmdet3d/models/necks/feature_transformation.py:68-187
                             mmdet3d/models/detectors/dfm.py:174-211 (voxel grid)
+    f2  SPPUNetNeck.lastconv (section 8(f) row 2)
+                            mmdet3d/models/necks/spp_unet_neck.py:60-75, :110
     f3  BEVHourglass.forward + LIGAAnchor3DHead.forward_single (section 8(f) row 3)
                             mmdet3d/models/backbones/bev_hourglass.py:11-137
                             mmdet3d/models/dense_heads/liga_anchor3d_head.py:37-128
@@ -613,6 +615,17 @@ def dfm_bev_stage(p_bev, p_head, volume_feat, num_convs=2):
 def bf16_round(x):
     """Round-to-nearest-even to bf16 precision, kept in fp32 (precision study only)."""
     return x.to(torch.bfloat16).to(torch.float32)
+
+
+# ----------------------------------------------------------------------------
+# f2  SPPUNetNeck tail (SURVEY.md section 8(f) row 2): the last two layers that produce the
+# full-resolution 32-channel stereo feature build_dfm_cost consumes
+# ----------------------------------------------------------------------------
+def spp_unet_lastconv(p, x):
+    """SPPUNetNeck.lastconv (necks/spp_unet_neck.py:60-75, applied at :110):
+    ConvModule(3x3, GN(32), ReLU) then Conv2d(1x1, bias=False)."""
+    y = F.relu(_gn2d(F.conv2d(x, p['lastconv.0.conv.weight'], None, 1, 1), p, 'lastconv.0.gn'))
+    return F.conv2d(y, p['lastconv.1.weight'])
 
 
 def tf32_round(x):

@@ -268,6 +268,7 @@ def load_reference():
         sys.modules['mmdet3d.models.utils'].hourglass = cm.hourglass
         sys.modules['mmdet3d.models.utils'].convbn_3d = cm.convbn_3d
         sys.modules['mmdet3d.models.utils'].convbn = cm.convbn
+        sys.modules['mmdet3d.models.utils'].upconv_module = cm.upconv_module
 
         bb = _exec('mmdet3d.models.backbones.dfm_backbone',
                    'mmdet3d/models/backbones/dfm_backbone.py')
@@ -282,6 +283,8 @@ def load_reference():
                    'mmdet3d/models/necks/feature_transformation.py')
         bh = _exec('mmdet3d.models.backbones.bev_hourglass',
                    'mmdet3d/models/backbones/bev_hourglass.py')
+        sp = _exec('mmdet3d.models.necks.spp_unet_neck',
+                   'mmdet3d/models/necks/spp_unet_neck.py')
 
         ns = types.SimpleNamespace(
             points_cam2img=su.points_cam2img,
@@ -296,6 +299,7 @@ def load_reference():
             DfMNeck=dn.DfMNeck,
             FrustumToVoxel=ft.FrustumToVoxel,
             BEVHourglass=bh.BEVHourglass,
+            SPPUNetNeck=sp.SPPUNetNeck,
             LIGAAnchor3DHead=_liga_head_class(),
             ConvModule=_ConvModule,
         )

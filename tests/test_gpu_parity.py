@@ -757,6 +757,19 @@ def test_pipeline_forward_host_matches_module_path():
     pipe.prefetch(hc, hp)
     vox2, pred2 = pipe(hc, hp, hs, metas)
     assert rel_err(vox2, vox_ref) < 1e-5 and rel_err(pred2, pred_ref) < 1e-5
+    # asynchronous form: two frames in flight (cur/prev swapped for the second), results collected
+    # in order; the first equals the synchronous result, the second differs from it
+    vox_ref1 = vox.clone()
+    pipe.submit(hc, hp, hs, metas)
+    pipe.submit(hp, hc, hs, metas)
+    with pytest.raises(RuntimeError):          # at most two frames in flight
+        pipe.submit(hc, hp, hs, metas)
+    a_vox, a_pred = pipe.wait()
+    a_vox, a_pred = a_vox.clone(), a_pred.clone()
+    b_vox, _ = pipe.wait()
+    assert rel_err(a_vox, vox_ref1) < 1e-5 and rel_err(a_pred, pred_ref) < 1e-5
+    assert rel_err(b_vox, vox_ref1) > 1e-3
+    vox, pred = pipe(hc, hp, hs, metas)
     # all-oracle pipeline
     with torch.no_grad():
         rc, rs, _ = O.dfm_backbone_forward(params, cur, prev, metas, cfg)
@@ -926,3 +939,94 @@ def test_box_regression_parity_end_to_end():
         e = rel_err(got, ref)
         print('end to end', key, e, 'worst element / tol', assert_close(got, ref, key))
         assert e < TOL, (key, e)
+
+
+@pytest.mark.parametrize('flip,aligned', [(False, True), (True, True), (False, False)])
+def test_voxel_sample_vs_oracle(flip, aligned):
+    """the CUDA voxel_sample against the oracle (which equals the verbatim
+    reference function, tests/test_oracle_golden.py)."""
+    rng = np.random.RandomState(13)
+    nx, ny, nz, c = 40, 32, 16, 6
+    # smooth features so trilinear taps are not noise-amplifying; nearest mode uses the same
+    vox = torch.cat([syn.smooth_field(rng, c, ny, nz, cell=4) for _ in range(nx)], 0)
+    vox = vox.permute(1, 0, 2, 3)[None].contiguous()          # [1, C, Nx, Ny, Nz]
+    vrange, vsize = [0.0, -8.0, -2.0, 20.0, 8.0, 2.0], [0.5, 0.5, 0.25]
+    depths = torch.linspace(2.0, 18.0, 16)
+    k = torch.tensor([[40., 0, 32, 0], [0, 40., 16, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+    l2c = torch.tensor([[0., -1, 0, 0], [0, 0, -1, 0.3], [1, 0, 0, 0.1], [0, 0, 0, 1]])
+    proj = k @ l2c
+    args = (vrange, vsize, depths, proj, 4, torch.tensor([1.02, 0.98]),
+            torch.tensor([1.0, 2.0]), flip, (32, 64), (30, 62))
+    ref = O.voxel_sample(vox, *args, aligned=aligned)
+    got = modules.voxel_sample(vox.cuda(), *args, aligned=aligned)
+    assert got.shape == ref.shape == (1, c, 4, 8, 16)
+    assert float(ref.abs().sum()) > 0
+    if aligned:
+        e = rel_err(got, ref)
+        print('voxel_sample', flip, e)
+        assert e < 1e-4
+    else:
+        # nearest: identical taps except where fp32 rounding of the coordinate sits on a tie
+        bad = float(((got.cpu() - ref).abs().amax(1) > 1e-6).float().mean())
+        print('voxel_sample nearest mismatching', bad)
+        assert bad <= 0.02
+
+
+@pytest.mark.parametrize('tpi', ['2', '5'])
+@pytest.mark.parametrize('name', ['neck_dfm_mt', 'neck_imvoxel_mt'])
+def test_neck_multitile_items_share_a_weight_image(name, tpi):
+    """conv_tc_neck.cuh keeps the accumulators of several tiles in TMEM so that one weight image
+    serves all of them (tiles-per-item, chosen from the grid size: 1 on these small fixtures).
+    Forced here to 2 and 5 (capped per layer by 512 / (Zo * 32) columns) on the 3 x 3-tile
+    reference fixtures: same result as one tile per item."""
+    gold = np.load(os.path.join(GOLDEN, name + '.npz'))
+    rng, x = make_neck_mt_case(name)
+    mod = (modules.DfMNeck(64, 256, num_frames=2) if name == 'neck_dfm_mt'
+           else modules.OutdoorImVoxelNeck(64, 256))
+    mod.load_state_dict(syn.make_neck_params(rng, mod.state_dict()), strict=True)
+    mod = mod.cuda().eval()
+    os.environ['DFM_NECK_TPI'] = tpi
+    try:
+        y = mod(x.cuda())[0]
+        capi.sync_check()
+    finally:
+        os.environ.pop('DFM_NECK_TPI', None)
+    e = rel_err(y, torch.from_numpy(gold['y']))
+    print(name, 'tiles per item', tpi, e)
+    assert e < TOL
+
+
+@pytest.mark.parametrize('impl', ['simt', 'auto'])
+def test_spp_unet_tail_vs_oracle_and_channels_last_backbone(impl):
+    """SPPUNetNeck.lastconv on CUDA against the oracle (equal to
+    the verbatim reference module, tests/test_oracle_golden.py), and DfMBackbone fed by its
+    channels-last twin against DfMBackbone fed by the NCHW tensor."""
+    h, w, d = 64, 128, 8
+    rng = np.random.RandomState(77)
+    p = {'lastconv.0.conv.weight': torch.from_numpy(syn._kaiming(rng, (32, 32, 3, 3), 32 * 9)),
+         'lastconv.0.gn.weight': torch.from_numpy((0.5 + rng.random_sample(32)).astype(np.float32)),
+         'lastconv.0.gn.bias': torch.from_numpy((0.2 * rng.standard_normal(32)).astype(np.float32)),
+         'lastconv.1.weight': torch.from_numpy(syn._kaiming(rng, (32, 32, 1, 1), 32))}
+    tail = modules.SPPUNetNeckTail(conv_impl=impl)
+    tail.load_state_dict(p, strict=True)
+    tail = tail.cuda().eval()
+    xc = syn.smooth_field(rng, 32, h, w)
+    xp = syn.smooth_field(rng, 32, h, w)
+    with torch.no_grad():
+        rc, rp = O.spp_unet_lastconv(p, xc), O.spp_unet_lastconv(p, xp)
+    cur, prev = tail(xc.cuda()), tail(xp.cuda())
+    capi.sync_check()
+    for got, ref in ((cur, rc), (prev, rp)):
+        e = rel_err(got, ref)
+        print('spp-unet tail', impl, e)
+        assert e < (2e-5 if impl == 'simt' else 1e-4)
+        assert torch.equal(got._dfm_cl.permute(2, 0, 1)[None], got)
+    _, _, metas, params = syn.make_kitti_pair(78, h, w, d)
+    cfg = syn.depth_cfg_for(d)
+    bb = _backbone(params, cfg, 'auto')
+    with torch.no_grad():
+        a = bb(cur, prev, copy.deepcopy(metas))                  # channels-last twins
+        b = bb(cur.clone(), prev.clone(), copy.deepcopy(metas))  # NCHW tensors (twin dropped)
+    capi.sync_check()
+    for x, y in zip(a, b):
+        assert rel_err(x, y) < 1e-5

@@ -228,3 +228,24 @@ def test_bev_stage_oracle_equals_reference_source():
         got = O.dfm_bev_stage(c['bev'], c['head'], c['volume'])
     for a, b in zip(got, ref):
         assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/mmdet3d'), reason='reference tree not mounted')
+def test_spp_unet_lastconv_equals_reference_module():
+    """the oracle restatement of SPPUNetNeck.lastconv against the
+    reference class executed in place (spp_unet_neck.py:60-75, :110)."""
+    from oracle.ref_loader import load_reference
+    ns = load_reference()
+    gn = dict(type='GN', num_groups=32, requires_grad=True)
+    m = ns.SPPUNetNeck(in_channels=[3, 64, 128, 128, 128], start_level=2, sem_channels=[128, 32],
+                       stereo_channels=[32, 32], with_upconv=True, cat_img_feature=True,
+                       norm_cfg=gn).eval()
+    p = {k: v for k, v in m.state_dict().items() if k.startswith('lastconv')}
+    assert sorted(p) == ['lastconv.0.conv.weight', 'lastconv.0.gn.bias', 'lastconv.0.gn.weight',
+                         'lastconv.1.weight']
+    x = torch.randn(1, 32, 24, 40, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        assert torch.equal(m.lastconv(x), O.spp_unet_lastconv(p, x))
+    # the mirror takes the same keys
+    from depth_from_motion_b200 import modules
+    modules.SPPUNetNeckTail().load_state_dict(p, strict=True)
