@@ -48,7 +48,7 @@ IO_BYTES_PER_FRAME = 2 * 32 * H * W * 4 + 5.25e6 + 33 * V * 4
 KITTI_WORKLOAD = 'dfm_r34_1x8_kitti-3d-3class D=112 384x1248 batch=1'
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the
 # committed `ncu --set full` capture (profiles/): kitti: conv_tc 32->32 full resolution
-NCU_TRAFFIC = {'kitti': (973.3e6, 'profiles/r01_ncu_conv_tc.csv')}
+NCU_TRAFFIC = {'kitti': (974.2e6, 'profiles/r02_ncu_conv_tc.csv (587.1 MB read + 387.0 MB written)')}
 WAYMO = {
     'waymo_mv': dict(T=1, agg='mean', neck='OutdoorImVoxelNeck', flops=3.212e12,
                      name='multiview-dfm_r101_dcn_2x16_waymoD5 (5 views, 832x1248 input) '
@@ -441,12 +441,13 @@ def run_kitti(args):
     hbm_rows = {}
     alg = {'depth_head': 2 * (4 * D) * H * W * 4 + V * 4,
            'cout1_logits': V * 32 * 4 + V * 4,
-           'gate': 3 * V * 4}
+           'gate': 3 * V * 4,
+           'presplit': 3 * V * 32 * 4}     # two fp32 terms read, one pre-split tensor written
     for key, nbytes in alg.items():
         rows = [v for k, v in prof.items() if k == key or k.startswith(key)]
         if rows:
             ms = sum(v['ms'] for v in rows) / args.steps
-            if key == 'cout1_logits':   # stereo (D planes) + shortened mono tower (40 planes)
+            if key in ('cout1_logits', 'presplit'):   # stereo (D planes) + shortened mono (40)
                 nbytes = nbytes * (1 + 40.0 / D)
             hbm_rows[key] = dict(ms=round(ms, 4), algorithmic_gb=round(nbytes / 1e9, 3),
                                  gbs=round(nbytes / ms / 1e6, 1),

@@ -9,7 +9,7 @@ SRC = os.path.join(HERE, 'csrc', 'dfm_b200.cu')
 OUT = os.path.join(HERE, 'libdfm_b200.so')
 DEPS = [os.path.join(HERE, 'csrc', f) for f in
         ('dfm_b200.cu', 'common.cuh', 'simt_kernels.cuh', 'conv_tc.cuh', 'conv_tc_neck.cuh',
-         'neck_api.inc', 'frustum_api.inc', 'frustum_kernels.cuh', 'pipeline_api.inc', 'bev_api.inc', 'tail_kernels.cuh', 'voxel_sample_api.inc', 'stereo_tail_api.inc')] + [os.path.join(HERE, '..', 'include', 'dfm_b200.h')]
+         'neck_api.inc', 'frustum_api.inc', 'frustum_kernels.cuh', 'pipeline_api.inc', 'bev_api.inc', 'tail_kernels.cuh', 'voxel_sample_api.inc', 'stereo_tail_api.inc', 'logits_tc.cuh')] + [os.path.join(HERE, '..', 'include', 'dfm_b200.h')]
 
 
 def nvcc_path():

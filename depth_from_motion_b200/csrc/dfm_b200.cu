@@ -18,6 +18,7 @@
 #include "simt_kernels.cuh"
 #include "frustum_kernels.cuh"
 #include "tail_kernels.cuh"
+#include "logits_tc.cuh"
 
 namespace {
 
@@ -478,6 +479,7 @@ struct Tower {
   ConvW dres0, dres1, c1, c2, c3, c4, c5, c6, p0;
   DevBuf p1w;  // [27][32]
   std::vector<float> p1w_host;  // same, host copy: kernel-parameter weights of logits_conv_kernel
+  dfm::LogitsTcWeights p1q;     // same as a 32 x 32 (27 taps) bf16 hi/lo image: logits_tc_kernel
   ConvW p1tc;  // the 32->1 logit conv zero-padded to 32 output channels for the tensor cores
   // z-invariance of the cur-frame half: dres0 split into its cur- and
   // prev-channel halves (stereo); the cur contribution is computed on 5 replicated planes
@@ -570,6 +572,7 @@ void tower_release(Tower& t) {
     c->simt.release();
     c->tc.release();
   }
+  t.p1q.release();
 }
 
 std::vector<std::string> tower_param_names(bool mono) {
@@ -660,6 +663,7 @@ int tower_set_param(Tower& t, bool mono, int cin0, int cv, const std::string& na
       for (int k = 0; k < 27; ++k) padded[(size_t)c * 27 + k] = h[(size_t)c * 27 + k];
     DFM_TRY(set_conv(t.p1tc, padded.data(), (long long)padded.size(), cv, cv, 0, dfm::TC_S1));
     t.p1w_host = p;
+    if (cv == 32 && !t.p1q.build(p.data())) return fail(DFM_ERR_CUDA, "logits weight upload failed");
     return upload(t.p1w, p.data(), p.size());
   }
   *handled = false;
@@ -806,9 +810,21 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
   // dot products staged in shared memory (tail_kernels.cuh).  DFM_LOGITS_TC=1 keeps the
   // round-1 tensor-core variant (N = 96 MMA, 1/32 useful columns) for A/B runs; the fp32
   // SIMT bring-up path keeps its own independent kernel.
-  static const bool logits_tc = getenv("DFM_LOGITS_TC") != nullptr;
+  // Default: logits_tc_kernel (logits_tc.cuh) -- the 27 per-tap dot products of every input
+  // position as one small tcgen05 GEMM, the stencil as a shared-memory gather.  DFM_LOGITS=simt
+  // selects the CUDA-core variant (tail_kernels.cuh), DFM_LOGITS=mma the round-1 N = 96 MMA.
+  static const char* logits_env = getenv("DFM_LOGITS");
+  static const bool logits_tc = getenv("DFM_LOGITS_TC") != nullptr ||
+                                (logits_env && std::string(logits_env) == "mma");
+  static const bool logits_simt = logits_env && std::string(logits_env) == "simt";
   const dfm::Src lsrc = src1(term(t.p0b, &t.gp0, 1));
-  if (impl != DFM_CONV_SIMT && !logits_tc && cv == 32 && t.p1w_host.size() == 27u * 32u) {
+  if (impl != DFM_CONV_SIMT && !logits_tc && !logits_simt && cv == 32 && t.p1q.ready()) {
+    ProfScope ps(conv_class("cout1_logits_tc", g, "src"), 2.0 * V * cv * 27, st);
+    if (!dfm::logits_tc_launch(lsrc, t.p1q, t.logit.p, D, Ho, Wo, st))
+      return fail(DFM_ERR_CUDA, "logits_tc_kernel launch failed");
+    g_launches.fetch_add(1);
+    g_tc_launches.fetch_add(1);
+  } else if (impl != DFM_CONV_SIMT && !logits_tc && cv == 32 && t.p1w_host.size() == 27u * 32u) {
     ProfScope ps(conv_class("cout1_logits", g, "src"), 2.0 * V * cv * 27, st);
     if (!dfm::logits_conv_launch(lsrc, t.p1w_host.data(), t.logit.p, D, Ho, Wo, st))
       return fail(DFM_ERR_CUDA, "logits_conv_kernel launch failed");
