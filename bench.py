@@ -361,13 +361,13 @@ def run_kitti(args):
         _, _, metas, hc, hp = pairs[i % 2]
         if use_prefetch[0]:
             nxt = pairs[(i + 1) % 2]
-            pipe.prefetch(nxt[3], nxt[4])
+            pipe.prefetch(nxt[3], nxt[4], h_sem)
         pipe.submit(hc, hp, h_sem, metas)
 
     # self-check: the asynchronous, prefetched path must reproduce the plain synchronous call
     ref_vox = e2e_sync_step(0)[0].clone()
     try:
-        pipe.prefetch(pairs[0][3], pairs[0][4])
+        pipe.prefetch(pairs[0][3], pairs[0][4], h_sem)
         use_prefetch[0] = True
         e2e_submit(0)
         if not torch.allclose(pipe.wait()[0], ref_vox, rtol=1e-5, atol=1e-6):

@@ -35,6 +35,7 @@ SYMBOLS = (
     'dfm_neck_forward', 'dfm_frustum_create', 'dfm_frustum_destroy',
     'dfm_frustum_set_param', 'dfm_frustum_missing_params', 'dfm_frustum_forward',
     'dfm_pipeline_forward_host', 'dfm_pipeline_submit_host', 'dfm_pipeline_wait',
+    'dfm_pipeline_prefetch_host',
     'dfm_bev_hourglass_create', 'dfm_bev_hourglass_destroy', 'dfm_bev_hourglass_set_param',
     'dfm_bev_hourglass_missing_params', 'dfm_bev_hourglass_forward',
     'dfm_anchor_head_create', 'dfm_anchor_head_destroy', 'dfm_anchor_head_set_param',
@@ -147,6 +148,7 @@ def lib():
     L.dfm_backbone_forward_host.argtypes = [vp, vp, vp, POINTER(Geometry),
                                             c_int, vp, vp, vp, vp]
     L.dfm_backbone_prefetch_host.argtypes = [vp, vp, vp]
+    L.dfm_pipeline_prefetch_host.argtypes = [vp, vp, vp, vp, ctypes.c_longlong]
     L.dfm_backbone_cost_device.argtypes = [vp]
     L.dfm_backbone_cost_device.restype = vp
     L.dfm_backbone_stereo_feat_device.argtypes = [vp]

@@ -499,9 +499,10 @@ struct dfm_backbone {
   // NCHW staging of the host-buffer entry point, double-buffered so that the next pair can be
   // copied in (dfm_backbone_prefetch_host) while the current one is being processed
   struct HostStage {
-    DevBuf cur, prev;
+    DevBuf cur, prev, sem;
     const float* h_cur = nullptr;
     const float* h_prev = nullptr;
+    const float* h_sem = nullptr;  // staged with the pair by dfm_pipeline_prefetch_host
     bool pending = false;      // holds a prefetched pair that no forward has consumed yet
     cudaEvent_t ready = nullptr;
     cudaEvent_t consumed = nullptr;  // recorded after the last kernel that reads this slot
@@ -511,6 +512,7 @@ struct dfm_backbone {
   unsigned long long stage_tick = 0;
   // grow-only device scratch of the host-buffer entry points (no cudaMalloc per call)
   DevBuf out_st, out_mo, pipe_sem, pipe_vox, pipe_preds, pipe_samples;
+  std::vector<float> pipe_samples_host;  // what pipe_samples holds (re-uploaded on change only)
   bool depths_set = false;
   std::set<std::string> missing;
   std::map<std::string, std::pair<const DevBuf*, int>> dbg;  // name -> (buffer, channels)
@@ -1253,12 +1255,9 @@ int stage_host_pair(dfm_backbone_t* bb, const float* h_cur, const float* h_prev,
   *d_prev_out = d_prev;
   return DFM_OK;
 }
-}  // namespace
 
-extern "C" {
-
-int dfm_backbone_prefetch_host(dfm_backbone_t* bb, const float* h_cur, const float* h_prev) {
-  if (!bb || !h_cur || !h_prev) return fail(DFM_ERR_INVALID, "null argument");
+int prefetch_impl(dfm_backbone_t* bb, const float* h_cur, const float* h_prev, const float* h_sem,
+                  size_t nsem) {
   HostCopyCtx* cx = nullptr;
   DFM_TRY(host_copy_ctx(&cx));
   const size_t nfeat = (size_t)bb->d.in_channels * bb->d.feat_h * bb->d.feat_w;
@@ -1267,17 +1266,29 @@ int dfm_backbone_prefetch_host(dfm_backbone_t* bb, const float* h_cur, const flo
              : (bb->stage[0].tick <= bb->stage[1].tick ? 0 : 1);
   dfm_backbone::HostStage& hs = bb->stage[slot];
   DFM_TRY(stage_alloc(hs, nfeat));
+  if (h_sem && nsem) DFM_TRY(hs.sem.alloc(nsem));
   // the synchronous entry points return after the device is done with this slot; the
   // asynchronous pipeline records `consumed` after the last kernel that reads it
   CU_TRY(cudaStreamWaitEvent(cx->stream, hs.consumed, 0));
   CU_TRY(cudaMemcpyAsync(hs.cur.p, h_cur, nfeat * 4, cudaMemcpyHostToDevice, cx->stream));
   CU_TRY(cudaMemcpyAsync(hs.prev.p, h_prev, nfeat * 4, cudaMemcpyHostToDevice, cx->stream));
+  if (h_sem && nsem)
+    CU_TRY(cudaMemcpyAsync(hs.sem.p, h_sem, nsem * 4, cudaMemcpyHostToDevice, cx->stream));
   CU_TRY(cudaEventRecord(hs.ready, cx->stream));
   hs.h_cur = h_cur;
   hs.h_prev = h_prev;
+  hs.h_sem = (h_sem && nsem) ? h_sem : nullptr;
   hs.pending = true;
   hs.tick = ++bb->stage_tick;
   return DFM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dfm_backbone_prefetch_host(dfm_backbone_t* bb, const float* h_cur, const float* h_prev) {
+  if (!bb || !h_cur || !h_prev) return fail(DFM_ERR_INVALID, "null argument");
+  return prefetch_impl(bb, h_cur, h_prev, nullptr, 0);
 }
 
 int dfm_backbone_forward_host(dfm_backbone_t* bb, const float* h_cur, const float* h_prev,

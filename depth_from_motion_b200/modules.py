@@ -774,11 +774,15 @@ class HotPathPipeline:
     def _out(self):
         return self._outs[0]
 
-    def prefetch(self, h_cur, h_prev):
-        """Start copying the NEXT pair (pinned host tensors) while the current one runs."""
-        capi.check(capi.lib().dfm_backbone_prefetch_host(
-            self.backbone._handle, _ptr(h_cur), _ptr(h_prev)),
-            'dfm_backbone_prefetch_host')
+    def prefetch(self, h_cur, h_prev, h_sem=None):
+        """Start copying the NEXT frame's inputs (pinned host tensors) while the current one
+        runs.  Pass ``h_sem`` too: a host->device copy issued at submit time queues on the copy
+        engine behind this bulk copy and stalls the compute stream."""
+        if self.backbone._handle is None:
+            self.backbone._prepare(h_cur.shape[-2], h_cur.shape[-1])
+        capi.check(capi.lib().dfm_pipeline_prefetch_host(
+            self.backbone._handle, _ptr(h_cur), _ptr(h_prev), _ptr(h_sem),
+            0 if h_sem is None else h_sem.numel()), 'dfm_pipeline_prefetch_host')
 
     def _args(self, h_cur, h_prev, h_sem, img_metas):
         for t in (h_cur, h_prev):

@@ -369,6 +369,13 @@ int dfm_pipeline_submit_host(dfm_backbone_t* bb, dfm_frustum_t* fr, const float*
                              int pad_w, const float* h_depth_samples, float* h_voxel,
                              float* h_depth_preds, void* stream);
 int dfm_pipeline_wait(dfm_backbone_t* bb);
+/* dfm_backbone_prefetch_host for the pipeline: also stages the NEXT frame's sem features
+ * (`sem_numel` floats, may be NULL / 0) together with its pair on the side stream.  A small
+ * host->device copy issued at submit time would queue on the copy engine behind this bulk
+ * copy and stall the compute stream (measured: ~1 ms per frame), so everything a frame reads
+ * from the host should be handed over here, one frame ahead. */
+int dfm_pipeline_prefetch_host(dfm_backbone_t* bb, const float* h_cur, const float* h_prev,
+                               const float* h_sem, long long sem_numel);
 
 /* ------------------------------------------------------------------------------------
  * The tail of SPPUNetNeck (mmdet3d/models/necks/spp_unet_neck.py:60-75 `lastconv`, applied at

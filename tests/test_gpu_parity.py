@@ -757,9 +757,21 @@ def test_pipeline_forward_host_matches_module_path():
     pipe.prefetch(hc, hp)
     vox2, pred2 = pipe(hc, hp, hs, metas)
     assert rel_err(vox2, vox_ref) < 1e-5 and rel_err(pred2, pred_ref) < 1e-5
+    # sem features staged with the pair; a different sem tensor at call time is a miss for the
+    # staged copy (the call's tensor wins)
+    pipe.prefetch(hc, hp, hs)
+    vox2, pred2 = pipe(hc, hp, hs, metas)
+    assert rel_err(vox2, vox_ref) < 1e-5 and rel_err(pred2, pred_ref) < 1e-5
+    hs_other = (hs * 0.5).contiguous().pin_memory()
+    pipe.prefetch(hc, hp, hs_other)
+    vox2, _ = pipe(hc, hp, hs, metas)
+    assert rel_err(vox2, vox_ref) < 1e-5
+    pipe.prefetch(hc, hp, hs_other)
+    vox3, _ = pipe(hc, hp, hs_other, metas)
+    assert rel_err(vox3, vox_ref) > 1e-3
     # asynchronous form: two frames in flight (cur/prev swapped for the second), results collected
     # in order; the first equals the synchronous result, the second differs from it
-    vox_ref1 = vox.clone()
+    vox_ref1 = pipe(hc, hp, hs, metas)[0].clone()   # (pinned outputs are overwritten by later calls)
     pipe.submit(hc, hp, hs, metas)
     pipe.submit(hp, hc, hs, metas)
     with pytest.raises(RuntimeError):          # at most two frames in flight
