@@ -581,7 +581,7 @@ def run_waymo(args):
                 peak_source=pk['src'] + ' bf16 dense (sustained)',
                 ms_per_step=round(neck_ms, 3), share_of_step=round(neck_ms * args.steps / ms_total, 4),
                 note='algorithmic fp32 conv FLOPs of the neck (SURVEY.md 8d) / summed conv time')
-    roof_lift = dict(bound='hbm', kernel='lift (NCHW->NHWC staging + lift_voxel_kernel)',
+    roof_lift = dict(bound='hbm', kernel='lift (NCHW->NHWC staging of the 2-D features + lift_cl_kernel, channels-last volume out)',
                      achieved=round((in_bytes + out_bytes) / (lift_ms * 1e-3) / 1e9, 1) if lift_ms else None,
                      peak=pk['hbm'], unit='GB/s',
                      frac=round((in_bytes + out_bytes) / (lift_ms * 1e-3) / 1e9 / pk['hbm'], 4) if lift_ms else None,

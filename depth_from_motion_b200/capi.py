@@ -30,9 +30,9 @@ SYMBOLS = (
     'dfm_backbone_cost_device',
     'dfm_backbone_stereo_feat_device',
     'dfm_backbone_debug_tensor', 'dfm_op_build_cost_volume', 'dfm_op_conv3d',
-    'dfm_depth_head_forward', 'dfm_multiview_lift', 'dfm_neck_create',
+    'dfm_depth_head_forward', 'dfm_multiview_lift', 'dfm_multiview_lift_cl', 'dfm_neck_create',
     'dfm_neck_destroy', 'dfm_neck_set_param', 'dfm_neck_missing_params',
-    'dfm_neck_forward', 'dfm_frustum_create', 'dfm_frustum_destroy',
+    'dfm_neck_forward', 'dfm_neck_forward_cl', 'dfm_frustum_create', 'dfm_frustum_destroy',
     'dfm_frustum_set_param', 'dfm_frustum_missing_params', 'dfm_frustum_forward',
     'dfm_pipeline_forward_host', 'dfm_pipeline_submit_host', 'dfm_pipeline_wait',
     'dfm_pipeline_prefetch_host',
@@ -164,11 +164,14 @@ def lib():
                                          vp, vp, vp, vp]
     L.dfm_multiview_lift.argtypes = [POINTER(LiftDesc), vp, vp, vp, vp, vp, vp,
                                      vp, vp]
+    L.dfm_multiview_lift_cl.argtypes = [POINTER(LiftDesc), vp, vp, vp, vp, vp, vp,
+                                     vp, vp]
     L.dfm_neck_create.argtypes = [POINTER(NeckDesc), POINTER(vp)]
     L.dfm_neck_destroy.argtypes = [vp]
     L.dfm_neck_set_param.argtypes = [vp, c_char_p, vp, c_longlong]
     L.dfm_neck_missing_params.argtypes = [vp]
     L.dfm_neck_forward.argtypes = [vp, vp, vp, vp]
+    L.dfm_neck_forward_cl.argtypes = [vp, vp, vp, vp]
     L.dfm_frustum_create.argtypes = [POINTER(FrustumDesc), vp, vp, vp,
                                      POINTER(vp)]
     L.dfm_frustum_destroy.argtypes = [vp]

@@ -385,10 +385,24 @@ int run_conv_warp(const dfm::WarpLoader& ld, const ConvW& w, float* out, const d
       }, "warp", w, out, g, impl, gn, st);
 }
 
-int to_nhwc(const float* in, float* out, int C, long long HW, cudaStream_t st) {
-  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32), block(32, 8);
-  dfm::nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(in, out, C, HW);
-  LAUNCH_CHECK();
+// `batch` images of [C][HW], contiguous on both sides
+int to_nhwc(const float* in, float* out, int C, long long HW, cudaStream_t st, int batch = 1) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+  if ((C == 32 || C == 64) && HW % 4 == 0 && aligned && batch <= 65535) {
+    dim3 grid((unsigned)((HW + 127) / 128), batch);
+    if (C == 32)
+      dfm::nchw_to_nhwc_v4_kernel<32><<<grid, 256, 0, st>>>(in, out, HW, C * HW, C * HW);
+    else
+      dfm::nchw_to_nhwc_v4_kernel<64><<<grid, 256, 0, st>>>(in, out, HW, C * HW, C * HW);
+    LAUNCH_CHECK();
+    return DFM_OK;
+  }
+  for (int b = 0; b < batch; ++b) {
+    dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32), block(32, 8);
+    dfm::nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(in + (size_t)b * C * HW,
+                                                      out + (size_t)b * C * HW, C, HW);
+    LAUNCH_CHECK();
+  }
   return DFM_OK;
 }
 int to_ncdhw(const float* in, float* out, int C, long long V, cudaStream_t st) {

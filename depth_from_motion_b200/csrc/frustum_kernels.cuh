@@ -63,9 +63,9 @@ __device__ __forceinline__ void fr_axis(float g, int size, int stride, bool on, 
 }
 
 // One warp per 32 consecutive voxels.  Phase A, lane = voxel: projection, validity, the depth
-// distribution (8 scattered taps per voxel).  Phase B, lane = channel: the warp walks its 32
-// voxels, broadcasting each one's sample position, and moves 128-byte channel rows (8 stereo
-// taps + 4 semantic taps in, 2 rows out).  (The first version recomputed the projection in all
+// distribution (8 scattered taps per voxel).  Phase B, 8 lanes x float4 per voxel: the warp walks
+// its 32 voxels four at a time, broadcasting each one's sample position inside its lane group,
+// and moves 128-byte channel rows (8 stereo taps + 4 semantic taps in, 2 rows out).  (The first version recomputed the projection in all
 // 32 lanes of a per-voxel warp and was instruction-issue bound at 515 instructions/voxel.)
 // stereo: channels-last [D][Ho][Wo][32]; sem: channels-last [Hs][Ws][32]; softmax: materialised
 // [fD][fH][fW] volume or nullptr, in which case (cost, norm) rebuild the taps; out:
@@ -139,48 +139,62 @@ frustum_gather_kernel(FrustumParams p, const float* __restrict__ xs, const float
   }
   const int my_flags = (valid ? 1 : 0) | (sem_on ? 2 : 0);
 
-  // ---- phase B: lane = channel ------------------------------------------------------------
+  // ---- phase B: 8 lanes x float4 per voxel, four voxels per step ---------------------------
+  // (one voxel per step with lane = channel was latency-bound: 21 shuffles + 12 loads in a
+  // dependent chain per voxel; four independent chains per step hide it)
   const int cout = p.cat_img ? 64 : 32;
-  const float* sl = stereo + lane;
-  const float* ml = sem + lane;
-  for (int j = 0; j < nlive; ++j) {
+  const int grp = lane >> 3, gl = lane & 7;
+  const float4* sl = reinterpret_cast<const float4*>(stereo) + gl;
+  const float4* ml = reinterpret_cast<const float4*>(sem) + gl;
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = jj * 4 + grp;
+    if (jj * 4 >= nlive) break;  // warp-uniform
     const int flags = __shfl_sync(FULL, my_flags, j);
-    float* o = out + (v0 + j) * cout;
-    float sv = 0.f;
-    if (flags & 1) {
-      int jo[6];
-      float jw[6];
+    int jo[6];
+    float jw[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        jo[i] = __shfl_sync(FULL, so[i], j);
-        jw[i] = __shfl_sync(FULL, sw[i], j);
-      }
+    for (int i = 0; i < 6; ++i) {
+      jo[i] = __shfl_sync(FULL, so[i], j);
+      jw[i] = __shfl_sync(FULL, sw[i], j);
+    }
+    float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (flags & 1) {
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const int dx = t & 1, dy = (t >> 1) & 1, dz = t >> 2;
         const float wgt = jw[dz] * jw[2 + dy] * jw[4 + dx];
-        sv = fmaf(wgt, __ldg(sl + (jo[dz] + jo[2 + dy] + jo[4 + dx])), sv);
+        const float4 f = __ldg(sl + ((jo[dz] + jo[2 + dy] + jo[4 + dx]) >> 2));
+        sv.x = fmaf(wgt, f.x, sv.x);
+        sv.y = fmaf(wgt, f.y, sv.y);
+        sv.z = fmaf(wgt, f.z, sv.z);
+        sv.w = fmaf(wgt, f.w, sv.w);
       }
     }
-    o[lane] = sv;
+    float* o = out + (v0 + j) * cout + 4 * gl;
+    if (j < nlive) *reinterpret_cast<float4*>(o) = sv;
     if (!p.cat_img) continue;
     // semantic feature (bilinear; the reference samples a depth-1 volume at z = 0)
-    float mv = 0.f;
-    if (flags & 2) {
-      int jo[4];
-      float jw[4];
+    int ko[4];
+    float kw[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        jo[i] = __shfl_sync(FULL, mo[i], j);
-        jw[i] = __shfl_sync(FULL, mw[i], j);
-      }
+    for (int i = 0; i < 4; ++i) {
+      ko[i] = __shfl_sync(FULL, mo[i], j);
+      kw[i] = __shfl_sync(FULL, mw[i], j);
+    }
+    float4 mv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (flags & 2) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int dx = t & 1, dy = t >> 1;
-        mv = fmaf(jw[dy] * jw[2 + dx], __ldg(ml + (jo[dy] + jo[2 + dx])), mv);
+        const float wgt = kw[dy] * kw[2 + dx];
+        const float4 f = __ldg(ml + ((ko[dy] + ko[2 + dx]) >> 2));
+        mv.x = fmaf(wgt, f.x, mv.x);
+        mv.y = fmaf(wgt, f.y, mv.y);
+        mv.z = fmaf(wgt, f.z, mv.z);
+        mv.w = fmaf(wgt, f.w, mv.w);
       }
     }
-    o[32 + lane] = mv;
+    if (j < nlive) *reinterpret_cast<float4*>(o + 32) = mv;
   }
 }
 

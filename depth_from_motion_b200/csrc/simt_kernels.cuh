@@ -32,6 +32,43 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
   }
 }
 
+// Vectorised variant for C = 32 / 64 and HW % 4 == 0: 16-byte global accesses on both sides
+// (512-byte runs along the pixels in, whole channel rows out), a [C][128 + 1] tile whose odd
+// pitch keeps both the (4 rows x 8 float4) store pattern and the (4 pixels x 8 channel
+// quads) gather pattern free of bank conflicts.  blockIdx.y walks a batch of images.
+template <int C>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_v4_kernel(const float* __restrict__ in, float* __restrict__ out, long long HW,
+                       long long in_bstride, long long out_bstride) {
+  constexpr int TP = 128, P = TP + 1;
+  __shared__ float tile[C * P];
+  const float* src = in + (long long)blockIdx.y * in_bstride;
+  float* dst = out + (long long)blockIdx.y * out_bstride;
+  const long long p0 = (long long)blockIdx.x * TP;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = tid; i < C * (TP / 4); i += 256) {
+    const int q8 = i & 7, r = (i >> 3) & 3, blk = i >> 5;
+    const int colgrp = blk % (TP / 32), rowgrp = blk / (TP / 32);
+    const int c = rowgrp * 4 + r, px = (colgrp * 8 + q8) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p0 + px < HW) v = __ldcs(reinterpret_cast<const float4*>(src + (long long)c * HW + p0 + px));
+    float* t = tile + c * P + px;
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = tid; i < TP * (C / 4); i += 256) {
+    const int cq8 = i & 7, px4 = (i >> 3) & 3, blk = i >> 5;
+    const int cgrp = blk % (C / 32), pgrp = blk / (C / 32);
+    const int c = (cgrp * 8 + cq8) * 4, px = pgrp * 4 + px4;
+    if (p0 + px < HW) {
+      const float* t = tile + c * P + px;
+      *reinterpret_cast<float4*>(dst + (p0 + px) * C + c) = make_float4(t[0], t[P], t[2 * P], t[3 * P]);
+    }
+  }
+}
+
 // channels-last [V][C] -> NCDHW [C][V]
 __global__ void cl_to_ncdhw_kernel(const float* __restrict__ in, float* __restrict__ out,
                                    int C, long long V) {
@@ -782,6 +819,79 @@ lift_voxel_kernel(LiftParams p, const float* __restrict__ feats, const float* __
     const float den = (float)max(tot_n, 1);  // tot is all zero when tot_n == 0
 #pragma unroll
     for (int c = 0; c < C; ++c) out[(long long)c * nvox + ovox] = __fdiv_rn(tot[c], den);
+  }
+}
+
+
+// Channels-last variant, one warp per 32 consecutive voxels.  Phase A (lane = voxel) runs the
+// reference's projection / validity / nearest-pixel arithmetic exactly as lift_voxel_kernel does;
+// phase B (lane = channel pair) gathers the 256-byte feature rows of the valid (voxel, view)
+// pairs with one coalesced warp load each and writes every voxel's channels as one contiguous
+// 256-byte row of out [nvox][Ctot] -- the layout the neck's conv loaders read, so neither the
+// strided channel-plane stores of the NCDHW kernel nor the neck's transpose pass exist on this
+// path.  Per-frame sums run over the views in the reference's order (bit-identical results).
+// Requires C == 64 and (concat or T == 1).
+__global__ void __launch_bounds__(256)
+lift_cl_kernel(LiftParams p, const float* __restrict__ feats, const float* __restrict__ xs,
+               const float* __restrict__ ys, const float* __restrict__ zs,
+               float* __restrict__ out) {
+  constexpr int C = 64;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const long long nvox = (long long)p.nx * p.ny * p.nz;
+  const long long v0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (v0 >= nvox) return;
+  const bool live = v0 + lane < nvox;
+  const long long ovox = min(v0 + lane, nvox - 1);
+  const int iz = (int)(ovox % p.nz), iy = (int)((ovox / p.nz) % p.ny),
+            ix = (int)(ovox / ((long long)p.nz * p.ny));
+  const float px = __ldg(xs + ix), py = __ldg(ys + iy), pz = __ldg(zs + iz);
+  const long long HW = (long long)p.Hf * p.Wf;
+  const int ctot = p.concat ? p.T * C : C;
+  const float2* f2 = reinterpret_cast<const float2*>(feats) + lane;
+  for (int f = 0; f < p.T; ++f) {
+    float2 acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = make_float2(0.f, 0.f);
+    int nvalid = 0;
+    for (int v = 0; v < p.Nv; ++v) {
+      const int s = f * p.Nv + v;
+      float cx, cy, d;
+      lift_project(p.proj[s], px, py, pz, p.scale_x, p.scale_y, p.crop_x, p.crop_y, cx, cy, d);
+      if (p.flip) cx = __fsub_rn((float)p.img_w[s], cx);
+      const bool valid = cx < (float)p.in_w && cx > 0.f && cy < (float)p.in_h && cy > 0.f &&
+                         d > 0.f;
+      int off = -1;  // float2 index of the sampled feature row (S * HW * 32 < 2^31, host-checked)
+      if (valid && live) {
+        ++nvalid;
+        const int sx = nearest_index(cx, p.Wf, (float)p.in_w);
+        const int sy = nearest_index(cy, p.Hf, (float)p.in_h);
+        if (sx >= 0 && sx < p.Wf && sy >= 0 && sy < p.Hf)
+          off = (s * (int)HW + sy * p.Wf + sx) * (C / 2);
+      }
+      if (__ballot_sync(FULL, off >= 0) == 0u) continue;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int o = __shfl_sync(FULL, off, j);
+        if (o >= 0) {
+          const float2 t = __ldg(f2 + o);
+          acc[j].x += t.x;
+          acc[j].y += t.y;
+        }
+      }
+    }
+    const float den = (float)max(nvalid, 1);  // acc is all zero when nvalid == 0
+    float2* o2 = reinterpret_cast<float2*>(out + v0 * ctot + (long long)f * C) + lane;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float dj = __shfl_sync(FULL, den, j);
+      if (v0 + j < nvox) {
+        // x / 1 == x: most voxels are seen by one camera (warp-uniform branch)
+        const float2 r = dj == 1.f ? acc[j]
+                                   : make_float2(__fdiv_rn(acc[j].x, dj), __fdiv_rn(acc[j].y, dj));
+        __stcs(o2 + (long long)j * (ctot / 2), r);
+      }
+    }
   }
 }
 

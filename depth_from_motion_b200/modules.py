@@ -499,9 +499,14 @@ class _NeckBase(_CudaMirror):
         outs = []
         for i in range(n):
             bev = torch.empty((self._cout, ny, nx), device=x.device)
-            capi.check(L.dfm_neck_forward(self._handle, _ptr(x[i].contiguous()),
-                                          _ptr(bev), _stream()),
-                       'dfm_neck_forward')
+            xi = x[i]
+            if xi.permute(1, 2, 3, 0).is_contiguous():   # channels-last (multiview_lift's output)
+                capi.check(L.dfm_neck_forward_cl(self._handle, _ptr(xi), _ptr(bev), _stream()),
+                           'dfm_neck_forward_cl')
+            else:
+                capi.check(L.dfm_neck_forward(self._handle, _ptr(xi.contiguous()),
+                                              _ptr(bev), _stream()),
+                           'dfm_neck_forward')
             outs.append(bev)
         return [torch.stack(outs)]
 
@@ -1103,10 +1108,14 @@ def _require_identity_3d_aug(img_meta):
 
 
 def multiview_lift(feats, img_meta, n_voxels, voxel_range, num_views,
-                   num_frames, temporal_aggregate='mean'):
+                   num_frames, temporal_aggregate='mean', out=None, channels_last=True):
     """The lifting loop of MultiViewDfM.feature_transformation
     (multiview_dfm.py:139-209, valid_sample=True) for one sample.
-    feats: [T*Nv, C, Hf, Wf] CUDA -> [C(*T), Nx, Ny, Nz]."""
+    feats: [T*Nv, C, Hf, Wf] CUDA -> [C(*T), Nx, Ny, Nz].  The returned tensor has the
+    reference's shape but channels-last strides (memory [Nx, Ny, Nz, C]): that is what the
+    necks' conv loaders read, so neither the lifting kernel's stores nor the neck pay for a
+    layout change.  ``out``: optional contiguous [Nx, Ny, Nz, C(*T)] CUDA buffer to fill.
+    ``channels_last=False`` runs the reference-layout kernel (contiguous [C, Nx, Ny, Nz])."""
     _check_cuda(feats, 'feats')
     s, c, hf, wf = feats.shape
     assert s == num_views * num_frames
@@ -1133,16 +1142,30 @@ def multiview_lift(feats, img_meta, n_voxels, voxel_range, num_views,
         [int(img_meta['img_shape'][i][1]) for i in range(s)], dtype=np.int32)
     xs, ys, zs = aligned_voxel_centers(n_voxels, voxel_range)
     cout = c * num_frames if desc.concat else c
-    out = torch.empty((cout, n_voxels[0], n_voxels[1], n_voxels[2]),
-                      device=feats.device, dtype=torch.float32)
-    capi.check(capi.lib().dfm_multiview_lift(
+    if not channels_last:
+        assert out is None
+        vol = torch.empty((cout, n_voxels[0], n_voxels[1], n_voxels[2]),
+                          device=feats.device, dtype=torch.float32)
+        capi.check(capi.lib().dfm_multiview_lift(
+            ctypes.byref(desc), _ptr(feats.contiguous()),
+            proj.ctypes.data_as(ctypes.c_void_p),
+            img_w.ctypes.data_as(ctypes.c_void_p),
+            ctypes.c_void_p(xs.data_ptr()), ctypes.c_void_p(ys.data_ptr()),
+            ctypes.c_void_p(zs.data_ptr()), _ptr(vol), _stream()),
+            'dfm_multiview_lift')
+        return vol
+    shape_cl = (n_voxels[0], n_voxels[1], n_voxels[2], cout)
+    if out is None:
+        out = torch.empty(shape_cl, device=feats.device, dtype=torch.float32)
+    assert tuple(out.shape) == shape_cl and out.is_contiguous() and out.is_cuda
+    capi.check(capi.lib().dfm_multiview_lift_cl(
         ctypes.byref(desc), _ptr(feats.contiguous()),
         proj.ctypes.data_as(ctypes.c_void_p),
         img_w.ctypes.data_as(ctypes.c_void_p),
         ctypes.c_void_p(xs.data_ptr()), ctypes.c_void_p(ys.data_ptr()),
         ctypes.c_void_p(zs.data_ptr()), _ptr(out), _stream()),
-        'dfm_multiview_lift')
-    return out
+        'dfm_multiview_lift_cl')
+    return out.permute(3, 0, 1, 2)
 
 
 def voxel_sample(voxel_features, voxel_range, voxel_size, depth_samples, proj_mat,
@@ -1212,15 +1235,18 @@ class MultiViewDfMFeatureTransformation:
                 '(depth_head=None, backbone_3d=None); voxel_sample is not on that path')
         if not getattr(self, 'valid_sample', True):
             raise NotImplementedError('valid_sample=False is not implemented')
-        volumes = []
-        for feature, img_meta in zip(batch_feats, img_metas):       # :128
+        nvx = list(self.n_voxels)
+        cout = batch_feats[0].shape[1] * (num_frames if self.temporal_aggregate == 'concat' else 1)
+        # one channels-last buffer for the batch; the reference-shaped view is returned
+        buf = torch.empty((len(batch_feats), nvx[0], nvx[1], nvx[2], cout),
+                          device=batch_feats[0].device, dtype=torch.float32)
+        for b, (feature, img_meta) in enumerate(zip(batch_feats, img_metas)):   # :128
             meta = dict(img_meta)
             if 'scale_factor' not in meta:                           # :129-138
                 meta['scale_factor'] = 1.0
-            volumes.append(multiview_lift(
-                feature, meta, list(self.n_voxels), list(self.voxel_range), num_views,
-                num_frames, self.temporal_aggregate))
-        volume_feat = torch.stack(volumes)                           # (B, C, Nx, Ny, Nz), :209
+            multiview_lift(feature, meta, nvx, list(self.voxel_range), num_views,
+                           num_frames, self.temporal_aggregate, out=buf[b])
+        volume_feat = buf.permute(0, 4, 1, 2, 3)                     # (B, C, Nx, Ny, Nz), :209
         if getattr(self, 'with_neck_3d', self.neck_3d is not None):
             volume_feat = self.neck_3d(volume_feat)[0]               # :263
         return (volume_feat, )                                       # :265-268

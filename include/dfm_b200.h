@@ -195,6 +195,15 @@ int dfm_multiview_lift(const dfm_lift_desc_t* desc, const float* d_feats,
                        const float* h_xs /* [Nx] */, const float* h_ys /* [Ny] */,
                        const float* h_zs /* [Nz] voxel-centre coordinates */,
                        float* d_volume, void* stream);
+/* Same lifting, channels-last output [Nx][Ny][Nz][C*(concat?T:1)] -- the layout the necks' conv
+ * loaders read (dfm_neck_forward_cl): the voxel's channels are one contiguous row, written by one
+ * coalesced warp store, and the neck's NCDHW -> channels-last pass disappears.  Bit-identical
+ * values.  (C == 64 and (concat or T == 1) run the fused kernel; other configurations run the
+ * reference-layout kernel plus one transpose.) */
+int dfm_multiview_lift_cl(const dfm_lift_desc_t* desc, const float* d_feats,
+                          const double* h_lidar2img, const int* h_img_w, const float* h_xs,
+                          const float* h_ys, const float* h_zs, float* d_volume_cl,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------
  * DfMNeck / OutdoorImVoxelNeck, eval mode (mmdet3d/models/necks/dfm_neck.py:10-122,
@@ -218,6 +227,8 @@ int dfm_neck_set_param(dfm_neck_t* neck, const char* name, const float* h_data,
 int dfm_neck_missing_params(const dfm_neck_t* neck);
 /* d_x [1, Cin_total, Nx, Ny, Nz] -> d_bev [1, out_channels, Ny, Nx]. */
 int dfm_neck_forward(dfm_neck_t* neck, const float* d_x, float* d_bev, void* stream);
+/* d_x_cl: channels-last [Nx][Ny][Nz][C*T] (dfm_multiview_lift_cl's output) */
+int dfm_neck_forward_cl(dfm_neck_t* neck, const float* d_x_cl, float* d_bev, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * FrustumToVoxel (mmdet3d/models/necks/feature_transformation.py:12-173), the stage that

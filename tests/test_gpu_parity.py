@@ -548,6 +548,13 @@ def test_multiview_lift_full_size_exact(t, agg):
                            pts.new_tensor(meta['img_crop_offset']), False,
                            meta['input_shape'], meta['img_shape'], agg)
     assert got.shape == ref.shape == (64 * (t if agg == 'concat' else 1), 220, 300, 12)
+    # channels-last memory (what the necks read); the reference-layout entry point gives the
+    # same bits
+    assert got.permute(1, 2, 3, 0).is_contiguous()
+    got_ncdhw = modules.multiview_lift(feats.cuda(), meta, n_voxels, vrange, nv, t, agg,
+                                       channels_last=False)
+    assert got_ncdhw.is_contiguous() and torch.equal(got_ncdhw, got)
+    del got_ncdhw
     bad = _lift_mismatches(got.cpu(), ref, pts, meta, t * nv)
     nonzero = float((ref.abs().amax(0) > 0).float().mean())
     print(f'lift T={t} {agg}: {bad} mismatching voxels of {pts.shape[0]}, '
