@@ -837,42 +837,47 @@ lift_cl_kernel(LiftParams p, const float* __restrict__ feats, const float* __res
                float* __restrict__ out) {
   constexpr int C = 64;
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
+  __shared__ int s_off[8][16][32];  // [warp][view][voxel]: float2 index of the sampled row, or -1
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long nvox = (long long)p.nx * p.ny * p.nz;
-  const long long v0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  const long long v0 = ((long long)blockIdx.x * (blockDim.x >> 5) + wib) * 32;
   if (v0 >= nvox) return;
   const bool live = v0 + lane < nvox;
   const long long ovox = min(v0 + lane, nvox - 1);
   const int iz = (int)(ovox % p.nz), iy = (int)((ovox / p.nz) % p.ny),
             ix = (int)(ovox / ((long long)p.nz * p.ny));
   const float px = __ldg(xs + ix), py = __ldg(ys + iy), pz = __ldg(zs + iz);
-  const long long HW = (long long)p.Hf * p.Wf;
+  const int HW = p.Hf * p.Wf;
   const int ctot = p.concat ? p.T * C : C;
+  const int S = p.T * p.Nv;
+  // ---- phase A (lane = voxel): all views, independent chains --------------------------------
+  unsigned vmask = 0;  // views in which this voxel is valid (counts towards the mean)
+#pragma unroll 5
+  for (int s = 0; s < S; ++s) {
+    float cx, cy, d;
+    lift_project(p.proj[s], px, py, pz, p.scale_x, p.scale_y, p.crop_x, p.crop_y, cx, cy, d);
+    if (p.flip) cx = __fsub_rn((float)p.img_w[s], cx);
+    const bool valid = live && cx < (float)p.in_w && cx > 0.f && cy < (float)p.in_h &&
+                       cy > 0.f && d > 0.f;
+    const int sx = nearest_index(cx, p.Wf, (float)p.in_w);
+    const int sy = nearest_index(cy, p.Hf, (float)p.in_h);
+    const bool inside = valid && sx >= 0 && sx < p.Wf && sy >= 0 && sy < p.Hf;
+    s_off[wib][s][lane] = inside ? (s * HW + sy * p.Wf + sx) * (C / 2) : -1;
+    vmask |= valid ? 1u << s : 0u;
+  }
+  __syncwarp();
+  // ---- phase B (lane = channel pair) ----------------------------------------------------------
   const float2* f2 = reinterpret_cast<const float2*>(feats) + lane;
   for (int f = 0; f < p.T; ++f) {
     float2 acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = make_float2(0.f, 0.f);
-    int nvalid = 0;
     for (int v = 0; v < p.Nv; ++v) {
       const int s = f * p.Nv + v;
-      float cx, cy, d;
-      lift_project(p.proj[s], px, py, pz, p.scale_x, p.scale_y, p.crop_x, p.crop_y, cx, cy, d);
-      if (p.flip) cx = __fsub_rn((float)p.img_w[s], cx);
-      const bool valid = cx < (float)p.in_w && cx > 0.f && cy < (float)p.in_h && cy > 0.f &&
-                         d > 0.f;
-      int off = -1;  // float2 index of the sampled feature row (S * HW * 32 < 2^31, host-checked)
-      if (valid && live) {
-        ++nvalid;
-        const int sx = nearest_index(cx, p.Wf, (float)p.in_w);
-        const int sy = nearest_index(cy, p.Hf, (float)p.in_h);
-        if (sx >= 0 && sx < p.Wf && sy >= 0 && sy < p.Hf)
-          off = (s * (int)HW + sy * p.Wf + sx) * (C / 2);
-      }
-      if (__ballot_sync(FULL, off >= 0) == 0u) continue;
+      if (__ballot_sync(FULL, s_off[wib][s][lane] >= 0) == 0u) continue;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int o = __shfl_sync(FULL, off, j);
+        const int o = s_off[wib][s][j];  // broadcast read
         if (o >= 0) {
           const float2 t = __ldg(f2 + o);
           acc[j].x += t.x;
@@ -880,6 +885,7 @@ lift_cl_kernel(LiftParams p, const float* __restrict__ feats, const float* __res
         }
       }
     }
+    const int nvalid = __popc((vmask >> (f * p.Nv)) & ((1u << p.Nv) - 1u));
     const float den = (float)max(nvalid, 1);  // acc is all zero when nvalid == 0
     float2* o2 = reinterpret_cast<float2*>(out + v0 * ctot + (long long)f * C) + lane;
 #pragma unroll

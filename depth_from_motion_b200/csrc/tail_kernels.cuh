@@ -174,6 +174,11 @@ inline bool logits_conv_launch(const Src& s, const float* h_w /*[27][32] host*/,
 // the carried pair (b0, b1) and an inner loop over the bins of the interval, all per-bin
 // constants come from shared-memory tables.  ~38 instructions per 4-pixel bin and pass.
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 constexpr int DH4_PX = 128;   // output pixels along x per block
 __host__ __device__ inline int dh4_ncols(int f) { return DH4_PX / f + 3; }
 inline size_t dh4_smem_bytes(int D, int f) { return (size_t)D * dh4_ncols(f) * sizeof(float); }
@@ -262,21 +267,28 @@ depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ sam
   }
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, esum[4] = {0.f, 0.f, 0.f, 0.f};
   float b0[4], b1[4];
+  // sum pass in the exp2 domain with the maximum folded into the interval ends:
+  // l0 + l1 == 1, so l0 * (b0 - m) + l1 * (b1 - m) == v - m and a bin costs mul, fma, ex2,
+  // add, fma per pixel
+  constexpr float LOG2E = 1.4426950408889634f;
+  float ml2[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) b1[j] = col(zA, j);
+  for (int j = 0; j < 4; ++j) {
+    ml2[j] = m[j] * LOG2E;
+    b1[j] = fmaf(col(zA, j), LOG2E, -ml2[j]);
+  }
   for (int z = zA; z < zB; ++z) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       b0[j] = b1[j];
-      b1[j] = z < D - 1 ? col(z + 1, j) : b0[j];
+      b1[j] = z < D - 1 ? fmaf(col(z + 1, j), LOG2E, -ml2[j]) : b0[j];
     }
     const int ke = tab_k0[z + 1];
     for (int k = tab_k0[z]; k < ke; ++k) {
       const float l0 = tab_l0[k], l1 = tab_l1[k], s = tab_s[k];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float v = l0 * b0[j] + l1 * b1[j];
-        const float e = __expf(v - m[j]);
+        const float e = ex2_approx(fmaf(l1, b1[j], l0 * b0[j]));
         ssum[j] += e;
         esum[j] = fmaf(e, s, esum[j]);
       }
@@ -332,8 +344,10 @@ depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ sam
                make_float4(v[0], v[1], v[2], v[3]));
       if (sm)
         __stcs(reinterpret_cast<float4*>(sm + k * oplane + opix),
-               make_float4(__expf(v[0] - m[0]) * inv[0], __expf(v[1] - m[1]) * inv[1],
-                           __expf(v[2] - m[2]) * inv[2], __expf(v[3] - m[3]) * inv[3]));
+               make_float4(ex2_approx(fmaf(v[0], LOG2E, -ml2[0])) * inv[0],
+                           ex2_approx(fmaf(v[1], LOG2E, -ml2[1])) * inv[1],
+                           ex2_approx(fmaf(v[2], LOG2E, -ml2[2])) * inv[2],
+                           ex2_approx(fmaf(v[3], LOG2E, -ml2[3])) * inv[3]));
     }
   }
 }
