@@ -538,10 +538,10 @@ namespace {
 int launch_materialize(const dfm::Src& src, int C, long long V, long long HW, dfm::ZExpand ze,
                        float* out_cl, float* out_ncdhw, const char* tag, cudaStream_t st) {
   ProfScope ps(tag, 0.0, st);
-  if (C == 32 && V % 4 == 0 && V < (1LL << 31)) {
-    const int ntiles = (int)((V + 31) / 32);
-    dfm::materialize32_kernel<<<std::min(ntiles, 148 * 16), 256, 0, st>>>(src, (int)V, (int)HW, ze,
-                                                                         out_cl, out_ncdhw);
+  if (C == 32 && V < (1LL << 31)) {
+    const int ntiles = (int)((V + dfm::MAT_TV - 1) / dfm::MAT_TV);
+    dfm::materialize32_kernel<<<std::min(ntiles, dfm::tc_sm_count() * 6), 256, 0, st>>>(
+        src, (int)V, (int)HW, ze, out_cl, out_ncdhw);
   } else {
     dim3 block(32, 8), grid((unsigned)((V + 31) / 32), (C + 31) / 32);
     dfm::materialize_kernel<<<grid, block, 0, st>>>(src, C, V, HW, ze, out_cl, out_ncdhw);
@@ -1161,7 +1161,7 @@ int launch_depth_head(const float* d_cost, const float* d_samples, int D, int Ho
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
       attr_sz = sm4;
     }
-    dim3 grid((Wo * factor + dfm::DH4_PX - 1) / dfm::DH4_PX, Ho * factor), block(32, dfm::DH_ZS);
+    dim3 grid((Wo * factor + dfm::DH4_PX - 1) / dfm::DH4_PX, Ho * factor), block(32, dfm::DH4_ZS);
     dfm::depth_head4_kernel<<<grid, block, sm4, st>>>(d_cost, d_samples, D, Ho, Wo, factor,
                                                       d_volume, d_softmax, d_preds, d_norm);
   } else {

@@ -357,15 +357,18 @@ materialize_kernel(Src s, int C, long long V, long long HW, ZExpand ze, float* _
   }
 }
 
-// Vectorised variant for C == 32: 256 threads = 32 voxels x 8 channel quads; the per-channel
-// affine parameters of a thread's quad live in registers, loads / channels-last stores are
-// float4, the NCDHW copy goes through a 32x32 shared-memory transpose and is written as
-// float4 runs of 4 consecutive voxels.  Requires V % 4 == 0 for the NCDHW float4 path.
+// Vectorised variant for C == 32: a block walks tiles of 128 voxels.  256 threads = 32 voxels x
+// 8 channel quads, four voxel groups per tile (12 independent 16-byte loads in flight per
+// thread); the per-channel affine parameters of a thread's quad live in registers, loads and
+// channels-last stores are float4.  The NCDHW copy goes through a [32][128 + 1] shared-memory
+// transpose (odd pitch: both the quad-wise stores and the voxel-wise reads are conflict-free)
+// and leaves as 512-byte runs per channel.
+constexpr int MAT_TV = 128;
 __global__ void __launch_bounds__(256)
 materialize32_kernel(Src s, int V, int HW, ZExpand ze, float* __restrict__ out_cl,
                      float* __restrict__ out_ncdhw) {
-  constexpr int C = 32;
-  __shared__ float tile[C][36];
+  constexpr int C = 32, P = MAT_TV + 1;
+  __shared__ float tile[C * P];
   const int q = threadIdx.x & 7, vl = threadIdx.x >> 3;
   float4 sc[3], sh[3];
 #pragma unroll
@@ -377,49 +380,63 @@ materialize32_kernel(Src s, int V, int HW, ZExpand ze, float* __restrict__ out_c
       sh[i] = __ldg(reinterpret_cast<const float4*>(s.t[i].shift) + q);
     }
   }
-  const int ntiles = (V + 31) / 32;
+  const int ntiles = (V + MAT_TV - 1) / MAT_TV;
   for (int tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
-    const int v = tile_i * 32 + vl;
-    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (v < V) {
-      const int z = zexpand(ze, v / HW), pos = v % HW;
+    float4 raw[4][3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (i < s.n) {
-          const long long off = ((long long)term_plane(s.t[i], z) * HW + pos) * C + 4 * q;
-          float4 a = __ldg(reinterpret_cast<const float4*>(s.t[i].x + off));
-          a.x = fmaf(a.x, sc[i].x, sh[i].x);
-          a.y = fmaf(a.y, sc[i].y, sh[i].y);
-          a.z = fmaf(a.z, sc[i].z, sh[i].z);
-          a.w = fmaf(a.w, sc[i].w, sh[i].w);
-          if (s.t[i].relu) {
-            a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f);
-            a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+    for (int g = 0; g < 4; ++g) {
+      const int v = tile_i * MAT_TV + g * 32 + vl;
+      if (v < V) {
+        const int z = zexpand(ze, v / HW), pos = v % HW;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (i < s.n)
+            raw[g][i] = __ldg(reinterpret_cast<const float4*>(
+                s.t[i].x + ((long long)term_plane(s.t[i], z) * HW + pos) * C + 4 * q));
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int v = tile_i * MAT_TV + g * 32 + vl;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < V) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (i < s.n) {
+            float4 a = raw[g][i];
+            a.x = fmaf(a.x, sc[i].x, sh[i].x);
+            a.y = fmaf(a.y, sc[i].y, sh[i].y);
+            a.z = fmaf(a.z, sc[i].z, sh[i].z);
+            a.w = fmaf(a.w, sc[i].w, sh[i].w);
+            if (s.t[i].relu) {
+              a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f);
+              a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+            }
+            val.x += a.x; val.y += a.y; val.z += a.z; val.w += a.w;
           }
-          val.x += a.x; val.y += a.y; val.z += a.z; val.w += a.w;
         }
+        if (s.outer_relu) {
+          val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f);
+          val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f);
+        }
+        if (out_cl) *reinterpret_cast<float4*>(out_cl + (long long)v * C + 4 * q) = val;
       }
-      if (s.outer_relu) {
-        val.x = fmaxf(val.x, 0.f); val.y = fmaxf(val.y, 0.f);
-        val.z = fmaxf(val.z, 0.f); val.w = fmaxf(val.w, 0.f);
+      if (out_ncdhw) {
+        float* t = tile + (4 * q) * P + g * 32 + vl;
+        t[0] = val.x; t[P] = val.y; t[2 * P] = val.z; t[3 * P] = val.w;
       }
-      if (out_cl) *reinterpret_cast<float4*>(out_cl + (long long)v * C + 4 * q) = val;
     }
     if (out_ncdhw) {
-      tile[4 * q][vl] = val.x;
-      tile[4 * q + 1][vl] = val.y;
-      tile[4 * q + 2][vl] = val.z;
-      tile[4 * q + 3][vl] = val.w;
       __syncthreads();
-      const int c = threadIdx.x >> 3, vq = threadIdx.x & 7;
-      const int v0 = tile_i * 32 + 4 * vq;
-      if (v0 + 3 < V) {
-        *reinterpret_cast<float4*>(out_ncdhw + (long long)c * V + v0) =
-            make_float4(tile[c][4 * vq], tile[c][4 * vq + 1], tile[c][4 * vq + 2],
-                        tile[c][4 * vq + 3]);
-      } else {
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;   // warp w: channels w, w+8, ...
+      const int vbase = tile_i * MAT_TV;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = w + 8 * cc;
+        float* dst = out_ncdhw + (long long)c * V + vbase;
+#pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (v0 + k < V) out_ncdhw[(long long)c * V + v0 + k] = tile[c][4 * vq + k];
+          if (vbase + k * 32 + lane < V) __stcs(dst + k * 32 + lane, tile[c * P + k * 32 + lane]);
       }
       __syncthreads();
     }

@@ -181,17 +181,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 constexpr int DH4_PX = 128;   // output pixels along x per block
 __host__ __device__ inline int dh4_ncols(int f) { return DH4_PX / f + 3; }
-inline size_t dh4_smem_bytes(int D, int f) { return (size_t)D * dh4_ncols(f) * sizeof(float); }
+constexpr int DH4_ZS = 8;     // depth segments (warps) per block: they share the staged rows
+// dynamic shared memory: per-bin table float4[D f] | first-bin table int[D + 2 (+pad)] | rows
+__host__ __device__ inline int dh4_k0_ints(int D) { return (D + 2 + 3) / 4 * 4; }
+inline size_t dh4_smem_bytes(int D, int f) {
+  return (size_t)D * f * sizeof(float4) + (size_t)dh4_k0_ints(D) * sizeof(int) +
+         (size_t)D * dh4_ncols(f) * sizeof(float);
+}
 
-__global__ void __launch_bounds__(32 * DH_ZS)
+__global__ void __launch_bounds__(32 * DH4_ZS, 4)
 depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ samples, int D,
                    int Ho, int Wo, int f, float* __restrict__ vol, float* __restrict__ sm,
                    float* __restrict__ preds, float2* __restrict__ norm) {
-  extern __shared__ float dh_rows[];                 // [D][nc]: y-blended low-res rows
-  __shared__ float red[3][DH_ZS][DH4_PX];
-  __shared__ float tab_l0[DH_MAXBINS], tab_l1[DH_MAXBINS], tab_s[DH_MAXBINS];
-  __shared__ int tab_k0[DH_MAXBINS + 2];             // first bin of low-res interval z
+  constexpr int DH_ZS = DH4_ZS;                      // (shadows the one-pixel kernel's constant)
+  extern __shared__ float4 dh4_dyn[];
   const int OW = Wo * f, OH = Ho * f, OD = D * f;
+  float4* tab = dh4_dyn;                                          // per bin: (l0, l1, sample, -)
+  int* tab_k0 = reinterpret_cast<int*>(tab + OD);                 // first bin of interval z
+  float* dh_rows = reinterpret_cast<float*>(tab_k0 + dh4_k0_ints(D));  // [D][nc]: y-blended rows
+  __shared__ float red[3][DH_ZS][DH4_PX];
   const int tx = threadIdx.x, seg = threadIdx.y, tid = seg * 32 + tx;
   const float sz = OD > 1 ? (float)(D - 1) / (OD - 1) : 0.f;
   for (int z = tid; z <= D; z += 32 * DH_ZS) tab_k0[z] = OD;
@@ -200,9 +208,7 @@ depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ sam
     const float fz = sz * k;       // ATen: area_pixel_compute_source_index, align_corners
     const int z0 = min((int)fz, D - 1);
     const float l1 = fz - z0;
-    tab_l1[k] = l1;
-    tab_l0[k] = 1.f - l1;
-    tab_s[k] = samples ? __ldg(samples + k) : 0.f;
+    tab[k] = make_float4(1.f - l1, l1, samples ? __ldg(samples + k) : 0.f, 0.f);
     atomicMin(&tab_k0[z0], k);
   }
   const int Xb = blockIdx.x * DH4_PX;
@@ -285,7 +291,8 @@ depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ sam
     }
     const int ke = tab_k0[z + 1];
     for (int k = tab_k0[z]; k < ke; ++k) {
-      const float l0 = tab_l0[k], l1 = tab_l1[k], s = tab_s[k];
+      const float4 tk = tab[k];
+      const float l0 = tk.x, l1 = tk.y, s = tk.z;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float e = ex2_approx(fmaf(l1, b1[j], l0 * b0[j]));
@@ -327,6 +334,9 @@ depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ sam
   if (!sm && !vol) return;
 #pragma unroll
   for (int j = 0; j < 4; ++j) b1[j] = col(zA, j);
+  // bins are visited in increasing k: running output pointers (null outputs are never stored)
+  float* pv = vol + (long long)tab_k0[zA] * oplane + opix;
+  float* ps = sm + (long long)tab_k0[zA] * oplane + opix;
   for (int z = zA; z < zB; ++z) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -335,19 +345,20 @@ depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ sam
     }
     const int ke = tab_k0[z + 1];
     for (int k = tab_k0[z]; k < ke; ++k) {
-      const float l0 = tab_l0[k], l1 = tab_l1[k];
+      const float2 tk = *reinterpret_cast<const float2*>(&tab[k]);
+      const float l0 = tk.x, l1 = tk.y;
       float v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = l0 * b0[j] + l1 * b1[j];
-      if (vol)
-        __stcs(reinterpret_cast<float4*>(vol + k * oplane + opix),
-               make_float4(v[0], v[1], v[2], v[3]));
+      if (vol) __stcs(reinterpret_cast<float4*>(pv), make_float4(v[0], v[1], v[2], v[3]));
+      pv += oplane;
       if (sm)
-        __stcs(reinterpret_cast<float4*>(sm + k * oplane + opix),
+        __stcs(reinterpret_cast<float4*>(ps),
                make_float4(ex2_approx(fmaf(v[0], LOG2E, -ml2[0])) * inv[0],
                            ex2_approx(fmaf(v[1], LOG2E, -ml2[1])) * inv[1],
                            ex2_approx(fmaf(v[2], LOG2E, -ml2[2])) * inv[2],
                            ex2_approx(fmaf(v[3], LOG2E, -ml2[3])) * inv[3]));
+      ps += oplane;
     }
   }
 }
