@@ -121,6 +121,13 @@ struct Norm {  // GroupNorm (statistics computed per frame) or folded BatchNorm 
   int C = 0;
   DevBuf gamma, beta, scale, shift;
   double* sums = nullptr;
+  bool sums_clean = false;  // gn_finalize_kernel left the sums zeroed and nothing touched them since
+  // call before launching kernels that accumulate into `sums`
+  int begin_stats(cudaStream_t st) {
+    if (!sums_clean) CU_TRY(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st));
+    sums_clean = false;
+    return DFM_OK;
+  }
   int init(int c) {
     C = c;
     DFM_TRY(gamma.alloc(c));
@@ -274,11 +281,12 @@ int gn_finalize(Norm& n, long long V, int groups, cudaStream_t st) {
   dfm::gn_finalize_kernel<<<1, 256, 0, st>>>(n.sums, n.gamma.p, n.beta.p, n.C, groups, (double)V,
                                            1e-5f, n.scale.p, n.shift.p);
   LAUNCH_CHECK();
+  n.sums_clean = true;
   return DFM_OK;
 }
 
 int run_gn(const float* raw, long long V, Norm& n, int groups, cudaStream_t st) {
-  CU_TRY(cudaMemsetAsync(n.sums, 0, 2 * n.C * sizeof(double), st));
+  DFM_TRY(n.begin_stats(st));
   const int blocks = (int)std::min<long long>(148 * 8, (V * n.C + 255) / 256);
   if (n.C == 32)
     dfm::channel_stats_kernel<32><<<blocks, 256, 0, st>>>(raw, V, n.sums);
@@ -310,7 +318,7 @@ int run_conv_impl(const L& simt_loader, TCFN tc_fn, const char* loader_name, con
     return fail(DFM_ERR_INVALID, "conv3d: no tensor-core kernel for this layer");
   if (impl != DFM_CONV_SIMT && tc_ok) {
     std::string err;
-    if (gn) CU_TRY(cudaMemsetAsync(gn->sums, 0, 2 * gn->C * sizeof(double), st));
+    if (gn) DFM_TRY(gn->begin_stats(st));
     {
       ProfScope ps(conv_class("conv_tc", g, loader_name), conv_flops(g), st);
       if (!tc_fn(gn ? gn->sums : nullptr, &err)) return fail(DFM_ERR_CUDA, err);
@@ -356,7 +364,7 @@ int run_conv_presplit(const dfm::Src& s, DevBuf& ps, const ConvW& w, float* out,
     g_launches.fetch_add(1);
   }
   const long long V = (long long)(zw.count_planes ? zw.count_planes : g.Do) * g.Ho * g.Wo;
-  if (gn) CU_TRY(cudaMemsetAsync(gn->sums, 0, 2 * gn->C * sizeof(double), st));
+  if (gn) DFM_TRY(gn->begin_stats(st));
   {
     std::string err;
     ProfScope pc(conv_class("conv_tc", g, "tma"), conv_flops(g), st);
@@ -745,7 +753,7 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
     if (mono) {
       // dres0_mono's whole output is z-class compressed; its GroupNorm statistics weigh the
       // three planes 1 : Dfull-2 : 1
-      CU_TRY(cudaMemsetAsync(t.g0.sums, 0, 2 * cv * sizeof(double), st));
+      DFM_TRY(t.g0.begin_stats(st));
       dfm::channel_stats_zcls_kernel<32><<<148, 256, 0, st>>>(t.cls3.p, (long long)Ho * Wo, Dfull,
                                                              t.g0.sums);
       LAUNCH_CHECK();

@@ -291,18 +291,23 @@ __global__ void pick_planes_kernel(const float* __restrict__ in, float* __restri
 
 // scale/shift of GroupNorm(groups, C) from per-channel sums over `count` voxels:
 // y = (x - mean_g) * rstd_g * gamma[c] + beta[c]  ==  x * scale[c] + shift[c]
-__global__ void gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+// The sums are zeroed once consumed, so the next frame's conv epilogues accumulate into clean
+// buffers without a memset node per layer in the stream.
+__global__ void gn_finalize_kernel(double* __restrict__ sums, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, int C, int groups,
                                    double count, float eps, float* __restrict__ scale,
                                    float* __restrict__ shift) {
   const int c = threadIdx.x;
-  if (c >= C) return;
-  const int cpg = C / groups, g = c / cpg;
+  const int cpg = C / groups, g = (c < C ? c : 0) / cpg;
   double s = 0.0, ss = 0.0;
   for (int k = 0; k < cpg; ++k) {
     s += sums[2 * (g * cpg + k)];
     ss += sums[2 * (g * cpg + k) + 1];
   }
+  __syncthreads();  // every group member has read its group's sums
+  if (c >= C) return;
+  sums[2 * c] = 0.0;
+  sums[2 * c + 1] = 0.0;
   const double n = count * cpg;
   const double mean = s / n;
   double var = ss / n - mean * mean;
