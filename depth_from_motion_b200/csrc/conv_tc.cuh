@@ -69,7 +69,7 @@ inline float bf16_bits_to_float(uint16_t b) {
 // ----------------------------------------------------------------------------------
 enum { TC_S1 = 0, TC_S2 = 1, TC_T = 2 };
 constexpr int TC_BX = 8, TC_BY = 16;  // M tile: 8 (x) * 16 (y) = 128 accumulator rows
-constexpr int TC_LOAD_THREADS = 256;
+constexpr int TC_LOAD_THREADS = 320;  // 2 groups x 5 warps: 15 warps per CTA = 4,4,4,3 per scheduler, still 128 registers/thread
 constexpr int TC_THREADS = 128 + TC_LOAD_THREADS + 32;  // epilogue | loaders | MMA issuer
 constexpr int TC_MAXOPS = 9, TC_MAXBLK = 48;
 constexpr int TC_ZERO_TAP = 255;  // TcBlk::tap of an all-zero padding block
