@@ -25,7 +25,7 @@ constexpr uint32_t NK_STAGE_BYTES = 2 * 4 * NK_ROWS * 16;
 constexpr uint32_t NK_TAP16 = 4 * 96;           // one in-plane tap of a group image, 16 B units
 constexpr uint32_t NK_WHI_BYTES = 9 * NK_TAP16 * 16;
 constexpr uint32_t NK_W_BYTES = 2 * NK_WHI_BYTES;
-constexpr int NK_LOAD_THREADS = 256;
+constexpr int NK_LOAD_THREADS = 320;   // 2 groups x 5 warps (15 warps: 128 registers/thread still fit)
 constexpr int NK_THREADS = 128 + NK_LOAD_THREADS + 32;
 
 enum { NKZ_S1P1 = 0, NKZ_S2P1 = 1, NKZ_S1P0 = 2 };
