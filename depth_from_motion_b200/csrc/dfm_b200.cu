@@ -1120,7 +1120,29 @@ int backbone_forward_impl(dfm_backbone_t* bb, const float* d_cur, const float* d
   // mono/stereo gate (dfm_backbone.py:130-141)
   const int HWo = bb->Ho * bb->Wo;
   const size_t gsm = dfm::gate_smem_bytes(bb->D);
-  if (bb->D <= 256 && gsm <= 200 * 1024 && getenv("DFM_GATE_V1") == nullptr) {
+  const size_t gsm4 = dfm::gate4_smem_bytes(bb->D);
+  static const char* gate_env = getenv("DFM_GATE");   // "v1" | "px1": A/B switches
+  const bool gate_v1 = getenv("DFM_GATE_V1") != nullptr || (gate_env && !strcmp(gate_env, "v1"));
+  if (bb->D <= 256 && HWo % 4 == 0 && gsm4 <= 220 * 1024 && !gate_v1 &&
+      !(gate_env && !strcmp(gate_env, "px1"))) {
+    // 4 pixels x 16 planes per thread, weights resident in shared memory, persistent blocks
+    size_t& attr_sz = dfm::per_device<size_t, 11>();
+    if (attr_sz < gsm4) {
+      CU_TRY(cudaFuncSetAttribute(dfm::gate_tile4_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm4));
+      attr_sz = gsm4;
+    }
+    const int ng = (bb->D + dfm::GT_PG - 1) / dfm::GT_PG;
+    const int ntiles = (HWo + dfm::GT4_TP - 1) / dfm::GT4_TP;
+    // equal rounds per block: 234 tiles -> 117 blocks x 2 rather than 148 blocks with 86 doing 2
+    const int sms = dfm::tc_sm_count();
+    const int rounds = (ntiles + sms - 1) / sms;
+    const int grid = (ntiles + rounds - 1) / rounds;
+    ProfScope ps("gate", 0.0, st);
+    dfm::gate_tile4_kernel<<<grid, 32 * ng, gsm4, st>>>(bb->st.logit.p, bb->mo.logit.p,
+                                                       bb->waggT.p, bb->cost.p, bb->D, HWo,
+                                                       ze_mono);
+  } else if (bb->D <= 256 && gsm <= 200 * 1024 && !gate_v1) {
     // weights resident in shared memory, one persistent block per SM
     bool& attr_done = dfm::per_device<bool, 8>();
     size_t& attr_sz = dfm::per_device<size_t, 9>();
@@ -1131,9 +1153,10 @@ int backbone_forward_impl(dfm_backbone_t* bb, const float* d_cur, const float* d
       attr_sz = gsm;
     }
     const int ng = (bb->D + dfm::GT_PG - 1) / dfm::GT_PG;
-    const int grid = std::min((HWo + 31) / 32, dfm::tc_sm_count());
+    const int nh = dfm::gate_halves(bb->D);
+    const int grid = std::min((HWo + 32 * nh - 1) / (32 * nh), dfm::tc_sm_count());
     ProfScope ps("gate", 0.0, st);
-    dfm::gate_persistent_kernel<<<grid, 32 * ng, gsm, st>>>(bb->st.logit.p, bb->mo.logit.p,
+    dfm::gate_persistent_kernel<<<grid, 32 * ng * nh, gsm, st>>>(bb->st.logit.p, bb->mo.logit.p,
                                                             bb->waggT.p, bb->cost.p, bb->D, HWo,
                                                             ze_mono);
   } else {

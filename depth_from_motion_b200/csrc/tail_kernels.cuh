@@ -370,8 +370,11 @@ depth_head4_kernel(const float* __restrict__ cost, const float* __restrict__ sam
 // ---------------------------------------------------------------------------------
 constexpr int GT_PG = 16;   // output planes per thread
 __host__ __device__ inline int gate_row_pitch(int D) { return (D + GT_PG - 1) / GT_PG * GT_PG; }
+// pixel halves per block: 2 x 32 pixels share the resident weights when the block stays <= 512
+// threads (14 instead of 7 warps per SM to hide the shared-memory latency)
+__host__ __device__ inline int gate_halves(int D) { return 32 * ((D + GT_PG - 1) / GT_PG) * 2 <= 512 ? 2 : 1; }
 inline size_t gate_smem_bytes(int D) {
-  return ((size_t)2 * D * gate_row_pitch(D) + (size_t)2 * D * 32) * sizeof(float);
+  return ((size_t)2 * D * gate_row_pitch(D) + (size_t)2 * D * 32 * gate_halves(D)) * sizeof(float);
 }
 // wT: the 1x1 conv weight transposed and padded on the host, [2D][gate_row_pitch(D)]
 __global__ void __launch_bounds__(512)
@@ -381,20 +384,22 @@ gate_persistent_kernel(const float* __restrict__ ls, const float* __restrict__ l
   extern __shared__ float gsm[];
   const int ng = (D + GT_PG - 1) / GT_PG, DP = ng * GT_PG;
   float* wT = gsm;                          // [2D][DP]
-  float* cat = gsm + (size_t)2 * D * DP;    // [2D][32]
-  const int nthreads = blockDim.x;          // 32 * ng
+  const int NH = gate_halves(D), TP = 32 * NH;   // pixels per tile
+  float* cat = gsm + (size_t)2 * D * DP;    // [2D][TP]
+  const int nthreads = blockDim.x;          // 32 * ng * NH
   {
     const float4* src = reinterpret_cast<const float4*>(wT_g);
     float4* dst = reinterpret_cast<float4*>(wT);
     for (int i = threadIdx.x; i < 2 * D * DP / 4; i += nthreads) dst[i] = __ldg(src + i);
   }
-  const int px = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int ntiles = (HW + 31) / 32;
+  const int g = (threadIdx.x >> 5) % ng;
+  const int px = (threadIdx.x & 31) + 32 * ((threadIdx.x >> 5) / ng);   // pixel inside the tile
+  const int ntiles = (HW + TP - 1) / TP;
   constexpr int MAXJ = 32;                  // planes of the cat column a thread stages (2D / ng)
   const int nj = (2 * D - g + ng - 1) / ng; // j = g, g + ng, ...
   float stage[MAXJ];
   auto fetch = [&](int tile) {
-    const int p = tile * 32 + px;
+    const int p = tile * TP + px;
 #pragma unroll
     for (int q = 0; q < MAXJ; ++q) {
       const int j = g + q * ng;
@@ -408,11 +413,11 @@ gate_persistent_kernel(const float* __restrict__ ls, const float* __restrict__ l
   int tile = blockIdx.x;
   if (tile < ntiles) fetch(tile);
   for (; tile < ntiles; tile += gridDim.x) {
-    const int p = tile * 32 + px;
+    const int p = tile * TP + px;
     __syncthreads();   // previous tile's cat fully consumed (and wT written, first time)
 #pragma unroll
     for (int q = 0; q < MAXJ; ++q)
-      if (q < nj) cat[(g + q * ng) * 32 + px] = stage[q];
+      if (q < nj) cat[(g + q * ng) * TP + px] = stage[q];
     __syncthreads();
     // the next tile's column is fetched while this one is being reduced
     if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
@@ -422,7 +427,7 @@ gate_persistent_kernel(const float* __restrict__ ls, const float* __restrict__ l
     const float4* wrow = reinterpret_cast<const float4*>(wT + g * GT_PG);
 #pragma unroll 4
     for (int j = 0; j < 2 * D; ++j) {
-      const float c = cat[j * 32 + px];
+      const float c = cat[j * TP + px];
       const float4* w4 = wrow + (size_t)j * (DP / 4);
 #pragma unroll
       for (int q = 0; q < GT_PG / 4; ++q) {
@@ -439,8 +444,89 @@ gate_persistent_kernel(const float* __restrict__ ls, const float* __restrict__ l
         const int d = g * GT_PG + k;
         if (d < D) {
           const float wgt = 1.f / (1.f + __expf(-a[k]));
-          const float sv = cat[d * 32 + px], mv = cat[(D + d) * 32 + px];
+          const float sv = cat[d * TP + px], mv = cat[(D + d) * TP + px];
           cost[(long long)d * HW + p] = wgt * sv + (1.f - wgt) * mv;
+        }
+      }
+    }
+  }
+}
+
+// Register-tiled variant: a thread owns 4 consecutive pixels x 16 output planes, so one broadcast
+// 16-byte weight read feeds 16 FMAs instead of 4.  (Measured: the one-pixel kernel is bound by its
+// shared-memory reads -- a warp-wide LDS.128 costs four LSU cycles even when every lane reads the
+// same address -- and doubling its occupancy changed nothing.)  Tiles of 128 pixels, the cat
+// column block [2D][128] staged once per tile; same summation order per output as the other
+// gate kernels.  Requires HW % 4 == 0.
+constexpr int GT4_TP = 128;
+inline size_t gate4_smem_bytes(int D) {
+  return ((size_t)2 * D * gate_row_pitch(D) + (size_t)2 * D * GT4_TP) * sizeof(float);
+}
+__global__ void __launch_bounds__(512)
+gate_tile4_kernel(const float* __restrict__ ls, const float* __restrict__ lm,
+                  const float* __restrict__ wT_g, float* __restrict__ cost, int D, int HW,
+                  ZExpand zm) {
+  extern __shared__ float gsm[];
+  const int ng = (D + GT_PG - 1) / GT_PG, DP = ng * GT_PG;
+  float* wT = gsm;                                   // [2D][DP]
+  float4* cat4 = reinterpret_cast<float4*>(gsm + (size_t)2 * D * DP);   // [2D][32] float4
+  const int nthreads = blockDim.x;                   // 32 * ng
+  {
+    const float4* src = reinterpret_cast<const float4*>(wT_g);
+    float4* dst = reinterpret_cast<float4*>(wT);
+    for (int i = threadIdx.x; i < 2 * D * DP / 4; i += nthreads) dst[i] = __ldg(src + i);
+  }
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int ntiles = (HW + GT4_TP - 1) / GT4_TP;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int p0 = tile * GT4_TP;
+    __syncthreads();   // previous tile's columns consumed (and wT written, first time)
+    for (int i = threadIdx.x; i < 2 * D * 32; i += nthreads) {
+      const int j = i >> 5, q = i & 31, p = p0 + 4 * q;
+      const float* row = j < D ? ls + (long long)j * HW : lm + (long long)zexpand(zm, j - D) * HW;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < HW) v = __ldg(reinterpret_cast<const float4*>(row + p));   // HW % 4 == 0
+      cat4[i] = v;
+    }
+    __syncthreads();
+    float a[GT_PG][4];
+#pragma unroll
+    for (int k = 0; k < GT_PG; ++k) a[k][0] = a[k][1] = a[k][2] = a[k][3] = 0.f;
+    const float4* wrow = reinterpret_cast<const float4*>(wT + g * GT_PG);
+#pragma unroll 2
+    for (int j = 0; j < 2 * D; ++j) {
+      const float4 c = cat4[j * 32 + lane];
+      const float4* w4 = wrow + (size_t)j * (DP / 4);
+#pragma unroll
+      for (int q = 0; q < GT_PG / 4; ++q) {
+        const float4 w = w4[q];
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          a[4 * q + r][0] = fmaf(wv[r], c.x, a[4 * q + r][0]);
+          a[4 * q + r][1] = fmaf(wv[r], c.y, a[4 * q + r][1]);
+          a[4 * q + r][2] = fmaf(wv[r], c.z, a[4 * q + r][2]);
+          a[4 * q + r][3] = fmaf(wv[r], c.w, a[4 * q + r][3]);
+        }
+      }
+    }
+    const int p = p0 + 4 * lane;
+    if (p < HW) {
+#pragma unroll
+      for (int k = 0; k < GT_PG; ++k) {
+        const int d = g * GT_PG + k;
+        if (d < D) {
+          const float4 sv = cat4[d * 32 + lane], mv = cat4[(D + d) * 32 + lane];
+          float4 o;
+          float wgt = 1.f / (1.f + __expf(-a[k][0]));
+          o.x = wgt * sv.x + (1.f - wgt) * mv.x;
+          wgt = 1.f / (1.f + __expf(-a[k][1]));
+          o.y = wgt * sv.y + (1.f - wgt) * mv.y;
+          wgt = 1.f / (1.f + __expf(-a[k][2]));
+          o.z = wgt * sv.z + (1.f - wgt) * mv.z;
+          wgt = 1.f / (1.f + __expf(-a[k][3]));
+          o.w = wgt * sv.w + (1.f - wgt) * mv.w;
+          *reinterpret_cast<float4*>(cost + (long long)d * HW + p) = o;
         }
       }
     }
