@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('DFM_B200_LIB') or os.path.join(_HERE, 'libdfm_b200.so')
 
 DFM_OK = 0
-DFM_CONV_AUTO, DFM_CONV_SIMT, DFM_CONV_TC, DFM_CONV_TC_NECK = 0, 1, 2, 3
+DFM_CONV_AUTO, DFM_CONV_SIMT, DFM_CONV_TC, DFM_CONV_TC_NECK, DFM_CONV_TC_NECK_DHW = 0, 1, 2, 3, 4
 DFM_OUT_COST, DFM_OUT_STEREO, DFM_OUT_MONO = 1, 2, 4
 DFM_LAYOUT_NCDHW, DFM_LAYOUT_DHWC = 0, 1
 

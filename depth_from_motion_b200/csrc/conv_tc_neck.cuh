@@ -11,6 +11,11 @@
 //     memory, then march the input planes through the usual loader -> MMA pipeline;
 //   * after the last group the epilogue drains the planes (raw conv output; BatchNorm/ReLU
 //     are applied by the consumer's load, like everywhere else).
+// "Windowed" use (neck_tc_conv_dhw): the same kernel runs the 64-channel stride-1 layers of the
+// plane-sweep volume [D][H][W][C] -- tile over (H, W), marched axis D cut into chunks of <= 16
+// output planes whose halo planes are real data -- because there the resident-weight kernel
+// (conv_tc.cuh) has to split the output channels four ways and issues N = 48 MMAs at the 47-cycle
+// floor; here an MMA covers 32 output channels x 3 planes (N = 96).
 #pragma once
 #include "conv_tc.cuh"
 
@@ -50,7 +55,9 @@ struct NeckTcWeights {
   // packed: [27][Cin][Cout] fp32, tap = kz*9 + ky*3 + kx with (kz,ky,kx) over (Nz, Ny, Nx)...
   // NOTE the conv dims are (D,H,W) = (Nx, Ny, Nz): the packed tap index is kd*9 + kh*3 + kw,
   // i.e. kd over Nx, kh over Ny, kw over Nz (the short, marched axis).
-  bool build(const float* packed, int cin, int cout, int zm, std::string* err) {
+  // dhw: the volume is [D][H][W][C] with D the marched axis (tile over H (16) x W (8)): the
+  // in-plane tap t is kh * 3 + kw and the marched tap is kd
+  bool build(const float* packed, int cin, int cout, int zm, std::string* err, bool dhw = false) {
     release();
     Cin = cin;
     Cout = cout;
@@ -69,7 +76,7 @@ struct NeckTcWeights {
               for (int e = 0; e < 8; ++e) {
                 const int kw = order[zm][r / 32];
                 const int co = s * 32 + r % 32, ci = cg * 32 + kc * 8 + e;
-                const int tap = kd * 9 + kh * 3 + kw;
+                const int tap = dhw ? kw * 9 + kd * 3 + kh : kd * 9 + kh * 3 + kw;
                 const float w = packed[((size_t)tap * cin + ci) * cout + co];
                 const uint16_t hi = bf16_rn_bits(w);
                 const uint16_t lo = bf16_rn_bits(w - bf16_bits_to_float(hi));
@@ -97,8 +104,15 @@ struct NeckParams {
   int zmode;
   int tiles_x, tiles_y, nsplit, ncg, n_items;
   int ntiles;   // tiles_x * tiles_y
-  int tpi;      // tiles per item: their accumulators (Zo * 32 columns each) share the 512 TMEM
+  int tpi;      // tiles per item: their accumulators (ZC * 32 columns each) share the 512 TMEM
                 // columns, so one 110 KB weight image serves tpi tiles before it is replaced
+  // voxel strides of (tile-y axis "x", tile-x axis "y", marched axis) for the input / output
+  long long in_sx, in_sy, in_sz, out_sx, out_sy, out_sz;
+  int ZC;       // output planes per item along the marched axis (== Zo unless windowed)
+  int nchunk;   // windows along the marched axis (1 unless windowed; windowed needs NKZ_S1P1)
+  double* stats;            // optional per-output-channel (sum, sum of squares) of the raw output
+  int zw_lo, zw_hi;         // planes [zw_lo, zw_hi) enter the statistics with weight zw
+  float zw;
   int* err;
 };
 
@@ -150,18 +164,19 @@ struct NeckLoader {
 };
 
 // which weight rows / output planes input plane iz feeds: rows [n0, n0+n) -> planes zo0...
-__device__ __forceinline__ void nk_plane_map(int zmode, int iz, int Zo, int& n0, int& nblk,
-                                             int& zo0) {
+// (iz: absolute input plane; the item owns output planes [zo_lo, zo_hi); zo0 is relative to zo_lo)
+__device__ __forceinline__ void nk_plane_map(int zmode, int iz, int zo_lo, int zo_hi, int& n0,
+                                             int& nblk, int& zo0) {
   if (zmode == NKZ_S1P1) {        // rows [kw=2|1|0] -> planes iz-1, iz, iz+1
-    const int lo = iz - 1 < 0 ? 1 : 0, hi = iz + 1 >= Zo ? 1 : 2;
-    n0 = lo * 32;
-    nblk = hi - lo + 1;
-    zo0 = iz - 1 + lo;
+    const int first = max(iz - 1, zo_lo), last = min(iz + 1, zo_hi - 1);
+    n0 = (first - (iz - 1)) * 32;
+    nblk = last - first + 1;
+    zo0 = first - zo_lo;
   } else if (zmode == NKZ_S2P1) { // rows [kw=2|0|1]; iz = 2q+1 -> planes q, q+1; iz = 2q -> q
     const int q = iz >> 1;
     if (iz & 1) {
       n0 = 0;
-      nblk = q + 1 < Zo ? 2 : 1;
+      nblk = q + 1 < zo_hi ? 2 : 1;
       zo0 = q;
     } else {
       n0 = 64;
@@ -173,6 +188,28 @@ __device__ __forceinline__ void nk_plane_map(int zmode, int iz, int Zo, int& n0,
     nblk = 1;
     zo0 = 0;
   }
+}
+
+// item -> (first tile, tiles, marched-axis window)
+struct NkItem {
+  int tile0, nt, zo_lo, zo_hi, iz_lo, nzi;
+};
+__device__ __forceinline__ NkItem nk_item(const NeckParams& p, int item) {
+  NkItem it;
+  const int unit = item / p.nsplit;
+  const int chunk = unit % p.nchunk;
+  it.tile0 = (unit / p.nchunk) * p.tpi;
+  it.nt = min(p.tpi, p.ntiles - it.tile0);
+  it.zo_lo = chunk * p.ZC;
+  it.zo_hi = min(it.zo_lo + p.ZC, p.Zo);
+  if (p.nchunk > 1) {  // windowed NKZ_S1P1: halo planes are real data where they exist
+    it.iz_lo = max(it.zo_lo - 1, 0);
+    it.nzi = min(it.zo_hi + 1, p.Zi) - it.iz_lo;
+  } else {
+    it.iz_lo = 0;
+    it.nzi = p.Zi;
+  }
+  return it;
 }
 
 template <int NT>
@@ -238,8 +275,8 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
     const int chunk = lt & 3;
     uint32_t stage_ctr = 0, w_ctr = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int tile0 = (item / p.nsplit) * p.tpi;
-      const int nt = min(p.tpi, p.ntiles - tile0);
+      const NkItem it = nk_item(p, item);
+      const int tile0 = it.tile0, nt = it.nt;
       for (int cg = 0; cg < p.ncg; ++cg, ++w_ctr) {
         // this group's weight image (all loader threads), once the previous group's MMAs retired
         mbar_wait(w_empty, (w_ctr & 1) ^ 1, p.err);
@@ -255,8 +292,9 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
         for (int t = 0; t < nt; ++t) {
           const int tile = tile0 + t;
           const int y0 = (tile % p.tiles_x) * NK_BX, x0 = (tile / p.tiles_x) * NK_BY;
-          for (int iz = 0; iz < p.Zi; ++iz, ++stage_ctr) {
+          for (int izl = 0; izl < it.nzi; ++izl, ++stage_ctr) {
             if ((int)(stage_ctr & 1) != lgrp) continue;
+            const int iz = it.iz_lo + izl;
             const int s = stage_ctr % NK_NSTAGE;
             mbar_wait(empty_a(s), ((stage_ctr / NK_NSTAGE) & 1) ^ 1, p.err);
             uint8_t* st = a_s + s * NK_STAGE_BYTES;
@@ -276,7 +314,7 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
                 inb[b] = live[b] && gx >= 0 && gx < p.Nx && gy >= 0 && gy < p.Ny;
                 soff[b] = (chunk * NK_ROWS + pos) * 16;
                 if (inb[b])
-                  NeckLoader<NT>::issue(p, ((long long)gx * p.Ny + gy) * p.Zi + iz, c0, raw[b]);
+                  NeckLoader<NT>::issue(p, gx * p.in_sx + gy * p.in_sy + iz * p.in_sz, c0, raw[b]);
               }
 #pragma unroll
               for (int b = 0; b < LB; ++b) {
@@ -310,19 +348,19 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
       // the previous item's accumulators must have been drained (and re-zeroed)
       mbar_wait(acc_empty, (item_ctr & 1) ^ 1, p.err);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int tile0 = (item / p.nsplit) * p.tpi;
-      const int nt = min(p.tpi, p.ntiles - tile0);
+      const NkItem it = nk_item(p, item);
+      const int nt = it.nt;
       for (int cg = 0; cg < p.ncg; ++cg, ++w_ctr) {
         mbar_wait(w_full, w_ctr & 1, p.err);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int t = 0; t < nt; ++t) {
-          for (int iz = 0; iz < p.Zi; ++iz, ++stage_ctr) {
+          for (int izl = 0; izl < it.nzi; ++izl, ++stage_ctr) {
             const int s = stage_ctr % NK_NSTAGE;
             mbar_wait(full_a(s), (stage_ctr / NK_NSTAGE) & 1, p.err);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int n0, nblk, zo0;
-            nk_plane_map(p.zmode, iz, p.Zo, n0, nblk, zo0);
-            const uint32_t d0 = tmem_u + (uint32_t)(t * p.Zo + zo0) * NK_NCTA;
+            nk_plane_map(p.zmode, it.iz_lo + izl, it.zo_lo, it.zo_hi, n0, nblk, zo0);
+            const uint32_t d0 = tmem_u + (uint32_t)(t * p.ZC + zo0) * NK_NCTA;
             const uint32_t idesc = idesc_bf16(nblk * NK_NCTA);
             const uint32_t a_lo_stage = (((a_base + s * NK_STAGE_BYTES) >> 4) & 0x3FFF) | (A_LBO16 << 16);
             const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFF) + (uint32_t)n0 + (B_LBO16 << 16);
@@ -367,29 +405,40 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
     // ============================ epilogue (warps 0-3) ============================
     const int m = warp * 32 + lane;
     uint32_t item_ctr = 0;
+    float ssum[NK_NCTA], ssq[NK_NCTA];   // GroupNorm sums of this item (p.stats), fp32 per thread
+#pragma unroll
+    for (int i = 0; i < NK_NCTA; ++i) ssum[i] = ssq[i] = 0.f;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_ctr) {
-      const int tile0 = (item / p.nsplit) * p.tpi;
-      const int nt = min(p.tpi, p.ntiles - tile0);
+      const NkItem it = nk_item(p, item);
       mbar_wait(acc_full, item_ctr & 1, p.err);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int t = 0; t < nt; ++t) {
-        const int tile = tile0 + t;
+      for (int t = 0; t < it.nt; ++t) {
+        const int tile = it.tile0 + t;
         const int y = (tile % p.tiles_x) * NK_BX + (m & 7), x = (tile / p.tiles_x) * NK_BY + (m >> 3);
         const bool ok = x < p.Nx && y < p.Ny;
-        for (int zo = 0; zo < p.Zo; ++zo) {
+        for (int zo = it.zo_lo; zo < it.zo_hi; ++zo) {
           uint32_t r[NK_NCTA];
           const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
-                              (uint32_t)(t * p.Zo + zo) * NK_NCTA;
+                              (uint32_t)(t * p.ZC + zo - it.zo_lo) * NK_NCTA;
           tmem_ld<NK_NCTA>(ta, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           tmem_zero<NK_NCTA>(ta);
           if (ok) {
             float4* dst = reinterpret_cast<float4*>(
-                p.out + (((long long)x * p.Ny + y) * p.Zo + zo) * p.Cout + split * NK_NCTA);
+                p.out + (x * p.out_sx + y * p.out_sy + zo * p.out_sz) * p.Cout + split * NK_NCTA);
 #pragma unroll
             for (int q = 0; q < NK_NCTA / 4; ++q)
               dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            if (p.stats) {
+              const float wz = (zo >= p.zw_lo && zo < p.zw_hi) ? p.zw : 1.f;
+#pragma unroll
+              for (int i = 0; i < NK_NCTA; ++i) {
+                const float v = __uint_as_float(r[i]);
+                ssum[i] = fmaf(wz, v, ssum[i]);
+                ssq[i] = fmaf(wz * v, v, ssq[i]);
+              }
+            }
           }
         }
       }
@@ -397,6 +446,22 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
+      if (p.stats) {  // one flush per item keeps the fp32 partial sums short (<= 16 values)
+#pragma unroll
+        for (int i = 0; i < NK_NCTA; ++i) {
+          double a = ssum[i], b = ssq[i];
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          if (lane == 0) {
+            atomicAdd(p.stats + 2 * (split * NK_NCTA + i), a);
+            atomicAdd(p.stats + 2 * (split * NK_NCTA + i) + 1, b);
+          }
+          ssum[i] = ssq[i] = 0.f;
+        }
+      }
     }
   }
 
@@ -407,32 +472,8 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
                  "r"(TMEM_COLS));
 }
 
-inline bool neck_tc_conv(const Src& s, const NeckTcWeights& w, float* out, const ConvGeom& g,
-                         cudaStream_t st, std::string* err) {
+inline bool neck_launch(NeckParams& p, int nterms, cudaStream_t st, std::string* err) {
   const size_t smem = NK_W_BYTES + (size_t)NK_NSTAGE * NK_STAGE_BYTES + (2 * NK_NSTAGE + 4) * 8 + 16;
-  NeckParams p{};
-  p.wimg = w.dev;
-  p.out = out;
-  p.src = s;
-  p.Nx = g.Di; p.Ny = g.Hi; p.Zi = g.Wi; p.Zo = g.Wo;
-  p.Cin = g.Cin; p.Cout = g.Cout;
-  p.zmode = w.zmode;
-  p.tiles_x = (g.Hi + NK_BX - 1) / NK_BX;   // along Ny
-  p.tiles_y = (g.Di + NK_BY - 1) / NK_BY;   // along Nx
-  p.nsplit = g.Cout / 32;
-  p.ncg = g.Cin / 32;
-  p.ntiles = p.tiles_x * p.tiles_y;
-  // tiles per item: as many as the 512 TMEM columns hold (Zo * 32 columns per tile), but not so
-  // many that the persistent grid runs short of items
-  const int tpi_env = getenv("DFM_NECK_TPI") ? atoi(getenv("DFM_NECK_TPI")) : 0;  // tests / A-B runs
-  {
-    const int cap = std::max(1, 512 / (g.Wo * NK_NCTA));
-    const int sms0 = tc_sm_count();
-    int tpi = std::min(cap, std::max(1, p.ntiles * p.nsplit / (2 * sms0)));
-    if (tpi_env > 0) tpi = std::min(cap, tpi_env);
-    p.tpi = std::max(1, tpi);
-  }
-  p.n_items = (p.ntiles + p.tpi - 1) / p.tpi * p.nsplit;
   p.err = tc_err_flag().get();
   const int sms = tc_sm_count();
   int grid = std::max(p.nsplit, sms / p.nsplit * p.nsplit);
@@ -453,10 +494,114 @@ inline bool neck_tc_conv(const Src& s, const NeckTcWeights& w, float* out, const
     }
     return true;
   };
-  if (s.n == 1) return launch(neck_conv_kernel<1>);
-  if (s.n == 2) return launch(neck_conv_kernel<2>);
+  if (nterms == 1) return launch(neck_conv_kernel<1>);
+  if (nterms == 2) return launch(neck_conv_kernel<2>);
   if (err) *err = "neck_tc_conv: at most two input terms";
   return false;
+}
+
+// BEV-neck orientation: volume [Nx][Ny][Nz][C], the short Nz axis is marched whole
+inline bool neck_tc_conv(const Src& s, const NeckTcWeights& w, float* out, const ConvGeom& g,
+                         cudaStream_t st, std::string* err) {
+  NeckParams p{};
+  p.wimg = w.dev;
+  p.out = out;
+  p.src = s;
+  p.Nx = g.Di; p.Ny = g.Hi; p.Zi = g.Wi; p.Zo = g.Wo;
+  p.Cin = g.Cin; p.Cout = g.Cout;
+  p.zmode = w.zmode;
+  p.tiles_x = (g.Hi + NK_BX - 1) / NK_BX;   // along Ny
+  p.tiles_y = (g.Di + NK_BY - 1) / NK_BY;   // along Nx
+  p.nsplit = g.Cout / 32;
+  p.ncg = g.Cin / 32;
+  p.ntiles = p.tiles_x * p.tiles_y;
+  p.in_sx = (long long)g.Hi * g.Wi; p.in_sy = g.Wi; p.in_sz = 1;
+  p.out_sx = (long long)g.Ho * g.Wo; p.out_sy = g.Wo; p.out_sz = 1;
+  p.ZC = g.Wo;
+  p.nchunk = 1;
+  p.stats = nullptr;
+  // tiles per item: as many as the 512 TMEM columns hold (Zo * 32 columns per tile), but not so
+  // many that the persistent grid runs short of items
+  const int tpi_env = getenv("DFM_NECK_TPI") ? atoi(getenv("DFM_NECK_TPI")) : 0;  // tests / A-B runs
+  {
+    const int cap = std::max(1, 512 / (g.Wo * NK_NCTA));
+    const int sms0 = tc_sm_count();
+    int tpi = std::min(cap, std::max(1, p.ntiles * p.nsplit / (2 * sms0)));
+    if (tpi_env > 0) tpi = std::min(cap, tpi_env);
+    p.tpi = std::max(1, tpi);
+  }
+  p.n_items = (p.ntiles + p.tpi - 1) / p.tpi * p.nsplit;
+  return neck_launch(p, s.n, st, err);
+}
+
+// Plane-sweep-volume orientation: [D][H][W][C], stride 1, pad 1; tiles over (H: 16, W: 8), the
+// D axis cut into windows of `zc` output planes (<= 16: 32 TMEM columns each).  `w` must have
+// been built with dhw = true.  stats: optional GroupNorm sums of the raw output (zeroed by the
+// caller), planes [zw_lo, zw_hi) weighted by zw.
+inline bool neck_dhw_supported(const ConvGeom& g) {
+  return !g.transposed && g.sd == 1 && g.sh == 1 && g.sw == 1 && g.pd == 1 && g.ph == 1 &&
+         g.pw == 1 && g.Cin % 32 == 0 && g.Cout % 32 == 0 && g.Cin >= 64;
+}
+// Window length / tiles per item of the windowed launch: static round-robin over equal items, so
+// pick the pair that minimises rounds x item cost (item cost ~ tpi * (zc + 2 halo planes) + the
+// weight-image reload, ~1.5 plane-equivalents per 32-channel input group).
+struct NeckDhwPlan {
+  int zc, tpi, items;
+};
+inline NeckDhwPlan neck_dhw_plan(const ConvGeom& g) {
+  const int sms = tc_sm_count();
+  const int ntiles = ((g.Wi + NK_BX - 1) / NK_BX) * ((g.Hi + NK_BY - 1) / NK_BY);
+  const int nsplit = g.Cout / 32;
+  NeckDhwPlan best{std::min(g.Do, 16), 1, 0};
+  double best_cost = 1e30;
+  for (int zc = std::min(g.Do, 16); zc >= std::min(g.Do, 4); --zc) {
+    const int nchunk = (g.Do + zc - 1) / zc;
+    for (int tpi = 1; tpi <= 512 / (zc * NK_NCTA); ++tpi) {
+      const int items = (ntiles + tpi - 1) / tpi * nchunk * nsplit;
+      const int rounds = (items + sms - 1) / sms;
+      const double cost = rounds * (tpi * (zc + 2.0) + 1.5);
+      if (cost < best_cost - 1e-9) {
+        best_cost = cost;
+        best = NeckDhwPlan{zc, tpi, items};
+      }
+    }
+  }
+  return best;
+}
+// worth it only when the items fill the machine (the resident-weight kernel cuts its work
+// stream-K style and keeps every SM busy on small volumes)
+inline bool neck_dhw_profitable(const ConvGeom& g) {
+  return neck_dhw_supported(g) && neck_dhw_plan(g).items >= tc_sm_count();
+}
+inline bool neck_tc_conv_dhw(const Src& s, const NeckTcWeights& w, float* out, const ConvGeom& g,
+                             double* stats, int zw_lo, int zw_hi, float zw, cudaStream_t st,
+                             std::string* err) {
+  NeckParams p{};
+  p.wimg = w.dev;
+  p.out = out;
+  p.src = s;
+  p.Nx = g.Hi; p.Ny = g.Wi; p.Zi = g.Di; p.Zo = g.Do;
+  p.Cin = g.Cin; p.Cout = g.Cout;
+  p.zmode = NKZ_S1P1;
+  p.tiles_x = (g.Wi + NK_BX - 1) / NK_BX;   // along W
+  p.tiles_y = (g.Hi + NK_BY - 1) / NK_BY;   // along H
+  p.nsplit = g.Cout / 32;
+  p.ncg = g.Cin / 32;
+  p.ntiles = p.tiles_x * p.tiles_y;
+  p.in_sx = g.Wi; p.in_sy = 1; p.in_sz = (long long)g.Hi * g.Wi;
+  p.out_sx = g.Wo; p.out_sy = 1; p.out_sz = (long long)g.Ho * g.Wo;
+  const NeckDhwPlan plan = neck_dhw_plan(g);
+  // tests / A-B runs (read per call, like DFM_NECK_TPI)
+  const int zc_env = getenv("DFM_NECK_ZC") ? atoi(getenv("DFM_NECK_ZC")) : 0;
+  const int tpi_env = getenv("DFM_NECK_ZTPI") ? atoi(getenv("DFM_NECK_ZTPI")) : 0;
+  p.ZC = std::min(zc_env > 0 ? std::min(zc_env, 16) : plan.zc, g.Do);
+  p.nchunk = (g.Do + p.ZC - 1) / p.ZC;
+  // (the window logic of nk_item serves nchunk == 1 too: iz_lo = 0, nzi = Zi)
+  p.tpi = std::max(1, std::min(512 / (p.ZC * NK_NCTA), tpi_env > 0 ? tpi_env : plan.tpi));
+  p.n_items = (p.ntiles + p.tpi - 1) / p.tpi * p.nchunk * p.nsplit;
+  p.stats = stats;
+  p.zw_lo = zw_lo; p.zw_hi = zw_hi; p.zw = zw;
+  return neck_launch(p, s.n, st, err);
 }
 
 }  // namespace dfm

@@ -152,6 +152,8 @@ struct ConvW {
   DevBuf simt;          // [27][Cin][Cout] fp32
   dfm::TcWeights tc;    // bf16 hi/lo images for the tensor-core kernel
   dfm::NeckTcWeights ntc;  // K-outer tensor-core kernel of the BEV necks
+  dfm::NeckTcWeights ntk;  // the same kernel on the plane-sweep volume (stride-1 layers with
+                           // >= 64 input channels: N = 96 MMAs instead of four N = 48 splits)
 };
 
 // (Cout,Cin,3,3,3) or transposed (Cin,Cout,3,3,3)  ->  [tap][ci][co]
@@ -187,6 +189,12 @@ int set_conv(ConvW& cw, const float* h, long long numel, int Cin, int Cout, int 
   if (tc_mode >= 0 && dfm::tc_supported(Cin, Cout, transposed)) {
     std::string err;
     if (!cw.tc.build(p.data(), Cin, Cout, tc_mode, &err)) return fail(DFM_ERR_CUDA, err);
+  }
+  cw.ntk.release();
+  if (tc_mode == dfm::TC_S1 && !transposed && Cin >= 64 && Cin % 32 == 0 && Cout % 32 == 0) {
+    std::string err;
+    if (!cw.ntk.build(p.data(), Cin, Cout, dfm::NKZ_S1P1, &err, /*dhw=*/true))
+      return fail(DFM_ERR_CUDA, err);
   }
   return DFM_OK;
 }
@@ -339,6 +347,23 @@ int run_conv(const dfm::Src& s, const ConvW& w, float* out, const dfm::ConvGeom&
   dfm::SrcLoader ld{s, g.Cin, g.Hi, g.Wi};
   if (zw.count_planes && (impl == DFM_CONV_SIMT || !w.tc.ready()))
     return fail(DFM_ERR_INVALID, "z-shortened volumes exist only on the tensor-core path");
+  // stride-1 layers with >= 64 input channels: K-outer kernel (conv_tc_neck.cuh, windowed along D)
+  static const bool no_ntk = getenv("DFM_NO_NTK") != nullptr;
+  if (impl != DFM_CONV_SIMT && !no_ntk && w.ntk.ready() && dfm::neck_dhw_profitable(g) &&
+      s.n <= 2 && s.t[0].zcls == 0 && (s.n < 2 || s.t[1].zcls == 0)) {
+    const long long V = (long long)(zw.count_planes ? zw.count_planes : g.Do) * g.Ho * g.Wo;
+    if (gn) DFM_TRY(gn->begin_stats(st));
+    {
+      std::string err;
+      ProfScope ps(conv_class("conv_tck", g, "src"), conv_flops(g), st);
+      if (!dfm::neck_tc_conv_dhw(s, w.ntk, out, g, gn ? gn->sums : nullptr, zw.lo, zw.hi, zw.w,
+                                 st, &err))
+        return fail(DFM_ERR_CUDA, err);
+    }
+    g_launches.fetch_add(1);
+    g_tc_launches.fetch_add(1);
+    return gn ? gn_finalize(*gn, V, 32, st) : DFM_OK;
+  }
   return run_conv_impl(
       ld, [&](double* stats, std::string* err) {
         dfm::TcOpts o;
@@ -595,6 +620,7 @@ void tower_release(Tower& t) {
                    &t.d0cur, &t.d0prev}) {
     c->simt.release();
     c->tc.release();
+    c->ntk.release();
   }
   t.p1q.release();
 }
@@ -1451,7 +1477,22 @@ int dfm_op_conv3d(const float* d_x, int Cin, int Di, int Hi, int Wi, const float
                          (conv_impl == DFM_CONV_TC_NECK || !w.tc.ready());
   if (conv_impl == DFM_CONV_TC_NECK && zm < 0)
     rc = fail(DFM_ERR_INVALID, "conv3d: the BEV-neck tensor-core kernel does not serve this shape");
-  if (rc == DFM_OK && want_neck) {
+  if (conv_impl == DFM_CONV_TC_NECK_DHW) {
+    // the same kernel in plane-sweep-volume orientation (windowed along D), forced
+    if (!dfm::neck_dhw_supported(g)) {
+      rc = fail(DFM_ERR_INVALID, "conv3d: the windowed K-outer kernel needs stride 1, pad 1, "
+                                 "channels in multiples of 32 and >= 64 input channels");
+    } else {
+      const std::vector<float> packed = repack_simt(h_w, Cin, Cout, 0);
+      std::string err;
+      if (!w.ntk.build(packed.data(), Cin, Cout, dfm::NKZ_S1P1, &err, true) ||
+          !dfm::neck_tc_conv_dhw(src1(term(xin, nullptr, 0)), w.ntk, yout.p, g, nullptr, 0, 0, 1.f,
+                                 st, &err))
+        rc = fail(DFM_ERR_CUDA, err);
+      g_launches.fetch_add(1);
+      g_tc_launches.fetch_add(1);
+    }
+  } else if (rc == DFM_OK && want_neck) {
     const std::vector<float> packed = repack_simt(h_w, Cin, Cout, 0);
     std::string err;
     if (!w.ntc.build(packed.data(), Cin, Cout, zm, &err) ||
@@ -1469,6 +1510,7 @@ int dfm_op_conv3d(const float* d_x, int Cin, int Di, int Hi, int Wi, const float
   w.simt.release();
   w.tc.release();
   w.ntc.release();
+  w.ntk.release();
   if (rc == DFM_OK && e != cudaSuccess) rc = fail(DFM_ERR_CUDA, cudaGetErrorString(e));
   if (rc == DFM_OK && dfm::tc_consume_error())
     rc = fail(DFM_ERR_CUDA, "tensor-core conv kernel: mbarrier hand-over timed out");

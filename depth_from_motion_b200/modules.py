@@ -29,7 +29,8 @@ from . import capi
 from .registry import BACKBONES, HEADS, NECKS
 
 _IMPL = {'auto': capi.DFM_CONV_AUTO, 'simt': capi.DFM_CONV_SIMT,
-         'tc': capi.DFM_CONV_TC, 'tc_neck': capi.DFM_CONV_TC_NECK}
+         'tc': capi.DFM_CONV_TC, 'tc_neck': capi.DFM_CONV_TC_NECK,
+         'tc_neck_dhw': capi.DFM_CONV_TC_NECK_DHW}
 
 
 def _ptr(t):

@@ -37,6 +37,8 @@ extern "C" {
 #define DFM_CONV_TC 2   /* tcgen05 only; error if a layer has no tensor-core kernel   */
 #define DFM_CONV_TC_NECK 3 /* dfm_op_conv3d only: force the K-outer tcgen05 kernel of the BEV
                               necks (64..256 channels, W <= 16, strides (1,1,1) / (1,1,2))  */
+#define DFM_CONV_TC_NECK_DHW 4 /* dfm_op_conv3d only: force the same kernel in [D][H][W]
+                                  orientation, D cut into windows (stride 1, pad 1, Cin >= 64) */
 
 /* output-selection flags for the *_host entry points */
 #define DFM_OUT_COST 1   /* gated depth logits           [1,1,D,Ho,Wo] */

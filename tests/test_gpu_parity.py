@@ -127,6 +127,31 @@ def test_neck_conv_kernel_vs_torch(case):
     assert e < 1e-4
 
 
+@pytest.mark.parametrize('zc,tpi', [(0, 0), (4, 1), (4, 4), (7, 2), (16, 1)])
+@pytest.mark.parametrize('cin,cout,dims', [(64, 64, (19, 37, 21)), (64, 32, (9, 16, 8)),
+                                           (128, 64, (33, 20, 30))])
+def test_windowed_k_outer_conv_vs_torch(cin, cout, dims, zc, tpi, monkeypatch):
+    """conv_tc_neck.cuh in plane-sweep-volume orientation ([D][H][W], D cut into windows whose
+    halo planes are real data), forced, against F.conv3d with TF32 off: ragged tile grids,
+    window lengths that do and do not divide D, several tiles per weight image."""
+    if zc:
+        monkeypatch.setenv('DFM_NECK_ZC', str(zc))
+        monkeypatch.setenv('DFM_NECK_ZTPI', str(tpi))
+    g = torch.Generator().manual_seed(cin * 1000 + cout + dims[0] + zc)
+    x = torch.randn((1, cin) + dims, generator=g).cuda()
+    w = torch.randn((cout, cin, 3, 3, 3), generator=g) * 0.05
+    ref = F.conv3d(x, w.cuda(), None, 1, 1)
+    _, tc0 = capi.launch_counters()
+    y = modules.conv3d(x, w, (1, 1, 1), (1, 1, 1), False, impl='tc_neck_dhw')
+    _, tc1 = capi.launch_counters()
+    assert tc1 == tc0 + 1
+    assert y.shape == ref.shape
+    e = rel_err(y, ref)
+    print('windowed K-outer kernel', cin, cout, dims, zc, tpi, e)
+    assert e < 1e-4
+    assert_close(y, ref, 'windowed conv')
+
+
 @pytest.mark.parametrize('impl', ['simt', 'auto'])
 @pytest.mark.parametrize('name', sorted(KITTI_CASES))
 def test_backbone_matches_reference_fixture(name, impl):
