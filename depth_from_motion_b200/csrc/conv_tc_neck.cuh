@@ -24,12 +24,26 @@ namespace dfm {
 constexpr int NK_BX = 8, NK_BY = 16;           // tile: 8 along y (brick x), 16 along x (brick y)
 constexpr int NK_PX = NK_BX + 2, NK_PY = NK_BY + 2;
 constexpr int NK_ROWS = 186;                    // 180 brick rows padded (== 2 mod 8)
-constexpr int NK_NSTAGE = 4;
-constexpr int NK_NCTA = 32;                     // output channels per CTA
-constexpr uint32_t NK_STAGE_BYTES = 2 * 4 * NK_ROWS * 16;
-constexpr uint32_t NK_TAP16 = 4 * 96;           // one in-plane tap of a group image, 16 B units
+// Two shapes of the per-CTA weight image (always 110.6 KB = 9 taps x CG x 3*NCTA x hi/lo):
+//   CG = 32 input channels per group, NCTA = 32 output channels per CTA (any plane count <= 16)
+//   CG = 16, NCTA = 64: every loaded brick feeds twice the MMA columns (N = 192 / 64 instead of
+//   96 / 32) and the output channels are split half as often, i.e. every brick is loaded half as
+//   often -- for layers with <= 8 output planes per tile (64 TMEM columns per plane).  The loaders
+//   bound these kernels, so this is what decides the small-Nz neck layers.
+template <int CG>
+struct NkCfg {
+  static constexpr int NCH = CG / 8;             // 16-byte channel chunks per stage
+  static constexpr int NCTA = 1024 / CG;         // output channels per CTA
+  static constexpr int KS = CG / 16;             // K steps per tap
+  static constexpr int NSTAGE = CG == 32 ? 4 : 8;
+  static constexpr uint32_t STAGE_BYTES = 2 * NCH * NK_ROWS * 16;
+  static constexpr uint32_t B_LBO16 = 3 * NCTA;  // rows of a group image: [kw block][NCTA]
+  static constexpr uint32_t TAP16 = NCH * B_LBO16;   // one in-plane tap, 16-byte units (= 384)
+};
+constexpr uint32_t NK_TAP16 = 4 * 96;           // == NkCfg<32>::TAP16 == NkCfg<16>::TAP16
 constexpr uint32_t NK_WHI_BYTES = 9 * NK_TAP16 * 16;
 constexpr uint32_t NK_W_BYTES = 2 * NK_WHI_BYTES;
+constexpr int NK_MAX_NCTA = 64;
 constexpr int NK_LOAD_THREADS = 320;   // 2 groups x 5 warps (15 warps: 128 registers/thread still fit)
 constexpr int NK_THREADS = 128 + NK_LOAD_THREADS + 32;
 
@@ -47,6 +61,7 @@ inline int nk_zmode(const ConvGeom& g) {
 struct NeckTcWeights {
   uint8_t* dev = nullptr;  // [nsplit][ncg][NK_W_BYTES]
   int Cin = 0, Cout = 0, zmode = -1;
+  int cg = 32;             // input channels per group (32 -> NCTA 32, 16 -> NCTA 64)
   bool ready() const { return dev != nullptr; }
   void release() {
     if (dev) cudaFree(dev);
@@ -57,31 +72,38 @@ struct NeckTcWeights {
   // i.e. kd over Nx, kh over Ny, kw over Nz (the short, marched axis).
   // dhw: the volume is [D][H][W][C] with D the marched axis (tile over H (16) x W (8)): the
   // in-plane tap t is kh * 3 + kw and the marched tap is kd
-  bool build(const float* packed, int cin, int cout, int zm, std::string* err, bool dhw = false) {
+  bool build(const float* packed, int cin, int cout, int zm, std::string* err, bool dhw = false,
+             int cgroup = 32) {
     release();
     Cin = cin;
     Cout = cout;
     zmode = zm;
-    const int nsplit = cout / 32, ncg = cin / 32;
+    cg = cgroup;
+    const int ncta = 1024 / cg, nch = cg / 8;
+    if ((cg != 32 && cg != 16) || cout % ncta || cin % cg) {
+      if (err) *err = "NeckTcWeights: channel counts do not fit the group shape";
+      return false;
+    }
+    const int nsplit = cout / ncta, ncg = cin / cg;
     // order of the three marched-axis taps inside an image (see kernel): consecutive row
     // blocks must land in consecutive output planes
     const int order[3][3] = {{2, 1, 0}, {2, 0, 1}, {0, 1, 2}};
     std::vector<uint16_t> img((size_t)nsplit * ncg * NK_W_BYTES / 2);
     for (int s = 0; s < nsplit; ++s)
-      for (int cg = 0; cg < ncg; ++cg)
+      for (int g = 0; g < ncg; ++g)
         for (int t = 0; t < 9; ++t) {      // in-plane tap: kd (Nx) * 3 + kh (Ny)
           const int kd = t / 3, kh = t % 3;
-          for (int kc = 0; kc < 4; ++kc)
-            for (int r = 0; r < 96; ++r)
+          for (int kc = 0; kc < nch; ++kc)
+            for (int r = 0; r < 3 * ncta; ++r)
               for (int e = 0; e < 8; ++e) {
-                const int kw = order[zm][r / 32];
-                const int co = s * 32 + r % 32, ci = cg * 32 + kc * 8 + e;
+                const int kw = order[zm][r / ncta];
+                const int co = s * ncta + r % ncta, ci = g * cg + kc * 8 + e;
                 const int tap = dhw ? kw * 9 + kd * 3 + kh : kd * 9 + kh * 3 + kw;
                 const float w = packed[((size_t)tap * cin + ci) * cout + co];
                 const uint16_t hi = bf16_rn_bits(w);
                 const uint16_t lo = bf16_rn_bits(w - bf16_bits_to_float(hi));
-                const size_t base = ((size_t)s * ncg + cg) * (NK_W_BYTES / 2);
-                const size_t off = base + (((size_t)t * 4 + kc) * 96 + r) * 8 + e;
+                const size_t base = ((size_t)s * ncg + g) * (NK_W_BYTES / 2);
+                const size_t off = base + (((size_t)t * nch + kc) * (3 * ncta) + r) * 8 + e;
                 img[off] = hi;
                 img[off + NK_WHI_BYTES / 2] = lo;
               }
@@ -165,11 +187,12 @@ struct NeckLoader {
 
 // which weight rows / output planes input plane iz feeds: rows [n0, n0+n) -> planes zo0...
 // (iz: absolute input plane; the item owns output planes [zo_lo, zo_hi); zo0 is relative to zo_lo)
+// n0 is in weight-row BLOCKS (multiply by NCTA)
 __device__ __forceinline__ void nk_plane_map(int zmode, int iz, int zo_lo, int zo_hi, int& n0,
                                              int& nblk, int& zo0) {
   if (zmode == NKZ_S1P1) {        // rows [kw=2|1|0] -> planes iz-1, iz, iz+1
     const int first = max(iz - 1, zo_lo), last = min(iz + 1, zo_hi - 1);
-    n0 = (first - (iz - 1)) * 32;
+    n0 = first - (iz - 1);
     nblk = last - first + 1;
     zo0 = first - zo_lo;
   } else if (zmode == NKZ_S2P1) { // rows [kw=2|0|1]; iz = 2q+1 -> planes q, q+1; iz = 2q -> q
@@ -179,12 +202,12 @@ __device__ __forceinline__ void nk_plane_map(int zmode, int iz, int zo_lo, int z
       nblk = q + 1 < zo_hi ? 2 : 1;
       zo0 = q;
     } else {
-      n0 = 64;
+      n0 = 2;
       nblk = 1;
       zo0 = q;
     }
   } else {                        // pad 0, single output plane: kw = iz
-    n0 = iz * 32;
+    n0 = iz;
     nblk = 1;
     zo0 = 0;
   }
@@ -212,15 +235,18 @@ __device__ __forceinline__ NkItem nk_item(const NeckParams& p, int item) {
   return it;
 }
 
-template <int NT>
+template <int NT, int CG>
 __global__ void __launch_bounds__(NK_THREADS, 1)
 neck_conv_kernel(const __grid_constant__ NeckParams p) {
-  constexpr uint32_t A_LBO = NK_ROWS * 16, A_SBO = NK_PX * 16, A_HL = 4 * NK_ROWS * 16;
-  constexpr uint32_t A_LBO16 = A_LBO >> 4, A_HL16 = A_HL >> 4, B_LBO16 = 96;
+  using Cfg = NkCfg<CG>;
+  constexpr int NCH = Cfg::NCH, NK_NCTA = Cfg::NCTA, KS = Cfg::KS, NK_NSTAGE = Cfg::NSTAGE;
+  constexpr uint32_t NK_STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr uint32_t A_LBO = NK_ROWS * 16, A_SBO = NK_PX * 16, A_HL = NCH * NK_ROWS * 16;
+  constexpr uint32_t A_LBO16 = A_LBO >> 4, A_HL16 = A_HL >> 4, B_LBO16 = Cfg::B_LBO16;
   constexpr uint32_t TMEM_COLS = 512;
   constexpr int NPOS = NK_PX * NK_PY, LG_THREADS = NK_LOAD_THREADS / 2;
-  constexpr int NITEM = (NPOS * 4 + LG_THREADS - 1) / LG_THREADS;
-  constexpr int LB = 6 / NT;
+  constexpr int NITEM = (NPOS * NCH + LG_THREADS - 1) / LG_THREADS;
+  constexpr int LB = NITEM < 6 / NT ? NITEM : 6 / NT;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* w_s = smem;
@@ -272,7 +298,7 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
     // ============================ loaders ============================
     const int lw = warp - 4, lgrp = lw & 1;
     const int lt = (lw >> 1) * 32 + lane, lall = lw * 32 + lane;
-    const int chunk = lt & 3;
+    const int chunk = lt % NCH;
     uint32_t stage_ctr = 0, w_ctr = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const NkItem it = nk_item(p, item);
@@ -298,7 +324,7 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
             const int s = stage_ctr % NK_NSTAGE;
             mbar_wait(empty_a(s), ((stage_ctr / NK_NSTAGE) & 1) ^ 1, p.err);
             uint8_t* st = a_s + s * NK_STAGE_BYTES;
-            const int c0 = cg * 32 + chunk * 8;
+            const int c0 = cg * CG + chunk * 8;
 #pragma unroll
             for (int k0 = 0; k0 < NITEM; k0 += LB) {
               typename NeckLoader<NT>::Raw raw[LB];
@@ -307,8 +333,8 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
 #pragma unroll
               for (int b = 0; b < LB; ++b) {
                 const int i = lt + (k0 + b) * LG_THREADS;
-                live[b] = (k0 + b) < NITEM && i < NPOS * 4;
-                const int pos = i >> 2;
+                live[b] = (k0 + b) < NITEM && i < NPOS * NCH;
+                const int pos = i / NCH;
                 const int bx = pos % NK_PX, by = pos / NK_PX;
                 const int gy = y0 - 1 + bx, gx = x0 - 1 + by;
                 inb[b] = live[b] && gx >= 0 && gx < p.Nx && gy >= 0 && gy < p.Ny;
@@ -363,10 +389,10 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
             const uint32_t d0 = tmem_u + (uint32_t)(t * p.ZC + zo0) * NK_NCTA;
             const uint32_t idesc = idesc_bf16(nblk * NK_NCTA);
             const uint32_t a_lo_stage = (((a_base + s * NK_STAGE_BYTES) >> 4) & 0x3FFF) | (A_LBO16 << 16);
-            const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFF) + (uint32_t)n0 + (B_LBO16 << 16);
-            uint64_t da[2][2], db[2][2];
+            const uint32_t b_lo0 = ((w_base >> 4) & 0x3FFF) + (uint32_t)n0 * NK_NCTA + (B_LBO16 << 16);
+            uint64_t da[KS][2], db[KS][2];
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
+            for (int ks = 0; ks < KS; ++ks) {
               da[ks][0] = pack64(a_lo_stage + 2 * ks * A_LBO16, a_desc_hi);
               da[ks][1] = pack64(a_lo_stage + 2 * ks * A_LBO16 + A_HL16, a_desc_hi);
               db[ks][0] = pack64(b_lo0 + 2 * ks * B_LBO16, b_desc_hi);
@@ -376,7 +402,7 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
             for (int tap = 0; tap < 9; ++tap) {
               if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
+                for (int ks = 0; ks < KS; ++ks) {
                   umma_bf16(d0, da[ks][0], db[ks][0], idesc, 1u);
                   umma_bf16(d0, da[ks][1], db[ks][0], idesc, 1u);
                   umma_bf16(d0, da[ks][0], db[ks][1], idesc, 1u);
@@ -384,7 +410,7 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
               }
               const uint32_t ainc = (tap == 2 || tap == 5) ? (uint32_t)(NK_PX - 2) : 1u;
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
+              for (int ks = 0; ks < KS; ++ks) {
                 desc_add(da[ks][0], ainc);
                 desc_add(da[ks][1], ainc);
                 desc_add(db[ks][0], NK_TAP16);
@@ -405,40 +431,61 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
     // ============================ epilogue (warps 0-3) ============================
     const int m = warp * 32 + lane;
     uint32_t item_ctr = 0;
-    float ssum[NK_NCTA], ssq[NK_NCTA];   // GroupNorm sums of this item (p.stats), fp32 per thread
+    constexpr int EW = 32, NSUB = NK_NCTA / EW;   // accumulator columns drained per pass
+    float ssum[EW], ssq[EW];   // GroupNorm sums of this item and column block (p.stats), fp32
 #pragma unroll
-    for (int i = 0; i < NK_NCTA; ++i) ssum[i] = ssq[i] = 0.f;
+    for (int i = 0; i < EW; ++i) ssum[i] = ssq[i] = 0.f;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_ctr) {
       const NkItem it = nk_item(p, item);
       mbar_wait(acc_full, item_ctr & 1, p.err);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int t = 0; t < it.nt; ++t) {
-        const int tile = it.tile0 + t;
-        const int y = (tile % p.tiles_x) * NK_BX + (m & 7), x = (tile / p.tiles_x) * NK_BY + (m >> 3);
-        const bool ok = x < p.Nx && y < p.Ny;
-        for (int zo = it.zo_lo; zo < it.zo_hi; ++zo) {
-          uint32_t r[NK_NCTA];
-          const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
-                              (uint32_t)(t * p.ZC + zo - it.zo_lo) * NK_NCTA;
-          tmem_ld<NK_NCTA>(ta, r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          tmem_zero<NK_NCTA>(ta);
-          if (ok) {
-            float4* dst = reinterpret_cast<float4*>(
-                p.out + (x * p.out_sx + y * p.out_sy + zo * p.out_sz) * p.Cout + split * NK_NCTA);
+#pragma unroll 1
+      for (int sub = 0; sub < NSUB; ++sub) {
+        for (int t = 0; t < it.nt; ++t) {
+          const int tile = it.tile0 + t;
+          const int y = (tile % p.tiles_x) * NK_BX + (m & 7), x = (tile / p.tiles_x) * NK_BY + (m >> 3);
+          const bool ok = x < p.Nx && y < p.Ny;
+          for (int zo = it.zo_lo; zo < it.zo_hi; ++zo) {
+            uint32_t r[EW];
+            const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) +
+                                (uint32_t)(t * p.ZC + zo - it.zo_lo) * NK_NCTA + sub * EW;
+            tmem_ld<EW>(ta, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_zero<EW>(ta);
+            if (ok) {
+              float4* dst = reinterpret_cast<float4*>(
+                  p.out + (x * p.out_sx + y * p.out_sy + zo * p.out_sz) * p.Cout +
+                  split * NK_NCTA + sub * EW);
 #pragma unroll
-            for (int q = 0; q < NK_NCTA / 4; ++q)
-              dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-            if (p.stats) {
-              const float wz = (zo >= p.zw_lo && zo < p.zw_hi) ? p.zw : 1.f;
+              for (int q = 0; q < EW / 4; ++q)
+                dst[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+              if (p.stats) {
+                const float wz = (zo >= p.zw_lo && zo < p.zw_hi) ? p.zw : 1.f;
 #pragma unroll
-              for (int i = 0; i < NK_NCTA; ++i) {
-                const float v = __uint_as_float(r[i]);
-                ssum[i] = fmaf(wz, v, ssum[i]);
-                ssq[i] = fmaf(wz * v, v, ssq[i]);
+                for (int i = 0; i < EW; ++i) {
+                  const float v = __uint_as_float(r[i]);
+                  ssum[i] = fmaf(wz, v, ssum[i]);
+                  ssq[i] = fmaf(wz * v, v, ssq[i]);
+                }
               }
             }
+          }
+        }
+        if (p.stats) {  // one flush per item and column block keeps the fp32 partial sums short
+#pragma unroll
+          for (int i = 0; i < EW; ++i) {
+            double a = ssum[i], b = ssq[i];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+              a += __shfl_xor_sync(0xffffffffu, a, o);
+              b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (lane == 0) {
+              atomicAdd(p.stats + 2 * (split * NK_NCTA + sub * EW + i), a);
+              atomicAdd(p.stats + 2 * (split * NK_NCTA + sub * EW + i) + 1, b);
+            }
+            ssum[i] = ssq[i] = 0.f;
           }
         }
       }
@@ -446,22 +493,6 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
-      if (p.stats) {  // one flush per item keeps the fp32 partial sums short (<= 16 values)
-#pragma unroll
-        for (int i = 0; i < NK_NCTA; ++i) {
-          double a = ssum[i], b = ssq[i];
-#pragma unroll
-          for (int o = 16; o; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-          }
-          if (lane == 0) {
-            atomicAdd(p.stats + 2 * (split * NK_NCTA + i), a);
-            atomicAdd(p.stats + 2 * (split * NK_NCTA + i) + 1, b);
-          }
-          ssum[i] = ssq[i] = 0.f;
-        }
-      }
     }
   }
 
@@ -472,15 +503,18 @@ neck_conv_kernel(const __grid_constant__ NeckParams p) {
                  "r"(TMEM_COLS));
 }
 
-inline bool neck_launch(NeckParams& p, int nterms, cudaStream_t st, std::string* err) {
-  const size_t smem = NK_W_BYTES + (size_t)NK_NSTAGE * NK_STAGE_BYTES + (2 * NK_NSTAGE + 4) * 8 + 16;
+inline bool neck_launch(NeckParams& p, int nterms, int cg, cudaStream_t st, std::string* err) {
+  const size_t stages = cg == 32 ? (size_t)NkCfg<32>::NSTAGE * NkCfg<32>::STAGE_BYTES
+                                 : (size_t)NkCfg<16>::NSTAGE * NkCfg<16>::STAGE_BYTES;
+  const int nstage = cg == 32 ? NkCfg<32>::NSTAGE : NkCfg<16>::NSTAGE;
+  const size_t smem = NK_W_BYTES + stages + (2 * nstage + 4) * 8 + 16;
   p.err = tc_err_flag().get();
   const int sms = tc_sm_count();
   int grid = std::max(p.nsplit, sms / p.nsplit * p.nsplit);
   grid = std::min(grid, p.n_items);
   grid = std::max(p.nsplit, grid / p.nsplit * p.nsplit);
   auto launch = [&](auto kern) -> bool {
-    // (both instantiations share one function-pointer type, so no static "done" flag here)
+    // (the instantiations share one function-pointer type, so no static "done" flag here)
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
         cudaSuccess) {
       if (err) *err = "neck_tc_conv: cannot reserve shared memory";
@@ -494,10 +528,18 @@ inline bool neck_launch(NeckParams& p, int nterms, cudaStream_t st, std::string*
     }
     return true;
   };
-  if (nterms == 1) return launch(neck_conv_kernel<1>);
-  if (nterms == 2) return launch(neck_conv_kernel<2>);
+  if (cg == 32 && nterms == 1) return launch(neck_conv_kernel<1, 32>);
+  if (cg == 32 && nterms == 2) return launch(neck_conv_kernel<2, 32>);
+  if (cg == 16 && nterms == 1) return launch(neck_conv_kernel<1, 16>);
+  if (cg == 16 && nterms == 2) return launch(neck_conv_kernel<2, 16>);
   if (err) *err = "neck_tc_conv: at most two input terms";
   return false;
+}
+
+// group shape of a layer with `planes` output planes per tile: 16 / 64 when the accumulators fit
+inline int neck_group_for(int cin, int cout, int planes) {
+  static const bool off = getenv("DFM_NECK_CG32") != nullptr;   // A/B runs
+  return (!off && planes * 64 <= 512 && cout % 64 == 0 && cin % 16 == 0) ? 16 : 32;
 }
 
 // BEV-neck orientation: volume [Nx][Ny][Nz][C], the short Nz axis is marched whole
@@ -512,8 +554,13 @@ inline bool neck_tc_conv(const Src& s, const NeckTcWeights& w, float* out, const
   p.zmode = w.zmode;
   p.tiles_x = (g.Hi + NK_BX - 1) / NK_BX;   // along Ny
   p.tiles_y = (g.Di + NK_BY - 1) / NK_BY;   // along Nx
-  p.nsplit = g.Cout / 32;
-  p.ncg = g.Cin / 32;
+  const int ncta = 1024 / w.cg;
+  if (g.Wo * ncta > 512) {
+    if (err) *err = "neck_tc_conv: the weight image's group shape does not fit this plane count";
+    return false;
+  }
+  p.nsplit = g.Cout / ncta;
+  p.ncg = g.Cin / w.cg;
   p.ntiles = p.tiles_x * p.tiles_y;
   p.in_sx = (long long)g.Hi * g.Wi; p.in_sy = g.Wi; p.in_sz = 1;
   p.out_sx = (long long)g.Ho * g.Wo; p.out_sy = g.Wo; p.out_sz = 1;
@@ -524,14 +571,14 @@ inline bool neck_tc_conv(const Src& s, const NeckTcWeights& w, float* out, const
   // many that the persistent grid runs short of items
   const int tpi_env = getenv("DFM_NECK_TPI") ? atoi(getenv("DFM_NECK_TPI")) : 0;  // tests / A-B runs
   {
-    const int cap = std::max(1, 512 / (g.Wo * NK_NCTA));
+    const int cap = std::max(1, 512 / (g.Wo * ncta));
     const int sms0 = tc_sm_count();
     int tpi = std::min(cap, std::max(1, p.ntiles * p.nsplit / (2 * sms0)));
     if (tpi_env > 0) tpi = std::min(cap, tpi_env);
     p.tpi = std::max(1, tpi);
   }
   p.n_items = (p.ntiles + p.tpi - 1) / p.tpi * p.nsplit;
-  return neck_launch(p, s.n, st, err);
+  return neck_launch(p, s.n, w.cg, st, err);
 }
 
 // Plane-sweep-volume orientation: [D][H][W][C], stride 1, pad 1; tiles over (H: 16, W: 8), the
@@ -548,15 +595,16 @@ inline bool neck_dhw_supported(const ConvGeom& g) {
 struct NeckDhwPlan {
   int zc, tpi, items;
 };
-inline NeckDhwPlan neck_dhw_plan(const ConvGeom& g) {
+inline NeckDhwPlan neck_dhw_plan(const ConvGeom& g, int ncta = 32) {
   const int sms = tc_sm_count();
   const int ntiles = ((g.Wi + NK_BX - 1) / NK_BX) * ((g.Hi + NK_BY - 1) / NK_BY);
-  const int nsplit = g.Cout / 32;
-  NeckDhwPlan best{std::min(g.Do, 16), 1, 0};
+  const int nsplit = g.Cout / ncta;
+  const int zmax = std::min(g.Do, 512 / ncta);
+  NeckDhwPlan best{zmax, 1, 0};
   double best_cost = 1e30;
-  for (int zc = std::min(g.Do, 16); zc >= std::min(g.Do, 4); --zc) {
+  for (int zc = zmax; zc >= std::min(g.Do, 4); --zc) {
     const int nchunk = (g.Do + zc - 1) / zc;
-    for (int tpi = 1; tpi <= 512 / (zc * NK_NCTA); ++tpi) {
+    for (int tpi = 1; tpi <= 512 / (zc * ncta); ++tpi) {
       const int items = (ntiles + tpi - 1) / tpi * nchunk * nsplit;
       const int rounds = (items + sms - 1) / sms;
       const double cost = rounds * (tpi * (zc + 2.0) + 1.5);
@@ -570,8 +618,8 @@ inline NeckDhwPlan neck_dhw_plan(const ConvGeom& g) {
 }
 // worth it only when the items fill the machine (the resident-weight kernel cuts its work
 // stream-K style and keeps every SM busy on small volumes)
-inline bool neck_dhw_profitable(const ConvGeom& g) {
-  return neck_dhw_supported(g) && neck_dhw_plan(g).items >= tc_sm_count();
+inline bool neck_dhw_profitable(const ConvGeom& g, int ncta = 32) {
+  return neck_dhw_supported(g) && neck_dhw_plan(g, ncta).items >= tc_sm_count();
 }
 inline bool neck_tc_conv_dhw(const Src& s, const NeckTcWeights& w, float* out, const ConvGeom& g,
                              double* stats, int zw_lo, int zw_hi, float zw, cudaStream_t st,
@@ -585,23 +633,24 @@ inline bool neck_tc_conv_dhw(const Src& s, const NeckTcWeights& w, float* out, c
   p.zmode = NKZ_S1P1;
   p.tiles_x = (g.Wi + NK_BX - 1) / NK_BX;   // along W
   p.tiles_y = (g.Hi + NK_BY - 1) / NK_BY;   // along H
-  p.nsplit = g.Cout / 32;
-  p.ncg = g.Cin / 32;
+  const int ncta = 1024 / w.cg;
+  p.nsplit = g.Cout / ncta;
+  p.ncg = g.Cin / w.cg;
   p.ntiles = p.tiles_x * p.tiles_y;
   p.in_sx = g.Wi; p.in_sy = 1; p.in_sz = (long long)g.Hi * g.Wi;
   p.out_sx = g.Wo; p.out_sy = 1; p.out_sz = (long long)g.Ho * g.Wo;
-  const NeckDhwPlan plan = neck_dhw_plan(g);
+  const NeckDhwPlan plan = neck_dhw_plan(g, ncta);
   // tests / A-B runs (read per call, like DFM_NECK_TPI)
   const int zc_env = getenv("DFM_NECK_ZC") ? atoi(getenv("DFM_NECK_ZC")) : 0;
   const int tpi_env = getenv("DFM_NECK_ZTPI") ? atoi(getenv("DFM_NECK_ZTPI")) : 0;
-  p.ZC = std::min(zc_env > 0 ? std::min(zc_env, 16) : plan.zc, g.Do);
+  p.ZC = std::min(zc_env > 0 ? std::min(zc_env, 512 / ncta) : plan.zc, g.Do);
   p.nchunk = (g.Do + p.ZC - 1) / p.ZC;
   // (the window logic of nk_item serves nchunk == 1 too: iz_lo = 0, nzi = Zi)
-  p.tpi = std::max(1, std::min(512 / (p.ZC * NK_NCTA), tpi_env > 0 ? tpi_env : plan.tpi));
+  p.tpi = std::max(1, std::min(512 / (p.ZC * ncta), tpi_env > 0 ? tpi_env : plan.tpi));
   p.n_items = (p.ntiles + p.tpi - 1) / p.tpi * p.nchunk * p.nsplit;
   p.stats = stats;
   p.zw_lo = zw_lo; p.zw_hi = zw_hi; p.zw = zw;
-  return neck_launch(p, s.n, st, err);
+  return neck_launch(p, s.n, w.cg, st, err);
 }
 
 }  // namespace dfm

@@ -193,7 +193,9 @@ int set_conv(ConvW& cw, const float* h, long long numel, int Cin, int Cout, int 
   cw.ntk.release();
   if (tc_mode == dfm::TC_S1 && !transposed && Cin >= 64 && Cin % 32 == 0 && Cout % 32 == 0) {
     std::string err;
-    if (!cw.ntk.build(p.data(), Cin, Cout, dfm::NKZ_S1P1, &err, /*dhw=*/true))
+    // (32-channel groups: on these volumes the 16 / 64 shape measured no better -- 0.283 vs
+    // 0.280 ms at 56x48x156, 0.147 vs 0.122 ms at 20x48x156 -- fewer, larger items balance worse)
+    if (!cw.ntk.build(p.data(), Cin, Cout, dfm::NKZ_S1P1, &err, /*dhw=*/true, 32))
       return fail(DFM_ERR_CUDA, err);
   }
   return DFM_OK;
@@ -349,7 +351,8 @@ int run_conv(const dfm::Src& s, const ConvW& w, float* out, const dfm::ConvGeom&
     return fail(DFM_ERR_INVALID, "z-shortened volumes exist only on the tensor-core path");
   // stride-1 layers with >= 64 input channels: K-outer kernel (conv_tc_neck.cuh, windowed along D)
   static const bool no_ntk = getenv("DFM_NO_NTK") != nullptr;
-  if (impl != DFM_CONV_SIMT && !no_ntk && w.ntk.ready() && dfm::neck_dhw_profitable(g) &&
+  if (impl != DFM_CONV_SIMT && !no_ntk && w.ntk.ready() &&
+      dfm::neck_dhw_profitable(g, 1024 / w.ntk.cg) &&
       s.n <= 2 && s.t[0].zcls == 0 && (s.n < 2 || s.t[1].zcls == 0)) {
     const long long V = (long long)(zw.count_planes ? zw.count_planes : g.Do) * g.Ho * g.Wo;
     if (gn) DFM_TRY(gn->begin_stats(st));
@@ -1485,7 +1488,9 @@ int dfm_op_conv3d(const float* d_x, int Cin, int Di, int Hi, int Wi, const float
     } else {
       const std::vector<float> packed = repack_simt(h_w, Cin, Cout, 0);
       std::string err;
-      if (!w.ntk.build(packed.data(), Cin, Cout, dfm::NKZ_S1P1, &err, true) ||
+      // DFM_NTK_CG16=1: exercise the 16-channel-group / 64-output shape in this orientation too
+      if (!w.ntk.build(packed.data(), Cin, Cout, dfm::NKZ_S1P1, &err, true,
+                       getenv("DFM_NTK_CG16") ? dfm::neck_group_for(Cin, Cout, 8) : 32) ||
           !dfm::neck_tc_conv_dhw(src1(term(xin, nullptr, 0)), w.ntk, yout.p, g, nullptr, 0, 0, 1.f,
                                  st, &err))
         rc = fail(DFM_ERR_CUDA, err);
@@ -1495,7 +1500,8 @@ int dfm_op_conv3d(const float* d_x, int Cin, int Di, int Hi, int Wi, const float
   } else if (rc == DFM_OK && want_neck) {
     const std::vector<float> packed = repack_simt(h_w, Cin, Cout, 0);
     std::string err;
-    if (!w.ntc.build(packed.data(), Cin, Cout, zm, &err) ||
+    if (!w.ntc.build(packed.data(), Cin, Cout, zm, &err, false,
+                     dfm::neck_group_for(Cin, Cout, g.Wo)) ||
         !dfm::neck_tc_conv(src1(term(xin, nullptr, 0)), w.ntc, yout.p, g, st, &err))
       rc = fail(DFM_ERR_CUDA, err);
     g_launches.fetch_add(1);

@@ -127,16 +127,21 @@ def test_neck_conv_kernel_vs_torch(case):
     assert e < 1e-4
 
 
+@pytest.mark.parametrize('cg16', [False, True])
 @pytest.mark.parametrize('zc,tpi', [(0, 0), (4, 1), (4, 4), (7, 2), (16, 1)])
 @pytest.mark.parametrize('cin,cout,dims', [(64, 64, (19, 37, 21)), (64, 32, (9, 16, 8)),
                                            (128, 64, (33, 20, 30))])
-def test_windowed_k_outer_conv_vs_torch(cin, cout, dims, zc, tpi, monkeypatch):
+def test_windowed_k_outer_conv_vs_torch(cin, cout, dims, zc, tpi, cg16, monkeypatch):
     """conv_tc_neck.cuh in plane-sweep-volume orientation ([D][H][W], D cut into windows whose
     halo planes are real data), forced, against F.conv3d with TF32 off: ragged tile grids,
     window lengths that do and do not divide D, several tiles per weight image."""
     if zc:
         monkeypatch.setenv('DFM_NECK_ZC', str(zc))
         monkeypatch.setenv('DFM_NECK_ZTPI', str(tpi))
+    if cg16:    # weight images of 16 input x 64 output channels (N = 192 MMAs) where they fit
+        if cout % 64:
+            pytest.skip('the 16 / 64 group shape needs a multiple of 64 output channels')
+        monkeypatch.setenv('DFM_NTK_CG16', '1')
     g = torch.Generator().manual_seed(cin * 1000 + cout + dims[0] + zc)
     x = torch.randn((1, cin) + dims, generator=g).cuda()
     w = torch.randn((cout, cin, 3, 3, 3), generator=g) * 0.05
