@@ -537,9 +537,13 @@ inline bool neck_launch(NeckParams& p, int nterms, int cg, cudaStream_t st, std:
 }
 
 // group shape of a layer with `planes` output planes per tile: 16 / 64 when the accumulators fit
-inline int neck_group_for(int cin, int cout, int planes) {
+// (windowed = true: the layer is stride 1 / pad 1 along the short axis, so a taller volume can be
+// cut into windows that fit -- DFM_NECK_WIN=1, A/B)
+inline int neck_group_for(int cin, int cout, int planes, bool windowed = false) {
   static const bool off = getenv("DFM_NECK_CG32") != nullptr;   // A/B runs
-  return (!off && planes * 64 <= 512 && cout % 64 == 0 && cin % 16 == 0) ? 16 : 32;
+  static const bool win = getenv("DFM_NECK_WIN") != nullptr;
+  const bool fits = planes * 64 <= 512 || (windowed && win);
+  return (!off && fits && cout % 64 == 0 && cin % 16 == 0) ? 16 : 32;
 }
 
 // BEV-neck orientation: volume [Nx][Ny][Nz][C], the short Nz axis is marched whole
@@ -555,29 +559,37 @@ inline bool neck_tc_conv(const Src& s, const NeckTcWeights& w, float* out, const
   p.tiles_x = (g.Hi + NK_BX - 1) / NK_BX;   // along Ny
   p.tiles_y = (g.Di + NK_BY - 1) / NK_BY;   // along Nx
   const int ncta = 1024 / w.cg;
+  // more planes than the accumulators hold in this group shape: windows along the short axis
+  // (stride 1, pad 1 only; their halo planes are real data)
+  int zc = g.Wo, nchunk = 1;
   if (g.Wo * ncta > 512) {
-    if (err) *err = "neck_tc_conv: the weight image's group shape does not fit this plane count";
-    return false;
+    if (w.zmode != NKZ_S1P1) {
+      if (err) *err = "neck_tc_conv: the weight image's group shape does not fit this plane count";
+      return false;
+    }
+    nchunk = (g.Wo * ncta + 511) / 512;
+    zc = (g.Wo + nchunk - 1) / nchunk;
+    nchunk = (g.Wo + zc - 1) / zc;
   }
   p.nsplit = g.Cout / ncta;
   p.ncg = g.Cin / w.cg;
   p.ntiles = p.tiles_x * p.tiles_y;
   p.in_sx = (long long)g.Hi * g.Wi; p.in_sy = g.Wi; p.in_sz = 1;
   p.out_sx = (long long)g.Ho * g.Wo; p.out_sy = g.Wo; p.out_sz = 1;
-  p.ZC = g.Wo;
-  p.nchunk = 1;
+  p.ZC = zc;
+  p.nchunk = nchunk;
   p.stats = nullptr;
   // tiles per item: as many as the 512 TMEM columns hold (Zo * 32 columns per tile), but not so
   // many that the persistent grid runs short of items
   const int tpi_env = getenv("DFM_NECK_TPI") ? atoi(getenv("DFM_NECK_TPI")) : 0;  // tests / A-B runs
   {
-    const int cap = std::max(1, 512 / (g.Wo * ncta));
+    const int cap = std::max(1, 512 / (zc * ncta));
     const int sms0 = tc_sm_count();
-    int tpi = std::min(cap, std::max(1, p.ntiles * p.nsplit / (2 * sms0)));
+    int tpi = std::min(cap, std::max(1, p.ntiles * nchunk * p.nsplit / (2 * sms0)));
     if (tpi_env > 0) tpi = std::min(cap, tpi_env);
     p.tpi = std::max(1, tpi);
   }
-  p.n_items = (p.ntiles + p.tpi - 1) / p.tpi * p.nsplit;
+  p.n_items = (p.ntiles + p.tpi - 1) / p.tpi * nchunk * p.nsplit;
   return neck_launch(p, s.n, w.cg, st, err);
 }
 
