@@ -777,14 +777,15 @@ int tower_forward(dfm_backbone* bb, Tower& t, bool mono, const dfm::WarpLoader& 
     g = geom_s(5, Ho, Wo, C, cv, 1, 1, 1, 1, 1, 1);
     DFM_TRY(run_conv_warp(wc, wcur, t.cls5.p, g, impl, st));
     const long long pe = (long long)Ho * Wo * cv;
-    dfm::pick_planes_kernel<<<(unsigned)((3 * pe + 255) / 256), 256, 0, st>>>(t.cls5.p, t.cls3.p, pe);
+    dfm::pick_planes_kernel<<<dim3((unsigned)((pe / 4 + 255) / 256), 3), 256, 0, st>>>(
+        t.cls5.p, t.cls3.p, pe);   // pe = Ho * Wo * 32: a multiple of 4
     LAUNCH_CHECK();
     if (mono) {
       // dres0_mono's whole output is z-class compressed; its GroupNorm statistics weigh the
       // three planes 1 : Dfull-2 : 1
       DFM_TRY(t.g0.begin_stats(st));
-      dfm::channel_stats_zcls_kernel<32><<<148, 256, 0, st>>>(t.cls3.p, (long long)Ho * Wo, Dfull,
-                                                             t.g0.sums);
+      dfm::channel_stats_zcls_kernel<32><<<dim3(296, 3), 256, 0, st>>>(t.cls3.p, Ho * Wo, Dfull,
+                                                                    t.g0.sums);
       LAUNCH_CHECK();
       DFM_TRY(gn_finalize(t.g0, (long long)Dfull * Ho * Wo, 32, st));
       T0 = term(t.cls3, &t.g0, 1, D);  // first / interior / last plane of the computed volume

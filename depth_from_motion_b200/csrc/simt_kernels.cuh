@@ -253,40 +253,47 @@ channel_stats_kernel(const float* __restrict__ x, long long V, double* __restric
 
 // Statistics of a z-class-compressed tensor [3][HW][C] that stands for D planes
 // (plane 0 once, plane 1 D-2 times, plane 2 once).
+// grid (blocks per plane, 3): blockIdx.y is the class plane, so the weight is a per-block
+// constant; fp32 partial sums per thread are short (<= HW / (gridDim.x * ROWS) values), fp64
+// across threads.
 template <int C>
 __global__ void __launch_bounds__(256)
-channel_stats_zcls_kernel(const float* __restrict__ x, long long HW, int D,
+channel_stats_zcls_kernel(const float* __restrict__ x, int HW, int D,
                           double* __restrict__ sums) {
   constexpr int ROWS = 256 / C;
   __shared__ double sh[2][256];
   const int c = threadIdx.x % C, r = threadIdx.x / C;
-  double s = 0.0, ss = 0.0;
-  for (long long v = (long long)blockIdx.x * ROWS + r; v < 3 * HW; v += (long long)gridDim.x * ROWS) {
-    const double wgt = (v / HW) == 1 ? (double)(D - 2) : 1.0;
-    const float a = x[v * C + c];
-    s += wgt * a;
-    ss += wgt * (double)a * a;
+  const float* xp = x + (long long)blockIdx.y * HW * C;
+  float s = 0.f, ss = 0.f;
+  for (int v = blockIdx.x * ROWS + r; v < HW; v += gridDim.x * ROWS) {
+    const float a = xp[(long long)v * C + c];
+    s += a;
+    ss = fmaf(a, a, ss);
   }
-  sh[0][threadIdx.x] = s;
-  sh[1][threadIdx.x] = ss;
+  const double wgt = blockIdx.y == 1 ? (double)(D - 2) : 1.0;
+  sh[0][threadIdx.x] = wgt * s;
+  sh[1][threadIdx.x] = wgt * ss;
   __syncthreads();
   if (r == 0) {
+    double ds = sh[0][c], dss = sh[1][c];
     for (int k = 1; k < ROWS; ++k) {
-      s += sh[0][k * C + c];
-      ss += sh[1][k * C + c];
+      ds += sh[0][k * C + c];
+      dss += sh[1][k * C + c];
     }
-    atomicAdd(sums + 2 * c, s);
-    atomicAdd(sums + 2 * c + 1, ss);
+    atomicAdd(sums + 2 * c, ds);
+    atomicAdd(sums + 2 * c + 1, dss);
   }
 }
 
-// planes 0, 2, 4 of a 5-plane conv output -> the 3-plane class tensor
+// planes 0, 2, 4 of a 5-plane conv output -> the 3-plane class tensor (grid.y = class plane,
+// 16-byte copies; plane_elems % 4 == 0)
 __global__ void pick_planes_kernel(const float* __restrict__ in, float* __restrict__ out,
                                    long long plane_elems) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 3 * plane_elems) return;
-  const long long pl = i / plane_elems, r = i % plane_elems;
-  out[i] = in[(2 * pl) * plane_elems + r];
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= plane_elems) return;
+  const long long pl = blockIdx.y;
+  *reinterpret_cast<float4*>(out + pl * plane_elems + i) =
+      __ldg(reinterpret_cast<const float4*>(in + 2 * pl * plane_elems + i));
 }
 
 // scale/shift of GroupNorm(groups, C) from per-channel sums over `count` voxels:
