@@ -48,7 +48,8 @@ IO_BYTES_PER_FRAME = 2 * 32 * H * W * 4 + 5.25e6 + 33 * V * 4
 KITTI_WORKLOAD = 'dfm_r34_1x8_kitti-3d-3class D=112 384x1248 batch=1'
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the
 # committed `ncu --set full` capture (profiles/): kitti: conv_tc 32->32 full resolution
-NCU_TRAFFIC = {'kitti': (974.2e6, 'profiles/r02_ncu_conv_tc.csv (587.1 MB read + 387.0 MB written)')}
+NCU_TRAFFIC = {'kitti': (973.0e6, 'profiles/r02_ncu_conv_tc_dominant_final.csv '
+                                  '(587.1 MB read + 386.0 MB written per launch)')}
 WAYMO = {
     'waymo_mv': dict(T=1, agg='mean', neck='OutdoorImVoxelNeck', flops=3.212e12,
                      name='multiview-dfm_r101_dcn_2x16_waymoD5 (5 views, 832x1248 input) '
